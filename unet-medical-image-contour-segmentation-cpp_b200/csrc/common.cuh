@@ -1,0 +1,142 @@
+// common.cuh -- shared declarations for libmedseg_b200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <algorithm>
+#include <cstdint>
+#include <cstdio>
+#include <string>
+#include <vector>
+
+#include "../../include/medseg_b200.h"
+
+#if defined(__CUDA_ARCH__) && !defined(__CUDA_ARCH_FEAT_SM100_ALL)
+#error "libmedseg_b200 device code is written for sm_100a only (compile with -gencode arch=compute_100a,code=sm_100a)"
+#endif
+
+namespace ms {
+
+struct Error {
+    int code;
+    std::string what;
+};
+
+// Thrown inside the library, caught at every C-ABI entry point (never crosses the boundary).
+[[noreturn]] void fail(int code, const std::string& what);
+
+#define MS_CUDA(expr)                                                                               \
+    do {                                                                                            \
+        cudaError_t _e = (expr);                                                                    \
+        if (_e != cudaSuccess)                                                                      \
+            ::ms::fail(MS_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e) + " (" +    \
+                                        __FILE__ + ":" + std::to_string(__LINE__) + ")");          \
+    } while (0)
+
+#define MS_REQUIRE(cond, code, msg)                                                                 \
+    do {                                                                                            \
+        if (!(cond)) ::ms::fail((code), std::string(msg));                                          \
+    } while (0)
+
+// Launch bookkeeping: every kernel launch goes through LAUNCH so ms_launch_count is honest.
+struct LaunchCounter {
+    int64_t n = 0;
+};
+extern thread_local LaunchCounter* g_counter;
+
+#define MS_LAUNCH_CHECK()                                                                           \
+    do {                                                                                            \
+        if (::ms::g_counter) ::ms::g_counter->n++;                                                  \
+        MS_CUDA(cudaGetLastError());                                                                \
+    } while (0)
+
+static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
+static inline int64_t cdiv64(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+// Simple growable device buffer (never shrinks; growth is outside any timed / captured region).
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    void reserve(size_t bytes) {
+        if (bytes <= cap) return;
+        if (p) MS_CUDA(cudaFree(p));
+        p = nullptr;
+        cap = 0;
+        MS_CUDA(cudaMalloc(&p, bytes));
+        cap = bytes;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+    template <class T>
+    T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+struct PinBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    void reserve(size_t bytes) {
+        if (bytes <= cap) return;
+        if (p) MS_CUDA(cudaFreeHost(p));
+        p = nullptr;
+        cap = 0;
+        MS_CUDA(cudaMallocHost(&p, bytes));
+        cap = bytes;
+    }
+    void release() {
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        cap = 0;
+    }
+    template <class T>
+    T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+// ---------------------------------------------------------------- stage launchers (device ptrs)
+
+// K1 preprocess.cu
+struct PreprocessWs {
+    DevBuf minmax;  // batch x 2 u32
+};
+void preprocess_launch(PreprocessWs& ws, const uint16_t* d_src, int w, int h, int batch, int out_w, int out_h,
+                       uint8_t* d_out_u8, __nv_bfloat16* d_out_bf16, cudaStream_t st);
+
+// ccl.cu -- union-find labelling shared by K5 and K6
+struct CclWs {
+    DevBuf labels;  // int32 per pixel
+    DevBuf area;    // int32 per pixel (valid at roots)
+    DevBuf flag;    // u8 per pixel (valid at roots): component touches the image border
+};
+
+// K5 postprocess.cu
+struct PostprocessWs {
+    CclWs ccl;
+    DevBuf bin_a, bin_b;  // u8 per pixel
+};
+void postprocess_launch(PostprocessWs& ws, const uint8_t* d_in, uint8_t* d_out, int h, int w, int batch, int fg_value,
+                        float min_area_ratio, cudaStream_t st);
+
+// K6 mask2polygon.cu
+struct PolyDev {              // device-resident polygon set + counters
+    DevBuf starts;            // int32 [cap_contours]  start pixel (slice-local linear index)
+    DevBuf start_slice;       // int32 [cap_contours]
+    DevBuf npts;              // int32 [cap_contours + 1]  counts, then exclusive offsets
+    DevBuf slice_start;       // int32 [batch + 1]
+    DevBuf block_counts;      // int32 scratch
+    DevBuf xy;                // int32 [cap_points * 2]
+    DevBuf header;            // int64 [4]: n_contours, n_points, overflow, trace_error
+    int64_t cap_contours = 0, cap_points = 0;
+};
+struct M2pWs {
+    CclWs fg, bg;
+    DevBuf nb;                // u8 per pixel: 8-neighbour foreground code
+    PolyDev poly;
+    PinBuf h_header;          // pinned int64[4]
+};
+// Phase A: labels, external starts (descending raster order per slice), per-contour vertex counts, offsets.
+void m2p_phase_a(M2pWs& ws, const uint8_t* d_mask, int h, int w, int batch, int threshold, cudaStream_t st);
+// Phase B: emit mapped vertices into ws.poly.xy (requires cap_points >= n_points).
+void m2p_phase_b(M2pWs& ws, int h, int w, int batch, int orig_w, int orig_h, cudaStream_t st);
+
+}  // namespace ms

@@ -1,0 +1,648 @@
+// engine.cu -- the C ABI of libmedseg_b200.so (include/medseg_b200.h): handle, config, stage entry
+// points, the in-memory per-batch pipeline and the per-file artefact writer.
+//
+// Host-side structure replaced: MedicalSeg::initialize_engine / TensorRTContext / execute_inference /
+// process_single_image / cleanup_resources (/root/reference/src/initialize.cpp, src/process.cpp,
+// src/cleanup.cpp).  Differences by design: state lives in a
+// handle instead of process globals + a thread_local context, every CUDA return code is checked,
+// intermediates stay in HBM instead of round-tripping through PNG/JSON files, and the batch is a
+// launch parameter instead of a hard-wired 1.
+#include "common.cuh"
+#include "unet.hpp"
+#include "json_min.hpp"
+#include "png_min.hpp"
+#include "overlay.hpp"
+
+#include <chrono>
+#include <cstring>
+#include <fstream>
+#include <iostream>
+#include <sstream>
+#include <sys/stat.h>
+
+namespace ms {
+
+thread_local LaunchCounter* g_counter = nullptr;
+static thread_local std::string t_last_error = "";
+
+void fail(int code, const std::string& what) { throw Error{code, what}; }
+
+}  // namespace ms
+
+using namespace ms;
+
+struct ms_handle {
+    int device = 0;
+    int sm_count = 148;
+    cudaStream_t stream = nullptr;
+    // config (defaults = the reference's literals)
+    int net_h = 512, net_w = 512, n_classes_cfg = 0, max_batch = 32;
+    int fg_value = 2, threshold = 127;
+    float min_area_ratio = 0.06f;
+    std::string weights_path;
+    // stages
+    UNet unet;
+    PreprocessWs pre;
+    PostprocessWs post;
+    M2pWs m2p;
+    // pipeline buffers
+    DevBuf d_src, d_norm, d_mask_raw, d_mask, d_logits, d_scratch_in, d_scratch_out;
+    PinBuf staging, h_header;
+    // log: every line is appended with open/append/close, so the C++ facade's own std::ofstream
+    // (opened with ios::app on the same file, see facade.cpp) interleaves correctly with it
+    std::string log_path;
+    bool log_on() const { return !log_path.empty(); }
+    void log(const std::string& line) const {
+        if (log_path.empty()) return;
+        FILE* f = std::fopen(log_path.c_str(), "a");
+        if (!f) return;
+        std::fputs(line.c_str(), f);
+        std::fputc('\n', f);
+        std::fclose(f);
+    }
+    std::string last_error;
+    LaunchCounter counter;
+};
+
+namespace {
+
+std::string dirname_of(const std::string& p) {
+    const size_t s = p.find_last_of('/');
+    return s == std::string::npos ? std::string(".") : p.substr(0, s);
+}
+std::string basename_of(const std::string& p) {
+    const size_t s = p.find_last_of('/');
+    return s == std::string::npos ? p : p.substr(s + 1);
+}
+std::string stem_of(const std::string& p) {
+    std::string b = basename_of(p);
+    const size_t d = b.find_last_of('.');
+    return (d == std::string::npos || d == 0) ? b : b.substr(0, d);
+}
+bool ends_with(const std::string& s, const std::string& suf) {
+    return s.size() >= suf.size() && s.compare(s.size() - suf.size(), suf.size(), suf) == 0;
+}
+void mkdirs(const std::string& path) {
+    std::string cur;
+    for (size_t i = 0; i <= path.size(); ++i) {
+        if (i == path.size() || path[i] == '/') {
+            if (!cur.empty()) ::mkdir(cur.c_str(), 0777);
+        }
+        if (i < path.size()) cur += path[i];
+    }
+}
+std::string read_text(const std::string& path) {
+    std::ifstream f(path, std::ios::binary);
+    MS_REQUIRE(f.good(), MS_ERR_IO, "cannot open " + path);
+    std::stringstream ss;
+    ss << f.rdbuf();
+    return ss.str();
+}
+
+template <class F>
+int guarded(ms_handle* h, F&& f) {
+    try {
+        if (h) {
+            MS_CUDA(cudaSetDevice(h->device));
+            g_counter = &h->counter;
+        }
+        f();
+        g_counter = nullptr;
+        return MS_OK;
+    } catch (const Error& e) {
+        g_counter = nullptr;
+        (h ? h->last_error : t_last_error) = e.what;
+        if (h) h->log("error: " + e.what);
+        return e.code;
+    } catch (const std::exception& e) {
+        g_counter = nullptr;
+        (h ? h->last_error : t_last_error) = e.what();
+        return MS_ERR_INTERNAL;
+    } catch (...) {
+        g_counter = nullptr;
+        (h ? h->last_error : t_last_error) = "unknown exception";
+        return MS_ERR_INTERNAL;
+    }
+}
+
+cudaStream_t pick_stream(ms_handle* h, void* s) { return s ? reinterpret_cast<cudaStream_t>(s) : h->stream; }
+
+bool is_cuda_host_ptr(const void* p) {
+    cudaPointerAttributes a{};
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return a.type == cudaMemoryTypeHost;
+}
+
+// H2D of caller memory: pinned -> direct async copy, pageable -> through the handle's pinned staging buffer.
+void upload(ms_handle* h, void* d_dst, const void* h_src, size_t bytes, cudaStream_t st) {
+    if (is_cuda_host_ptr(h_src)) {
+        MS_CUDA(cudaMemcpyAsync(d_dst, h_src, bytes, cudaMemcpyHostToDevice, st));
+    } else {
+        h->staging.reserve(bytes);
+        std::memcpy(h->staging.p, h_src, bytes);
+        MS_CUDA(cudaMemcpyAsync(d_dst, h->staging.p, bytes, cudaMemcpyHostToDevice, st));
+    }
+}
+void download_sync(ms_handle* h, void* h_dst, const void* d_src, size_t bytes, cudaStream_t st) {
+    (void)h;
+    MS_CUDA(cudaMemcpyAsync(h_dst, d_src, bytes, cudaMemcpyDeviceToHost, st));
+    MS_CUDA(cudaStreamSynchronize(st));
+}
+
+void apply_config(ms_handle* h, const json::Value& cfg, const std::string& base_dir) {
+    MS_REQUIRE(cfg.type == json::Value::Obj, MS_ERR_FORMAT, "config must be a JSON object");
+    h->net_h = (int)cfg.integer("net_h", cfg.integer("net_size", 512));
+    h->net_w = (int)cfg.integer("net_w", cfg.integer("net_size", 512));
+    h->n_classes_cfg = (int)cfg.integer("n_classes", 0);
+    h->max_batch = (int)cfg.integer("max_batch", 32);
+    h->fg_value = (int)cfg.integer("foreground_value", 2);
+    h->threshold = (int)cfg.integer("threshold", 127);
+    h->min_area_ratio = (float)cfg.number("min_area_ratio", 0.06f);
+    h->device = (int)cfg.integer("device", 0);
+    std::string w = cfg.string("weights", "");
+    if (!w.empty() && w[0] != '/') w = base_dir + "/" + w;
+    h->weights_path = w;
+    const std::string head = cfg.string("head", "");
+    if (head == "binary") MS_REQUIRE(h->n_classes_cfg == 0 || h->n_classes_cfg == 1, MS_ERR_FORMAT, "head=binary needs n_classes=1");
+    MS_REQUIRE(h->fg_value >= 1 && h->fg_value <= 255, MS_ERR_ARG, "foreground_value out of range");
+    MS_REQUIRE(h->max_batch >= 1, MS_ERR_ARG, "max_batch must be >= 1");
+}
+
+void finish_init(ms_handle* h, const char* log_dir) {
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        fail(MS_ERR_CUDA, "no CUDA device available (libmedseg_b200 has no CPU fallback)");
+    }
+    MS_REQUIRE(h->device >= 0 && h->device < ndev, MS_ERR_ARG, "device ordinal out of range");
+    MS_CUDA(cudaSetDevice(h->device));
+    cudaDeviceProp prop{};
+    MS_CUDA(cudaGetDeviceProperties(&prop, h->device));
+    MS_REQUIRE(prop.major == 10, MS_ERR_CUDA,
+               std::string("device '") + prop.name + "' is sm_" + std::to_string(prop.major * 10 + prop.minor) +
+                   "; libmedseg_b200 carries sm_100a code only");
+    h->sm_count = prop.multiProcessorCount;
+    MS_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    if (log_dir && log_dir[0]) {
+        mkdirs(log_dir);                                                   // src/initialize.cpp:29
+        h->log_path = std::string(log_dir) + "/segmentation_log.txt";      // :30
+        FILE* lf = std::fopen(h->log_path.c_str(), "w");                   // :31 (truncate)
+        if (!lf) {
+            const std::string p = h->log_path;
+            h->log_path.clear();
+            fail(MS_ERR_IO, "Failed to create log file: " + p);
+        }
+        std::fclose(lf);
+        h->log("=== Initializing Medical Image Segmentation Engine ===");
+        h->log(std::string("Engine: libmedseg_b200 (sm_100a) on ") + prop.name + ", weights: " + h->weights_path);
+    }
+    if (!h->weights_path.empty()) {
+        g_counter = &h->counter;
+        h->unet.load(h->weights_path, h->net_h, h->net_w, h->n_classes_cfg, h->max_batch, h->fg_value, h->sm_count);
+        h->log("UNet loaded: " + std::to_string(h->unet.n_params()) + " parameters, " +
+               std::to_string(h->unet.flops_per_slice() / 1e9) + " GFLOP per slice, n_classes=" + std::to_string(h->unet.n_classes()));
+    }
+    const size_t npx = (size_t)h->max_batch * h->net_h * h->net_w;
+    h->d_norm.reserve(npx);
+    h->d_mask_raw.reserve(npx);
+    h->d_mask.reserve(npx);
+    h->h_header.reserve(4 * sizeof(long long));
+    MS_CUDA(cudaStreamSynchronize(h->stream));
+}
+
+// Runs phase A (+ B) of mask2polygon with automatic growth of the device-side capacities.  On return
+// the pinned header holds {n_contours, n_points, overflow, trace_errors} and the stream is idle.
+void run_m2p(ms_handle* h, const uint8_t* d_mask, int hgt, int w, int batch, int threshold, int orig_w, int orig_h, cudaStream_t st) {
+    long long* hh = h->h_header.as<long long>();
+    for (int attempt = 0; attempt < 3; ++attempt) {
+        m2p_phase_a(h->m2p, d_mask, hgt, w, batch, threshold, st);
+        m2p_phase_b(h->m2p, hgt, w, batch, orig_w, orig_h, st);
+        download_sync(h, hh, h->m2p.poly.header.p, 4 * sizeof(long long), st);
+        MS_REQUIRE(hh[3] == 0, MS_ERR_INTERNAL, "mask2polygon: border following did not terminate");
+        MS_REQUIRE((hh[2] & 4) == 0, MS_ERR_CAPACITY, "mask2polygon: more than 2^31 points");
+        bool grown = false;
+        if (hh[0] > h->m2p.poly.cap_contours) { h->m2p.poly.cap_contours = hh[0] + hh[0] / 4 + 64; grown = true; }
+        if (hh[1] > h->m2p.poly.cap_points) { h->m2p.poly.cap_points = hh[1] + hh[1] / 4 + 1024; grown = true; }
+        if (!grown) return;
+    }
+    fail(MS_ERR_INTERNAL, "mask2polygon: capacity growth did not converge");
+}
+
+void copy_polygons_out(ms_handle* h, int batch, ms_polygons* out, cudaStream_t st) {
+    const long long* hh = h->h_header.as<long long>();
+    out->n_contours = hh[0];
+    out->n_points = hh[1];
+    MS_REQUIRE(out->cap_contours >= hh[0] && out->cap_points >= hh[1], MS_ERR_CAPACITY,
+               "polygon buffers too small: need " + std::to_string(hh[0]) + " contours, " + std::to_string(hh[1]) + " points");
+    MS_CUDA(cudaMemcpyAsync(out->slice_start, h->m2p.poly.slice_start.p, ((size_t)batch + 1) * 4, cudaMemcpyDeviceToHost, st));
+    MS_CUDA(cudaMemcpyAsync(out->contour_start, h->m2p.poly.npts.p, ((size_t)hh[0] + 1) * 4, cudaMemcpyDeviceToHost, st));
+    if (hh[1] > 0) MS_CUDA(cudaMemcpyAsync(out->xy, h->m2p.poly.xy.p, (size_t)hh[1] * 8, cudaMemcpyDeviceToHost, st));
+    MS_CUDA(cudaStreamSynchronize(st));
+}
+
+void check_polys(const ms_polygons* out, int batch) {
+    MS_REQUIRE(out && out->slice_start && out->contour_start && (out->xy || out->cap_points == 0) && out->cap_contours >= 0 &&
+                   out->cap_points >= 0 && batch > 0,
+               MS_ERR_ARG, "ms_polygons: null buffer or negative capacity");
+}
+
+// device pipeline shared by the batch entry points; input u16 already at d_src
+void pipeline_dev(ms_handle* h, const uint16_t* d_src, int w, int hgt, int batch, cudaStream_t st) {
+    MS_REQUIRE(h->unet.loaded(), MS_ERR_STATE, "no weights loaded (handle was created without a weight blob)");
+    MS_REQUIRE(batch >= 1 && batch <= h->max_batch, MS_ERR_ARG, "batch exceeds max_batch of this handle");
+    MS_REQUIRE(w > 0 && hgt > 0, MS_ERR_ARG, "bad slice size");
+    uint8_t* norm = h->d_norm.as<uint8_t>();
+    uint8_t* raw = h->d_mask_raw.as<uint8_t>();
+    uint8_t* mask = h->d_mask.as<uint8_t>();
+    preprocess_launch(h->pre, d_src, w, hgt, batch, h->net_w, h->net_h, norm, nullptr, st);         // src/process.cpp:211
+    h->unet.forward(norm, batch, raw, nullptr, st);                                                  // :224
+    postprocess_launch(h->post, raw, mask, h->net_h, h->net_w, batch, h->fg_value, h->min_area_ratio, st);  // :231
+    // mask_to_image + threshold(127) (:234, src/mask2polygon.cpp:31): after postprocess the mask is {0, fg};
+    // LUT(fg) > 127 <=> value == fg <=> value > fg - 1.
+    run_m2p(h, mask, h->net_h, h->net_w, batch, h->fg_value - 1, w, hgt, st);                        // :242
+}
+
+}  // namespace
+
+// ================================================================================== C ABI
+extern "C" {
+
+static int init_common(ms_handle* h, const char* log_dir, ms_handle** out) {
+    int rc = guarded(nullptr, [&] { finish_init(h, log_dir); });
+    if (rc != MS_OK) {
+        t_last_error = t_last_error.empty() ? h->last_error : t_last_error;
+        if (h->stream) cudaStreamDestroy(h->stream);
+        delete h;
+        return rc;
+    }
+    *out = h;
+    return MS_OK;
+}
+
+int ms_init(const char* path, const char* log_dir, ms_handle** out) {
+    if (!out) return MS_ERR_ARG;
+    *out = nullptr;
+    ms_handle* h = new ms_handle();
+    int rc = guarded(nullptr, [&] {
+        const std::string p = path ? path : "";
+        if (ends_with(p, ".json")) {
+            json::Value cfg;
+            try {
+                cfg = json::parse(read_text(p));
+            } catch (const std::exception& e) {
+                fail(MS_ERR_FORMAT, std::string("config ") + p + ": " + e.what());
+            }
+            apply_config(h, cfg, dirname_of(p));
+        } else if (!p.empty()) {
+            struct stat sb;
+            MS_REQUIRE(::stat(p.c_str(), &sb) == 0, MS_ERR_IO, "Error: engine file not found - " + p);  // src/initialize.cpp:42-45
+            h->weights_path = p;
+        }
+    });
+    if (rc != MS_OK) { delete h; return rc; }
+    return init_common(h, log_dir, out);
+}
+
+int ms_init_json(const char* cfg_json_text, const char* log_dir, ms_handle** out) {
+    if (!out || !cfg_json_text) return MS_ERR_ARG;
+    *out = nullptr;
+    ms_handle* h = new ms_handle();
+    int rc = guarded(nullptr, [&] {
+        json::Value cfg;
+        try {
+            cfg = json::parse(cfg_json_text);
+        } catch (const std::exception& e) {
+            fail(MS_ERR_FORMAT, std::string("config: ") + e.what());
+        }
+        apply_config(h, cfg, ".");
+    });
+    if (rc != MS_OK) { delete h; return rc; }
+    return init_common(h, log_dir, out);
+}
+
+void ms_destroy(ms_handle* h) {
+    if (!h) return;
+    cudaSetDevice(h->device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    h->log("\n=== Cleaning Up Resources ===");          // src/cleanup.cpp:13
+    h->log("All resources cleaned up successfully");    // :52
+    for (DevBuf* b : {&h->d_src, &h->d_norm, &h->d_mask_raw, &h->d_mask, &h->d_logits, &h->d_scratch_in, &h->d_scratch_out,
+                      &h->pre.minmax, &h->post.ccl.labels, &h->post.ccl.area, &h->post.ccl.flag, &h->post.bin_a, &h->post.bin_b,
+                      &h->m2p.fg.labels, &h->m2p.fg.area, &h->m2p.fg.flag, &h->m2p.bg.labels, &h->m2p.bg.area, &h->m2p.bg.flag, &h->m2p.nb,
+                      &h->m2p.poly.starts, &h->m2p.poly.start_slice, &h->m2p.poly.npts, &h->m2p.poly.slice_start,
+                      &h->m2p.poly.block_counts, &h->m2p.poly.xy, &h->m2p.poly.header})
+        b->release();
+    h->staging.release();
+    h->h_header.release();
+    h->m2p.h_header.release();
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;  // ~UNet frees weights and activations
+}
+
+const char* ms_last_error(ms_handle* h) { return h ? h->last_error.c_str() : t_last_error.c_str(); }
+
+int ms_get_info(ms_handle* h, ms_info* out) {
+    if (!h || !out) return MS_ERR_ARG;
+    out->device = h->device;
+    out->sm_count = h->sm_count;
+    out->net_h = h->net_h;
+    out->net_w = h->net_w;
+    out->n_classes = h->unet.loaded() ? h->unet.n_classes() : h->n_classes_cfg;
+    out->max_batch = h->max_batch;
+    out->foreground_value = h->fg_value;
+    out->min_area_ratio = h->min_area_ratio;
+    out->has_weights = h->unet.loaded() ? 1 : 0;
+    out->n_params = h->unet.loaded() ? h->unet.n_params() : 0;
+    out->flops_per_slice = h->unet.loaded() ? (int64_t)h->unet.flops_per_slice() : 0;
+    return MS_OK;
+}
+
+void* ms_alloc_pinned(size_t bytes) {
+    void* p = nullptr;
+    if (cudaMallocHost(&p, bytes) != cudaSuccess) {
+        cudaGetLastError();
+        return nullptr;
+    }
+    return p;
+}
+void ms_free_pinned(void* p) {
+    if (p) cudaFreeHost(p);
+}
+
+// ---------------------------------------------------------------- preprocess
+int ms_preprocess_dev(ms_handle* h, const uint16_t* d_src, int w, int hgt, int batch, uint8_t* d_out_u8, void* d_out_bf16, void* stream) {
+    if (!h) return MS_ERR_ARG;
+    return guarded(h, [&] {
+        MS_REQUIRE(d_src && d_out_u8, MS_ERR_ARG, "preprocess: null pointer");
+        preprocess_launch(h->pre, d_src, w, hgt, batch, h->net_w, h->net_h, d_out_u8, reinterpret_cast<__nv_bfloat16*>(d_out_bf16),
+                          pick_stream(h, stream));
+    });
+}
+int ms_preprocess_host(ms_handle* h, const uint16_t* h_src, int w, int hgt, int batch, uint8_t* h_out_u8) {
+    if (!h) return MS_ERR_ARG;
+    return guarded(h, [&] {
+        MS_REQUIRE(h_src && h_out_u8 && w > 0 && hgt > 0 && batch > 0, MS_ERR_ARG, "preprocess: bad argument");
+        const size_t in_bytes = (size_t)w * hgt * 2 * batch, out_bytes = (size_t)h->net_w * h->net_h * batch;
+        h->d_scratch_in.reserve(in_bytes);
+        h->d_scratch_out.reserve(out_bytes);
+        upload(h, h->d_scratch_in.p, h_src, in_bytes, h->stream);
+        preprocess_launch(h->pre, h->d_scratch_in.as<uint16_t>(), w, hgt, batch, h->net_w, h->net_h, h->d_scratch_out.as<uint8_t>(), nullptr, h->stream);
+        download_sync(h, h_out_u8, h->d_scratch_out.p, out_bytes, h->stream);
+    });
+}
+
+// ---------------------------------------------------------------- UNet
+int ms_unet_forward_dev(ms_handle* h, const uint8_t* d_in_u8, int batch, uint8_t* d_mask, float* d_logits, void* stream) {
+    if (!h) return MS_ERR_ARG;
+    return guarded(h, [&] {
+        MS_REQUIRE(d_in_u8 && d_mask, MS_ERR_ARG, "unet_forward: null pointer");
+        MS_REQUIRE(h->unet.loaded(), MS_ERR_STATE, "no weights loaded");
+        h->unet.forward(d_in_u8, batch, d_mask, d_logits, pick_stream(h, stream));
+    });
+}
+int ms_unet_forward_host(ms_handle* h, const uint8_t* h_in_u8, int batch, uint8_t* h_mask, float* h_logits) {
+    if (!h) return MS_ERR_ARG;
+    return guarded(h, [&] {
+        MS_REQUIRE(h_in_u8 && h_mask, MS_ERR_ARG, "unet_forward: null pointer");
+        MS_REQUIRE(h->unet.loaded(), MS_ERR_STATE, "no weights loaded");
+        MS_REQUIRE(batch >= 1 && batch <= h->max_batch, MS_ERR_ARG, "batch exceeds max_batch");
+        const size_t npx = (size_t)h->net_w * h->net_h * batch;
+        upload(h, h->d_norm.p, h_in_u8, npx, h->stream);
+        float* dl = nullptr;
+        if (h_logits) {
+            h->d_logits.reserve(npx * h->unet.n_classes() * 4);
+            dl = h->d_logits.as<float>();
+        }
+        h->unet.forward(h->d_norm.as<uint8_t>(), batch, h->d_mask_raw.as<uint8_t>(), dl, h->stream);
+        if (h_logits) MS_CUDA(cudaMemcpyAsync(h_logits, dl, npx * h->unet.n_classes() * 4, cudaMemcpyDeviceToHost, h->stream));
+        download_sync(h, h_mask, h->d_mask_raw.p, npx, h->stream);
+    });
+}
+
+// ---------------------------------------------------------------- postprocess
+int ms_postprocess_dev(ms_handle* h, const uint8_t* d_in, uint8_t* d_out, int hgt, int w, int batch, int fg_value, void* stream) {
+    if (!h) return MS_ERR_ARG;
+    return guarded(h, [&] {
+        MS_REQUIRE(d_in && d_out, MS_ERR_ARG, "postprocess: null pointer");
+        postprocess_launch(h->post, d_in, d_out, hgt, w, batch, fg_value > 0 ? fg_value : h->fg_value, h->min_area_ratio, pick_stream(h, stream));
+    });
+}
+int ms_postprocess_host(ms_handle* h, const uint8_t* h_in, uint8_t* h_out, int hgt, int w, int batch, int fg_value) {
+    if (!h) return MS_ERR_ARG;
+    return guarded(h, [&] {
+        MS_REQUIRE(h_in && h_out && hgt > 0 && w > 0 && batch > 0, MS_ERR_ARG, "postprocess: bad argument");
+        const size_t n = (size_t)hgt * w * batch;
+        h->d_scratch_in.reserve(n);
+        h->d_scratch_out.reserve(n);
+        upload(h, h->d_scratch_in.p, h_in, n, h->stream);
+        postprocess_launch(h->post, h->d_scratch_in.as<uint8_t>(), h->d_scratch_out.as<uint8_t>(), hgt, w, batch,
+                           fg_value > 0 ? fg_value : h->fg_value, h->min_area_ratio, h->stream);
+        download_sync(h, h_out, h->d_scratch_out.p, n, h->stream);
+    });
+}
+
+// ---------------------------------------------------------------- mask2polygon
+int ms_mask2polygon_dev(ms_handle* h, const uint8_t* d_mask, int hgt, int w, int batch, int threshold, int orig_w, int orig_h,
+                        ms_polygons* out, void* stream) {
+    if (!h) return MS_ERR_ARG;
+    return guarded(h, [&] {
+        check_polys(out, batch);
+        MS_REQUIRE(d_mask && orig_w > 0 && orig_h > 0, MS_ERR_ARG, "mask2polygon: bad argument");
+        cudaStream_t st = pick_stream(h, stream);
+        run_m2p(h, d_mask, hgt, w, batch, threshold, orig_w, orig_h, st);
+        copy_polygons_out(h, batch, out, st);
+    });
+}
+int ms_mask2polygon_host(ms_handle* h, const uint8_t* h_mask, int hgt, int w, int batch, int threshold, int orig_w, int orig_h,
+                         ms_polygons* out) {
+    if (!h) return MS_ERR_ARG;
+    return guarded(h, [&] {
+        check_polys(out, batch);
+        MS_REQUIRE(h_mask && hgt > 0 && w > 0 && orig_w > 0 && orig_h > 0, MS_ERR_ARG, "mask2polygon: bad argument");
+        const size_t n = (size_t)hgt * w * batch;
+        h->d_scratch_in.reserve(n);
+        upload(h, h->d_scratch_in.p, h_mask, n, h->stream);
+        run_m2p(h, h->d_scratch_in.as<uint8_t>(), hgt, w, batch, threshold, orig_w, orig_h, h->stream);
+        copy_polygons_out(h, batch, out, h->stream);
+    });
+}
+
+// ---------------------------------------------------------------- whole path
+int ms_process_batch_host(ms_handle* h, const uint16_t* h_src, int w, int hgt, int batch, ms_polygons* out, uint8_t* h_norm_u8,
+                          uint8_t* h_mask_u8) {
+    if (!h) return MS_ERR_ARG;
+    return guarded(h, [&] {
+        check_polys(out, batch);
+        MS_REQUIRE(h_src && w > 0 && hgt > 0, MS_ERR_ARG, "process_batch: bad argument");
+        const size_t in_bytes = (size_t)w * hgt * 2 * batch;
+        h->d_src.reserve(in_bytes);
+        upload(h, h->d_src.p, h_src, in_bytes, h->stream);
+        pipeline_dev(h, h->d_src.as<uint16_t>(), w, hgt, batch, h->stream);
+        const size_t npx = (size_t)h->net_w * h->net_h * batch;
+        if (h_norm_u8) MS_CUDA(cudaMemcpyAsync(h_norm_u8, h->d_norm.p, npx, cudaMemcpyDeviceToHost, h->stream));
+        if (h_mask_u8) MS_CUDA(cudaMemcpyAsync(h_mask_u8, h->d_mask.p, npx, cudaMemcpyDeviceToHost, h->stream));
+        copy_polygons_out(h, batch, out, h->stream);
+    });
+}
+
+int ms_process_batch_dev(ms_handle* h, const uint16_t* d_src, int w, int hgt, int batch, int64_t* n_points, int64_t* n_contours, void* stream) {
+    if (!h) return MS_ERR_ARG;
+    return guarded(h, [&] {
+        MS_REQUIRE(d_src, MS_ERR_ARG, "process_batch_dev: null pointer");
+        pipeline_dev(h, d_src, w, hgt, batch, pick_stream(h, stream));
+        const long long* hh = h->h_header.as<long long>();
+        if (n_contours) *n_contours = hh[0];
+        if (n_points) *n_points = hh[1];
+    });
+}
+
+int64_t ms_polygons_to_json(const int32_t* xy, const int32_t* contour_start, int n_contours, const char* base_name, int orig_w,
+                            int orig_h, char* dst, int64_t cap) {
+    if (n_contours < 0 || (n_contours > 0 && (!xy || !contour_start)) || !base_name) return MS_ERR_ARG;
+    try {
+        const std::string s = json::labelme_text(xy, contour_start, n_contours, base_name, orig_w, orig_h);
+        if (dst && cap > 0) std::memcpy(dst, s.data(), (size_t)std::min<int64_t>(cap, (int64_t)s.size()));
+        return (int64_t)s.size();
+    } catch (...) {
+        return MS_ERR_INTERNAL;
+    }
+}
+
+int ms_process_raw_file(ms_handle* h, const char* raw_path, int w, int hgt, const char* out_dir) {
+    if (!h) return MS_ERR_ARG;
+    return guarded(h, [&] {
+        MS_REQUIRE(raw_path && out_dir && w > 0 && hgt > 0, MS_ERR_ARG, "process_raw_file: bad argument");
+        const auto t0 = std::chrono::high_resolution_clock::now();
+        const std::string raw = raw_path, dir = out_dir;
+        const std::string base = stem_of(raw);                                             // src/process.cpp:201
+        h->log("\n=== Processing Image: " + basename_of(raw) + " ===");                     // :198
+        const std::string png_path = dir + "/" + base + "_normalized.png";                 // :207
+        const std::string sizes_path = dir + "/" + base + "_original_sizes.json";          // :208
+        const std::string mask_path = dir + "/" + base + "_mask.png";                      // :209
+        // read the headerless u16 slice (the reference mmaps w*h*2 bytes from offset 0, src/preprocess.cpp:86)
+        const size_t n_in = (size_t)w * hgt;
+        std::vector<uint16_t> src(n_in);
+        {
+            FILE* f = std::fopen(raw.c_str(), "rb");
+            MS_REQUIRE(f, MS_ERR_IO, "open failed: " + raw);
+            const size_t got = std::fread(src.data(), 2, n_in, f);
+            std::fclose(f);
+            MS_REQUIRE(got == n_in, MS_ERR_IO, "file shorter than width*height*2 bytes: " + raw);
+        }
+        mkdirs(dir);
+        const size_t npx = (size_t)h->net_w * h->net_h;
+        std::vector<uint8_t> norm(npx), mask(npx);
+        h->d_src.reserve(n_in * 2);
+        upload(h, h->d_src.p, src.data(), n_in * 2, h->stream);
+        const auto ti0 = std::chrono::high_resolution_clock::now();
+        pipeline_dev(h, h->d_src.as<uint16_t>(), w, hgt, 1, h->stream);
+        const auto ti1 = std::chrono::high_resolution_clock::now();
+        const long long* hh = h->h_header.as<long long>();
+        const int nc = (int)hh[0];
+        std::vector<int32_t> cstart((size_t)nc + 1), xy((size_t)std::max<long long>(hh[1], 1) * 2), sl(2);
+        ms_polygons pg{xy.data(), (int64_t)xy.size() / 2, cstart.data(), nc, sl.data(), 0, 0};
+        MS_CUDA(cudaMemcpyAsync(norm.data(), h->d_norm.p, npx, cudaMemcpyDeviceToHost, h->stream));
+        MS_CUDA(cudaMemcpyAsync(mask.data(), h->d_mask.p, npx, cudaMemcpyDeviceToHost, h->stream));
+        copy_polygons_out(h, 1, &pg, h->stream);
+        h->log("Inference time: " + std::to_string(std::chrono::duration_cast<std::chrono::milliseconds>(ti1 - ti0).count()) + " ms");  // :228
+
+        // artefacts (src/preprocess.cpp:121-134, src/process.cpp:234-239)
+        MS_REQUIRE(png::write_file(png_path, norm.data(), h->net_w, h->net_h, 1), MS_ERR_IO, "imwrite failed: " + png_path);
+        {
+            std::ofstream jf(sizes_path, std::ios::binary);
+            MS_REQUIRE(jf.good(), MS_ERR_IO, "cannot write " + sizes_path);
+            jf << json::sidecar_text(basename_of(raw), w, hgt, h->net_w, h->net_h);
+        }
+        std::vector<uint8_t> vis(npx);
+        for (size_t i = 0; i < npx; ++i) vis[i] = mask[i] == 1 ? 128 : (mask[i] == 2 ? 255 : (mask[i] == h->fg_value ? 255 : 0));  // :178-185
+        MS_REQUIRE(png::write_file(mask_path, vis.data(), h->net_w, h->net_h, 1), MS_ERR_IO, "Failed to save mask");
+
+        std::cout << "Processing Mask: " << base + ".png" << std::endl;                   // src/mask2polygon.cpp:141
+        std::cout << "Original Size: " << w << "x" << hgt << std::endl;                   // :162
+        std::cout << "Scaled Size: " << h->net_w << "x" << h->net_h << std::endl;          // :163
+        if (nc == 0) {
+            std::cout << "Warning: No Contours Detected" << std::endl;                    // :184 (no JSON is written)
+        } else {
+            std::cout << "Extracted " << nc << " Contours" << std::endl;                  // :187
+            // overlay with unmapped (network-space) contours, red, 1 px (src/mask2polygon.cpp:114-129, 189-193)
+            std::vector<int32_t> uxy((size_t)hh[1] * 2);
+            m2p_phase_b(h->m2p, h->net_h, h->net_w, 1, h->net_w, h->net_h, h->stream);
+            download_sync(h, uxy.data(), h->m2p.poly.xy.p, (size_t)hh[1] * 8, h->stream);
+            std::vector<uint8_t> rgb(npx * 3);
+            for (size_t i = 0; i < npx; ++i) rgb[3 * i] = rgb[3 * i + 1] = rgb[3 * i + 2] = norm[i];
+            draw_contours_red(rgb, h->net_w, h->net_h, uxy.data(), cstart.data(), nc);
+            const std::string overlay_path = dir + "/" + base + "_contour_overlay.png";  // :190
+            MS_REQUIRE(png::write_file(overlay_path, rgb.data(), h->net_w, h->net_h, 3), MS_ERR_IO, "Fail to Save Overlay PNG: " + overlay_path);
+            std::cout << "Overlay Image Saved to: " << overlay_path << std::endl;         // :193
+            const std::string out_json = dir + "/" + base + ".json";                      // :206
+            std::ofstream f(out_json, std::ios::binary);
+            MS_REQUIRE(f.good(), MS_ERR_IO, "Fail to Create JSON File: " + out_json);
+            f << json::labelme_text(xy.data(), cstart.data(), nc, base, w, hgt);           // :207
+            std::cout << "JSON Saved to: " << out_json << std::endl;                      // :208
+        }
+        const auto total_ms = std::chrono::duration_cast<std::chrono::milliseconds>(std::chrono::high_resolution_clock::now() - t0).count();
+        h->log("Total processing time: " + std::to_string(total_ms) + " ms");            // src/process.cpp:249
+        h->log("Processing completed for: " + base);                                      // :250
+        std::cout << "Total processing time: " << total_ms << " ms" << std::endl;         // :253
+    });
+}
+
+// ---------------------------------------------------------------- instrumentation
+int64_t ms_launch_count(ms_handle* h) { return h ? h->counter.n : 0; }
+int ms_layer_count(ms_handle* h) { return h && h->unet.loaded() ? (int)h->unet.layers().size() : 0; }
+const char* ms_layer_name(ms_handle* h, int layer) {
+    if (!h || !h->unet.loaded() || layer < 0 || layer >= (int)h->unet.layers().size()) return "";
+    return h->unet.layers()[layer].name.c_str();
+}
+int ms_time_layer(ms_handle* h, int layer, int batch, int iters, float* ms_per_launch, double* flops) {
+    if (!h) return MS_ERR_ARG;
+    return guarded(h, [&] {
+        MS_REQUIRE(h->unet.loaded(), MS_ERR_STATE, "no weights loaded");
+        MS_REQUIRE(iters >= 1 && ms_per_launch, MS_ERR_ARG, "time_layer: bad argument");
+        cudaEvent_t e0, e1;
+        MS_CUDA(cudaEventCreate(&e0));
+        MS_CUDA(cudaEventCreate(&e1));
+        for (int i = 0; i < 3; ++i) h->unet.run_layer(layer, h->d_norm.as<uint8_t>(), batch, h->d_mask_raw.as<uint8_t>(), nullptr, h->stream);
+        MS_CUDA(cudaEventRecord(e0, h->stream));
+        for (int i = 0; i < iters; ++i) h->unet.run_layer(layer, h->d_norm.as<uint8_t>(), batch, h->d_mask_raw.as<uint8_t>(), nullptr, h->stream);
+        MS_CUDA(cudaEventRecord(e1, h->stream));
+        MS_CUDA(cudaStreamSynchronize(h->stream));
+        float ms = 0;
+        MS_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+        cudaEventDestroy(e0);
+        cudaEventDestroy(e1);
+        *ms_per_launch = ms / iters;
+        if (flops) *flops = h->unet.layers()[layer].flops_per_slice * batch;
+    });
+}
+
+int64_t ms_debug_read_activation(ms_handle* h, const char* name, int batch, float* h_dst, int64_t cap) {
+    if (!h || !name) return MS_ERR_ARG;
+    int64_t result = 0;
+    int rc = guarded(h, [&] {
+        MS_REQUIRE(h->unet.loaded(), MS_ERR_STATE, "no weights loaded");
+        const ActBuf* buf = nullptr;
+        for (const auto& b : h->unet.buffers())
+            if (b.name == name) buf = &b;
+        MS_REQUIRE(buf, MS_ERR_ARG, std::string("unknown activation buffer: ") + name);
+        const int hh = h->net_h >> buf->level, ww = h->net_w >> buf->level, C = buf->C;
+        const size_t n = (size_t)batch * hh * ww * C;
+        result = (int64_t)n;
+        if (!h_dst || cap < (int64_t)n) return;
+        std::vector<__nv_bfloat16> tmp(n);
+        MS_CUDA(cudaStreamSynchronize(h->stream));
+        MS_CUDA(cudaMemcpy(tmp.data(), buf->p, n * 2, cudaMemcpyDeviceToHost));
+        for (int b = 0; b < batch; ++b)          // NHWC bf16 -> NCHW fp32
+            for (int y = 0; y < hh; ++y)
+                for (int x = 0; x < ww; ++x)
+                    for (int c = 0; c < C; ++c)
+                        h_dst[(((size_t)b * C + c) * hh + y) * ww + x] = __bfloat162float(tmp[(((size_t)b * hh + y) * ww + x) * C + c]);
+    });
+    return rc == MS_OK ? result : rc;
+}
+
+}  // extern "C"

@@ -1,0 +1,447 @@
+// unet.cu -- UNet forward: weight preparation, activation arena, tensor maps, layer schedule.
+//
+// Replaces the TensorRT engine the reference deserialises and replays
+// (/root/reference/src/initialize.cpp:48-60, src/process.cpp:45-120,147).  Architecture: the
+// canonical UNet fixed in SURVEY.md section 8(a) row P3 (1->64->128->256->512->1024, two
+// conv3x3+BN+ReLU per level, 2x2 max-pool down, ConvTranspose 2x2 s2 up, cat([skip, up]), 1x1 head).
+//
+// HBM layout (all activations NHWC bf16, sized for max_batch):
+//   e1a                         enc1a output (direct CUDA-core conv: Cin = 1, K = 9 is pure bandwidth)
+//   cat1..cat4  [.., 2C]        channels [0,C) written by the encoder's second conv (skip), [C,2C) by
+//                               the ConvT of the level below -> the concat is never materialised twice
+//   p1..p4                      pooled encoder outputs, written by the fused max-pool epilogue
+//   e2a,e3a,e4a,ba,bb,d4a..d1a  intermediate feature maps
+// The last feature map (dec1b) never reaches HBM: the head runs in the epilogue.
+#include "unet.hpp"
+#include "unet_conv_tc.cuh"
+#include "json_min.hpp"
+
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <map>
+
+namespace ms {
+
+namespace {
+
+// ------------------------------------------------------------------ first conv (Cin = 1): direct
+// One thread = one pixel x 8 output channels -> one 16-byte NHWC store; a warp covers 4 pixels x 64 ch
+// = 512 contiguous bytes.  x = float(u8) / 255.0f exactly as src/process.cpp:38.
+__global__ void __launch_bounds__(256) first_conv_kernel(const uint8_t* __restrict__ in, int H, int W, int batch,
+                                                          const float* __restrict__ w /*[64][9]*/, const float* __restrict__ bias,
+                                                          __nv_bfloat16* __restrict__ out /*NHWC 64*/) {
+    __shared__ float sw[64 * 9 + 64];
+    for (int i = threadIdx.x; i < 64 * 9 + 64; i += 256) sw[i] = i < 576 ? w[i] : bias[i - 576];
+    __syncthreads();
+    const size_t gid = (size_t)blockIdx.x * 256 + threadIdx.x;
+    const size_t npix = (size_t)batch * H * W;
+    const size_t pix = gid >> 3;
+    if (pix >= npix) return;
+    const int cg = (int)(gid & 7) * 8;
+    const int x = (int)(pix % W), y = (int)((pix / W) % H);
+    const uint8_t* img = in + (pix / ((size_t)H * W)) * (size_t)H * W;
+    float v[9];
+#pragma unroll
+    for (int t = 0; t < 9; ++t) {
+        const int yy = y + t / 3 - 1, xx = x + t % 3 - 1;
+        v[t] = (yy >= 0 && yy < H && xx >= 0 && xx < W) ? __fdiv_rn((float)img[(size_t)yy * W + xx], 255.0f) : 0.0f;
+    }
+    uint32_t pk[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        float a = sw[576 + cg + 2 * j], b = sw[576 + cg + 2 * j + 1];
+#pragma unroll
+        for (int t = 0; t < 9; ++t) {
+            a = fmaf(v[t], sw[(cg + 2 * j) * 9 + t], a);
+            b = fmaf(v[t], sw[(cg + 2 * j + 1) * 9 + t], b);
+        }
+        pk[j] = tc::pack_bf16(fmaxf(a, 0.0f), fmaxf(b, 0.0f));
+    }
+    *reinterpret_cast<uint4*>(out + pix * 64 + cg) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+}
+
+// ------------------------------------------------------------------ CUDA-core reference kernels
+// Debug / validation only (MEDSEG_NAIVE_CONV=1): same operands, same epilogue semantics as the
+// tcgen05 kernel, one thread per GEMM output element.  Never used by default.
+__global__ void naive_gemm_conv_kernel(const __nv_bfloat16* __restrict__ src, int src_c, const __nv_bfloat16* __restrict__ wgt,
+                                       tc::ConvArgs a, int epi) {
+    const size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t total = (size_t)a.batch * a.H * a.W * a.n_total;
+    if (gid >= total) return;
+    const int n = (int)(gid % a.n_total);
+    const size_t pix = gid / a.n_total;
+    const int x = (int)(pix % a.W), y = (int)((pix / a.W) % a.H), b = (int)(pix / ((size_t)a.W * a.H));
+    const int K = a.taps * a.Cin;
+    float acc = 0.0f;
+    for (int tap = 0; tap < a.taps; ++tap) {
+        const int yy = y + (a.taps == 9 ? tap / 3 - 1 : 0), xx = x + (a.taps == 9 ? tap % 3 - 1 : 0);
+        if (yy < 0 || yy >= a.H || xx < 0 || xx >= a.W) continue;
+        const __nv_bfloat16* s = src + (((size_t)b * a.H + yy) * a.W + xx) * src_c;
+        const __nv_bfloat16* wr = wgt + (size_t)n * K + (size_t)tap * a.Cin;
+        for (int ci = 0; ci < a.Cin; ++ci) acc = fmaf(__bfloat162float(s[ci]), __bfloat162float(wr[ci]), acc);
+    }
+    const int co = n % a.Cout;
+    acc += a.bias[co];
+    if (epi == tc::EPI_STORE) {
+        acc = fmaxf(acc, 0.0f);
+        a.out[(((size_t)b * a.H + y) * a.W + x) * a.out_cstride + a.out_coff + n] = __float2bfloat16_rn(acc);
+    } else {
+        const int q = n / a.Cout;
+        const int oy = 2 * y + (q >> 1), ox = 2 * x + (q & 1);
+        a.out[(((size_t)b * 2 * a.H + oy) * 2 * a.W + ox) * a.out_cstride + a.out_coff + co] = __float2bfloat16_rn(acc);
+    }
+}
+__global__ void naive_pool_kernel(const __nv_bfloat16* __restrict__ src, int cstride, int H, int W, int C, int batch,
+                                  __nv_bfloat16* __restrict__ dst) {
+    const size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t total = (size_t)batch * (H / 2) * (W / 2) * C;
+    if (gid >= total) return;
+    const int c = (int)(gid % C);
+    size_t p = gid / C;
+    const int x = (int)(p % (W / 2)), y = (int)((p / (W / 2)) % (H / 2)), b = (int)(p / ((size_t)(W / 2) * (H / 2)));
+    float m = -INFINITY;
+    for (int dy = 0; dy < 2; ++dy)
+        for (int dx = 0; dx < 2; ++dx)
+            m = fmaxf(m, __bfloat162float(src[(((size_t)b * H + 2 * y + dy) * W + 2 * x + dx) * cstride + c]));
+    dst[gid] = __float2bfloat16_rn(m);
+}
+__global__ void naive_head_conv_kernel(const __nv_bfloat16* __restrict__ src, const __nv_bfloat16* __restrict__ wgt, tc::ConvArgs a) {
+    const size_t pix = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (pix >= (size_t)a.batch * a.H * a.W) return;
+    const int x = (int)(pix % a.W), y = (int)((pix / a.W) % a.H), b = (int)(pix / ((size_t)a.W * a.H));
+    float logit[8];
+    for (int c = 0; c < a.n_classes; ++c) logit[c] = a.head_b[c];
+    for (int n = 0; n < 64; ++n) {
+        float acc = 0.0f;
+        for (int tap = 0; tap < 9; ++tap) {
+            const int yy = y + tap / 3 - 1, xx = x + tap % 3 - 1;
+            if (yy < 0 || yy >= a.H || xx < 0 || xx >= a.W) continue;
+            const __nv_bfloat16* s = src + (((size_t)b * a.H + yy) * a.W + xx) * 64;
+            const __nv_bfloat16* wr = wgt + (size_t)n * 576 + tap * 64;
+            for (int ci = 0; ci < 64; ++ci) acc = fmaf(__bfloat162float(s[ci]), __bfloat162float(wr[ci]), acc);
+        }
+        acc = fmaxf(acc + a.bias[n], 0.0f);
+        for (int c = 0; c < a.n_classes; ++c) logit[c] = fmaf(acc, a.head_w[c * 64 + n], logit[c]);
+    }
+    float best = -3.402823466e+38f;
+    int bc = 0;
+    const size_t plane = (size_t)a.H * a.W;
+    for (int c = 0; c < a.n_classes; ++c) {
+        if (a.logits) a.logits[((size_t)b * a.n_classes + c) * plane + (size_t)y * a.W + x] = logit[c];
+        if (logit[c] > best) { best = logit[c]; bc = c; }
+    }
+    a.mask[pix] = a.n_classes == 1 ? (uint8_t)(best > 0.0f ? a.fg_value : 0) : (uint8_t)bc;
+}
+
+// ------------------------------------------------------------------ tensor maps
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        MS_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q));
+        MS_REQUIRE(p && q == cudaDriverEntryPointSuccess, MS_ERR_CUDA, "cuTensorMapEncodeTiled not available in this driver");
+        fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+// activations [B][H][W][C] bf16, box {64, 16, 8, 1}, 128-byte swizzle, OOB -> zero (= conv padding)
+void make_act_map(CUtensorMap* m, const __nv_bfloat16* base, int B, int H, int W, int C) {
+    cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+    cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
+    cuuint32_t box[4] = {(cuuint32_t)tc::BLOCK_K, (cuuint32_t)tc::TILE_W, (cuuint32_t)tc::TILE_H, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = encode_fn()(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<__nv_bfloat16*>(base), dims, strides, box, estr,
+                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    MS_REQUIRE(r == CUDA_SUCCESS, MS_ERR_CUDA, "cuTensorMapEncodeTiled(activation) failed: " + std::to_string((int)r));
+}
+// weights [N][K] bf16, box {64, block_n}
+void make_wgt_map(CUtensorMap* m, const __nv_bfloat16* base, int N, int K, int block_n) {
+    cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)N};
+    cuuint64_t strides[1] = {(cuuint64_t)K * 2};
+    cuuint32_t box[2] = {(cuuint32_t)tc::BLOCK_K, (cuuint32_t)block_n};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = encode_fn()(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<__nv_bfloat16*>(base), dims, strides, box, estr,
+                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    MS_REQUIRE(r == CUDA_SUCCESS, MS_ERR_CUDA, "cuTensorMapEncodeTiled(weights) failed: " + std::to_string((int)r));
+}
+
+template <int BN, int EPI>
+void launch_tc(const UNetLayer& L, const tc::ConvArgs& a, int sm_count, cudaStream_t st) {
+    using C = tc::Cfg<BN>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        MS_CUDA(cudaFuncSetAttribute(tc::conv_gemm_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+        attr_set = true;
+    }
+    const int total = a.batch * (a.H / tc::TILE_H) * (a.W / tc::TILE_W) * (a.n_total / BN);
+    const int grid = std::min(total, sm_count);
+    tc::conv_gemm_kernel<BN, EPI><<<grid, tc::NUM_THREADS, C::SMEM_BYTES, st>>>(L.map_a, L.map_b, a);
+    MS_LAUNCH_CHECK();
+}
+
+struct Blob {
+    std::vector<char> raw;
+    size_t base = 0;
+    std::map<std::string, std::pair<const float*, std::vector<int64_t>>> t;
+    int n_classes = 0;
+    double eps = 1e-5;
+    const float* get(const std::string& name, size_t expect) const {
+        auto it = t.find(name);
+        MS_REQUIRE(it != t.end(), MS_ERR_FORMAT, "weight blob: missing tensor " + name);
+        size_t n = 1;
+        for (auto d : it->second.second) n *= (size_t)d;
+        MS_REQUIRE(n == expect, MS_ERR_FORMAT, "weight blob: tensor " + name + " has wrong size");
+        return it->second.first;
+    }
+};
+Blob read_blob(const std::string& path) {
+    Blob b;
+    std::ifstream f(path, std::ios::binary);
+    MS_REQUIRE(f.good(), MS_ERR_IO, "cannot open weight blob: " + path);
+    f.seekg(0, std::ios::end);
+    const size_t sz = (size_t)f.tellg();
+    f.seekg(0);
+    b.raw.resize(sz);
+    f.read(b.raw.data(), (std::streamsize)sz);
+    MS_REQUIRE(sz > 12 && std::memcmp(b.raw.data(), "MSEGW001", 8) == 0, MS_ERR_FORMAT, "not a MSEGW001 weight blob: " + path);
+    uint32_t hl;
+    std::memcpy(&hl, b.raw.data() + 8, 4);
+    MS_REQUIRE(12 + (size_t)hl <= sz, MS_ERR_FORMAT, "weight blob: truncated header");
+    json::Value h;
+    try {
+        h = json::parse(std::string(b.raw.data() + 12, hl));
+    } catch (const std::exception& e) {
+        fail(MS_ERR_FORMAT, std::string("weight blob header: ") + e.what());
+    }
+    b.base = (12 + (size_t)hl + 63) / 64 * 64;
+    b.n_classes = (int)h.at("arch").integer("n_classes", 3);
+    b.eps = h.at("arch").number("bn_eps", 1e-5);
+    for (const auto& tv : h.at("tensors").arr) {
+        std::vector<int64_t> shape;
+        size_t n = 1;
+        for (const auto& d : tv.at("shape").arr) { shape.push_back((int64_t)d.num); n *= (size_t)d.num; }
+        const size_t off = b.base + (size_t)tv.at("offset").num;
+        MS_REQUIRE(off + n * 4 <= sz, MS_ERR_FORMAT, "weight blob: tensor out of range: " + tv.at("name").str);
+        b.t[tv.at("name").str] = {reinterpret_cast<const float*>(b.raw.data() + off), shape};
+    }
+    return b;
+}
+
+}  // namespace
+
+UNet::~UNet() {
+    for (void* p : allocs_) cudaFree(p);
+    scratch_mask_.release();
+}
+
+void UNet::load(const std::string& blob_path, int net_h, int net_w, int n_classes_cfg, int max_batch, int fg_value, int sm_count) {
+    MS_REQUIRE(!loaded_, MS_ERR_STATE, "UNet already loaded");
+    MS_REQUIRE(net_h % 128 == 0 && net_w % 256 == 0 && net_h > 0 && net_w > 0, MS_ERR_ARG,
+               "net size must be a multiple of 128 (height) x 256 (width): 16x8-pixel tiles at 1/16 resolution");
+    MS_REQUIRE(max_batch >= 1 && max_batch <= 4096, MS_ERR_ARG, "max_batch out of range");
+    H_ = net_h; W_ = net_w; max_batch_ = max_batch; fg_value_ = fg_value; sm_count_ = sm_count;
+    const char* nv = std::getenv("MEDSEG_NAIVE_CONV");
+    naive_ = nv && nv[0] == '1';
+    Blob blob = read_blob(blob_path);
+    n_classes_ = blob.n_classes;
+    MS_REQUIRE(n_classes_cfg <= 0 || n_classes_cfg == n_classes_, MS_ERR_FORMAT, "config n_classes does not match the weight blob");
+    MS_REQUIRE(n_classes_ >= 1 && n_classes_ <= 8, MS_ERR_ARG, "n_classes must be 1..8");
+
+    auto dmalloc = [&](size_t bytes) { void* p = nullptr; MS_CUDA(cudaMalloc(&p, bytes)); allocs_.push_back(p); return p; };
+    auto upload_f32 = [&](const std::vector<float>& v) { float* d = (float*)dmalloc(v.size() * 4); MS_CUDA(cudaMemcpy(d, v.data(), v.size() * 4, cudaMemcpyHostToDevice)); return d; };
+    auto upload_bf16 = [&](const std::vector<__nv_bfloat16>& v) { auto* d = (__nv_bfloat16*)dmalloc(v.size() * 2); MS_CUDA(cudaMemcpy(d, v.data(), v.size() * 2, cudaMemcpyHostToDevice)); return d; };
+
+    // ---- activation arena
+    auto add_buf = [&](const char* name, int level, int C) {
+        ActBuf b; b.name = name; b.level = level; b.C = C;
+        const size_t n = (size_t)max_batch * (H_ >> level) * (W_ >> level) * C;
+        b.p = (__nv_bfloat16*)dmalloc(n * 2);
+        bufs_.push_back(b);
+        return (int)bufs_.size() - 1;
+    };
+    const int e1a = add_buf("e1a", 0, 64), cat1 = add_buf("cat1", 0, 128), p1 = add_buf("p1", 1, 64);
+    const int e2a = add_buf("e2a", 1, 128), cat2 = add_buf("cat2", 1, 256), p2 = add_buf("p2", 2, 128);
+    const int e3a = add_buf("e3a", 2, 256), cat3 = add_buf("cat3", 2, 512), p3 = add_buf("p3", 3, 256);
+    const int e4a = add_buf("e4a", 3, 512), cat4 = add_buf("cat4", 3, 1024), p4 = add_buf("p4", 4, 512);
+    const int ba = add_buf("ba", 4, 1024), bb = add_buf("bb", 4, 1024);
+    const int d4a = add_buf("d4a", 3, 512), d4b = add_buf("d4b", 3, 512);
+    const int d3a = add_buf("d3a", 2, 256), d3b = add_buf("d3b", 2, 256);
+    const int d2a = add_buf("d2a", 1, 128), d2b = add_buf("d2b", 1, 128);
+    const int d1a = add_buf("d1a", 0, 64);
+    scratch_mask_.reserve((size_t)max_batch * H_ * W_);
+
+    // ---- weights
+    n_params_ = 0;
+    flops_ = 0;
+    const double eps = blob.eps;
+    // conv3x3 + BN folded: returns K-major bf16 [Cout][9*Cin] and fp32 bias
+    auto fold_conv = [&](const std::string& conv, const std::string& bn, int cin, int cout, std::vector<float>& wf, std::vector<float>& bias) {
+        const float* w = blob.get(conv + ".weight", (size_t)cout * cin * 9);
+        const float* g = blob.get(bn + ".weight", cout);
+        const float* be = blob.get(bn + ".bias", cout);
+        const float* mu = blob.get(bn + ".running_mean", cout);
+        const float* var = blob.get(bn + ".running_var", cout);
+        wf.assign((size_t)cout * 9 * cin, 0.f);
+        bias.assign(cout, 0.f);
+        for (int co = 0; co < cout; ++co) {
+            const float s = g[co] / std::sqrt(var[co] + (float)eps);
+            bias[co] = be[co] - mu[co] * s;
+            for (int ci = 0; ci < cin; ++ci)
+                for (int t = 0; t < 9; ++t) wf[((size_t)co * 9 + t) * cin + ci] = w[((size_t)co * cin + ci) * 9 + t] * s;
+        }
+        n_params_ += (int64_t)cout * cin * 9 + 2 * cout;
+    };
+    auto to_bf16 = [](const std::vector<float>& v) {
+        std::vector<__nv_bfloat16> o(v.size());
+        for (size_t i = 0; i < v.size(); ++i) o[i] = __float2bfloat16_rn(v[i]);
+        return o;
+    };
+    auto pick_bn = [](int n_total) { return n_total % 256 == 0 ? 256 : (n_total % 128 == 0 ? 128 : 64); };
+    auto add_conv = [&](const char* name, const std::string& conv, const std::string& bn, int level, int cin, int cout, int src, int dst,
+                        int coff, int pool_dst, bool head) {
+        UNetLayer L;
+        L.name = name; L.kind = head ? 3 : 1; L.level = level; L.Cin = cin; L.Cout = cout; L.taps = 9; L.n_total = cout;
+        L.block_n = head ? 64 : pick_bn(cout);
+        L.src = src; L.dst = dst; L.dst_coff = coff; L.pool_dst = pool_dst;
+        std::vector<float> wf, bias;
+        fold_conv(conv, bn, cin, cout, wf, bias);
+        L.w = upload_bf16(to_bf16(wf));
+        L.bias = upload_f32(bias);
+        const int h = H_ >> level, w = W_ >> level;
+        L.flops_per_slice = 2.0 * h * w * (double)cout * 9 * cin;
+        make_act_map(&L.map_a, bufs_[src].p, max_batch, h, w, bufs_[src].C);
+        make_wgt_map(&L.map_b, L.w, cout, 9 * cin, L.block_n);
+        flops_ += L.flops_per_slice;
+        layers_.push_back(L);
+    };
+    auto add_convt = [&](const char* name, const std::string& up, int level_in, int cin, int cout, int src, int dst, int coff) {
+        UNetLayer L;
+        L.name = name; L.kind = 2; L.level = level_in; L.Cin = cin; L.Cout = cout; L.taps = 1; L.n_total = 4 * cout;
+        L.block_n = pick_bn(4 * cout);
+        L.src = src; L.dst = dst; L.dst_coff = coff;
+        const float* w = blob.get(up + ".weight", (size_t)cin * cout * 4);  // torch layout [Cin][Cout][2][2]
+        const float* b = blob.get(up + ".bias", cout);
+        std::vector<float> wf((size_t)4 * cout * cin);
+        for (int ci = 0; ci < cin; ++ci)
+            for (int co = 0; co < cout; ++co)
+                for (int q = 0; q < 4; ++q) wf[((size_t)q * cout + co) * cin + ci] = w[((size_t)ci * cout + co) * 4 + q];
+        L.w = upload_bf16(to_bf16(wf));
+        L.bias = upload_f32(std::vector<float>(b, b + cout));
+        const int h = H_ >> level_in, wd = W_ >> level_in;
+        L.flops_per_slice = 2.0 * h * wd * 4.0 * cout * cin;
+        make_act_map(&L.map_a, bufs_[src].p, max_batch, h, wd, bufs_[src].C);
+        make_wgt_map(&L.map_b, L.w, 4 * cout, cin, L.block_n);
+        n_params_ += (int64_t)cin * cout * 4 + cout;
+        flops_ += L.flops_per_slice;
+        layers_.push_back(L);
+    };
+
+    {   // enc1a: direct conv, fp32 weights [64][9]
+        UNetLayer L;
+        L.name = "enc1a"; L.kind = 0; L.level = 0; L.Cin = 1; L.Cout = 64; L.taps = 9; L.n_total = 64; L.dst = e1a;
+        std::vector<float> wf, bias;
+        fold_conv("inc.double_conv.0", "inc.double_conv.1", 1, 64, wf, bias);  // [co][t][ci=1] == [64][9]
+        L.w_f32 = upload_f32(wf);
+        L.bias = upload_f32(bias);
+        L.flops_per_slice = 2.0 * H_ * W_ * 64 * 9;
+        flops_ += L.flops_per_slice;
+        layers_.push_back(L);
+    }
+    add_conv("enc1b", "inc.double_conv.3", "inc.double_conv.4", 0, 64, 64, e1a, cat1, 0, p1, false);
+    const int enc_src[4] = {p1, p2, p3, p4}, enc_mid[4] = {e2a, e3a, e4a, ba}, enc_dst[4] = {cat2, cat3, cat4, bb};
+    const int enc_pool[4] = {p2, p3, p4, -1};
+    static const char* enc_a[4] = {"enc2a", "enc3a", "enc4a", "bott_a"};
+    static const char* enc_b[4] = {"enc2b", "enc3b", "enc4b", "bott_b"};
+    for (int i = 0; i < 4; ++i) {
+        const int cin = 64 << i, cout = 128 << i;
+        const std::string pre = "down" + std::to_string(i + 1) + ".maxpool_conv.1.double_conv";
+        add_conv(enc_a[i], pre + ".0", pre + ".1", i + 1, cin, cout, enc_src[i], enc_mid[i], 0, -1, false);
+        add_conv(enc_b[i], pre + ".3", pre + ".4", i + 1, cout, cout, enc_mid[i], enc_dst[i], 0, enc_pool[i], false);
+    }
+    const int up_src[4] = {bb, d4b, d3b, d2b}, up_cat[4] = {cat4, cat3, cat2, cat1}, dec_mid[4] = {d4a, d3a, d2a, d1a};
+    const int dec_out[4] = {d4b, d3b, d2b, -1};
+    static const char* up_n[4] = {"up4", "up3", "up2", "up1"};
+    static const char* dec_a[4] = {"dec4a", "dec3a", "dec2a", "dec1a"};
+    static const char* dec_b[4] = {"dec4b", "dec3b", "dec2b", "dec1b_head"};
+    for (int i = 0; i < 4; ++i) {
+        const int cin = 1024 >> i, cout = cin / 2, level = 3 - i;
+        const std::string pre = "up" + std::to_string(i + 1);
+        add_convt(up_n[i], pre + ".up", level + 1, cin, cout, up_src[i], up_cat[i], cout);
+        add_conv(dec_a[i], pre + ".conv.double_conv.0", pre + ".conv.double_conv.1", level, cin, cout, up_cat[i], dec_mid[i], 0, -1, false);
+        add_conv(dec_b[i], pre + ".conv.double_conv.3", pre + ".conv.double_conv.4", level, cout, cout, dec_mid[i], dec_out[i], 0, -1, i == 3);
+    }
+    {   // 1x1 head (fp32, applied in the dec1b epilogue)
+        const float* w = blob.get("outc.conv.weight", (size_t)n_classes_ * 64);
+        const float* b = blob.get("outc.conv.bias", n_classes_);
+        head_w_ = upload_f32(std::vector<float>(w, w + (size_t)n_classes_ * 64));
+        head_b_ = upload_f32(std::vector<float>(b, b + n_classes_));
+        n_params_ += (int64_t)n_classes_ * 64 + n_classes_;
+        flops_ += 2.0 * H_ * W_ * 64 * n_classes_;
+    }
+    loaded_ = true;
+}
+
+void UNet::run_layer(int li, const uint8_t* d_in_u8, int batch, uint8_t* d_mask, float* d_logits, cudaStream_t st) {
+    MS_REQUIRE(loaded_, MS_ERR_STATE, "UNet weights not loaded");
+    MS_REQUIRE(li >= 0 && li < (int)layers_.size(), MS_ERR_ARG, "layer index out of range");
+    MS_REQUIRE(batch >= 1 && batch <= max_batch_, MS_ERR_ARG, "batch exceeds max_batch");
+    const UNetLayer& L = layers_[li];
+    const int h = H_ >> L.level, w = W_ >> L.level;
+    if (L.kind == 0) {
+        const size_t threads = (size_t)batch * h * w * 8;
+        first_conv_kernel<<<(unsigned)cdiv64((int64_t)threads, 256), 256, 0, st>>>(d_in_u8, h, w, batch, L.w_f32, L.bias, bufs_[L.dst].p);
+        MS_LAUNCH_CHECK();
+        return;
+    }
+    tc::ConvArgs a{};
+    a.H = h; a.W = w; a.batch = batch; a.Cin = L.Cin; a.taps = L.taps; a.n_total = L.n_total; a.Cout = L.Cout; a.bias = L.bias;
+    if (L.dst >= 0) { a.out = bufs_[L.dst].p; a.out_cstride = bufs_[L.dst].C; a.out_coff = L.dst_coff; }
+    if (L.pool_dst >= 0) { a.pool = bufs_[L.pool_dst].p; a.pool_cstride = bufs_[L.pool_dst].C; }
+    a.head_w = head_w_; a.head_b = head_b_; a.n_classes = n_classes_; a.fg_value = fg_value_;
+    a.mask = d_mask ? d_mask : scratch_mask_.as<uint8_t>();
+    a.logits = d_logits;
+    if (naive_) {
+        const __nv_bfloat16* src = bufs_[L.src].p;
+        if (L.kind == 3) {
+            const size_t npix = (size_t)batch * h * w;
+            naive_head_conv_kernel<<<(unsigned)cdiv64((int64_t)npix, 128), 128, 0, st>>>(src, L.w, a);
+            MS_LAUNCH_CHECK();
+        } else {
+            const size_t total = (size_t)batch * h * w * L.n_total;
+            naive_gemm_conv_kernel<<<(unsigned)cdiv64((int64_t)total, 256), 256, 0, st>>>(src, bufs_[L.src].C, L.w, a,
+                                                                                         L.kind == 2 ? tc::EPI_CONVT : tc::EPI_STORE);
+            MS_LAUNCH_CHECK();
+            if (L.pool_dst >= 0) {
+                const size_t pt = (size_t)batch * (h / 2) * (w / 2) * L.Cout;
+                naive_pool_kernel<<<(unsigned)cdiv64((int64_t)pt, 256), 256, 0, st>>>(a.out + a.out_coff, a.out_cstride, h, w, L.Cout, batch, a.pool);
+                MS_LAUNCH_CHECK();
+            }
+        }
+        return;
+    }
+    if (L.kind == 3) {
+        launch_tc<64, tc::EPI_HEAD>(L, a, sm_count_, st);
+    } else if (L.kind == 2) {
+        if (L.block_n == 256) launch_tc<256, tc::EPI_CONVT>(L, a, sm_count_, st);
+        else if (L.block_n == 128) launch_tc<128, tc::EPI_CONVT>(L, a, sm_count_, st);
+        else launch_tc<64, tc::EPI_CONVT>(L, a, sm_count_, st);
+    } else {
+        if (L.block_n == 256) launch_tc<256, tc::EPI_STORE>(L, a, sm_count_, st);
+        else if (L.block_n == 128) launch_tc<128, tc::EPI_STORE>(L, a, sm_count_, st);
+        else launch_tc<64, tc::EPI_STORE>(L, a, sm_count_, st);
+    }
+}
+
+void UNet::forward(const uint8_t* d_in_u8, int batch, uint8_t* d_mask, float* d_logits, cudaStream_t st) {
+    for (int i = 0; i < (int)layers_.size(); ++i) run_layer(i, d_in_u8, batch, d_mask, d_logits, st);
+}
+
+}  // namespace ms

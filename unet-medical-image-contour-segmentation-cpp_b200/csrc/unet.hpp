@@ -1,0 +1,65 @@
+// unet.hpp -- the UNet forward ("process" stage) as a table of tcgen05 implicit-GEMM launches.
+#pragma once
+#include <cuda.h>
+#include <string>
+#include <vector>
+#include "common.cuh"
+
+namespace ms {
+
+struct UNetLayer {
+    std::string name;        // enc1a, enc1b, ..., up4, dec4a, ..., dec1b_head
+    int kind = 0;            // 0 = direct first conv (Cin = 1), 1 = conv3x3, 2 = ConvT 2x2 s2, 3 = conv3x3 + head
+    int level = 0;           // pixel grid of the GEMM rows: (H >> level) x (W >> level)
+    int Cin = 0, Cout = 0;
+    int taps = 9;
+    int n_total = 0;         // GEMM N
+    int block_n = 0;
+    int src = -1, dst = -1, pool_dst = -1;   // activation buffer ids
+    int dst_coff = 0;
+    __nv_bfloat16* w = nullptr;  // device [n_total][taps * Cin] bf16 (kinds 1..3)
+    float* w_f32 = nullptr;      // device [64][9] fp32 (kind 0)
+    float* bias = nullptr;       // device [Cout] fp32
+    CUtensorMap map_a, map_b;
+    double flops_per_slice = 0;  // 2 * MAC
+};
+
+struct ActBuf {
+    std::string name;
+    int level = 0, C = 0;
+    __nv_bfloat16* p = nullptr;
+};
+
+class UNet {
+  public:
+    ~UNet();
+    // Loads a MSEGW001 blob, folds BN, converts to bf16 K-major, builds buffers and tensor maps.
+    void load(const std::string& blob_path, int net_h, int net_w, int n_classes_cfg, int max_batch, int fg_value, int sm_count);
+    bool loaded() const { return loaded_; }
+    void forward(const uint8_t* d_in_u8, int batch, uint8_t* d_mask, float* d_logits, cudaStream_t st);
+    void run_layer(int li, const uint8_t* d_in_u8, int batch, uint8_t* d_mask, float* d_logits, cudaStream_t st);
+    const std::vector<UNetLayer>& layers() const { return layers_; }
+    const std::vector<ActBuf>& buffers() const { return bufs_; }
+    int n_classes() const { return n_classes_; }
+    int64_t n_params() const { return n_params_; }
+    double flops_per_slice() const { return flops_; }
+    int net_h() const { return H_; }
+    int net_w() const { return W_; }
+    int max_batch() const { return max_batch_; }
+    uint8_t* scratch_mask() { return scratch_mask_.as<uint8_t>(); }
+
+  private:
+    bool loaded_ = false;
+    int H_ = 0, W_ = 0, n_classes_ = 0, max_batch_ = 0, fg_value_ = 2, sm_count_ = 148;
+    bool naive_ = false;  // MEDSEG_NAIVE_CONV=1: CUDA-core reference kernels (debug / validation only)
+    int64_t n_params_ = 0;
+    double flops_ = 0;
+    std::vector<UNetLayer> layers_;
+    std::vector<ActBuf> bufs_;
+    std::vector<void*> allocs_;
+    float* head_w_ = nullptr;
+    float* head_b_ = nullptr;
+    DevBuf scratch_mask_;
+};
+
+}  // namespace ms

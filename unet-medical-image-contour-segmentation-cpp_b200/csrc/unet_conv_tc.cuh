@@ -1,0 +1,393 @@
+// unet_conv_tc.cuh -- implicit-GEMM convolution on tcgen05 / TMEM, fed by TMA (sm_100a).
+//
+// This is the dense contraction of the UNet forward that the reference runs inside an opaque
+// TensorRT engine (/root/reference/src/process.cpp:94,147).  One persistent, warp-specialised
+// kernel serves every GEMM-shaped layer of the network:
+//
+//   conv3x3 (pad 1) + folded BN + ReLU   M = pixels, N = Cout, K = 9 * Cin     (18 layers)
+//   ConvTranspose2d(k=2, s=2) + bias     M = input pixels, N = 4 * Cout, K = Cin  (4 layers)
+//
+// Data layout: activations NHWC bf16; weights [N][K] bf16, K-major, K = tap * Cin + ci.
+//
+// Tiling: one CTA tile = 16 (x) x 8 (y) output pixels = 128 GEMM rows, BLOCK_N output channels.
+//   A operand : for every (tap, 64-channel chunk) ONE 4-D TMA box {64 ch, 16 px, 8 rows, 1 image}
+//               at the tap's (dx, dy) shift.  TMA zero-fills out-of-bounds pixels, which *is* the
+//               conv's zero padding -- im2col never exists in memory.  The box lands as 128 rows of
+//               128 B with the 128-byte swizzle = the canonical K-major SW128 UMMA operand.
+//   B operand : 2-D TMA box {64 k, BLOCK_N rows}, same swizzle.
+//   D         : fp32 accumulators in TMEM, 128 lanes x BLOCK_N columns, double buffered
+//               (2 x BLOCK_N columns) so the epilogue of tile i overlaps the MMAs of tile i+1.
+//
+// Warp roles (192 threads): warp 0 = TMA producer (one lane), warp 1 = TMEM allocator + MMA issuer
+// (one lane issues tcgen05.mma / tcgen05.commit), warps 2..5 = epilogue (TMEM lane quarter =
+// warp_id % 4).  Pipelines: smem full/empty ring (TMA <-> MMA) and TMEM full/empty (MMA <-> epilogue).
+//
+// Epilogues (template EPI):
+//   EPI_STORE : + bias, ReLU, bf16, NHWC store at a channel offset / stride (so encoder outputs are
+//               written straight into the decoder's concat buffer -- torch.cat never runs), and an
+//               optional fused 2x2 max-pool: the 16x8 tile puts every 2x2 window inside one warp
+//               (lanes l, l^1, l^16, l^17), so the pool is two shuffles.
+//   EPI_CONVT : + bias, bf16, scatter to (2y+dy, 2x+dx) of the up-sampled image at the concat
+//               buffer's channel offset (transposed conv fused with the skip concat).
+//   EPI_HEAD  : + bias, ReLU, then the 1x1 head (64 -> n_classes) on the fp32 accumulators in
+//               registers, first-max argmax (src/process.cpp:158-170) or `logit > 0`; the last
+//               feature map never touches HBM.
+#pragma once
+#include <cuda.h>
+#include "common.cuh"
+
+namespace ms {
+namespace tc {
+
+constexpr int BLOCK_M = 128;
+constexpr int TILE_W = 16, TILE_H = 8;
+constexpr int BLOCK_K = 64;   // bf16 elements = 128 bytes = one swizzle row
+constexpr int UMMA_K = 16;
+constexpr int NUM_THREADS = 192;
+constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;  // 16 KiB
+
+enum Epi { EPI_STORE = 0, EPI_CONVT = 1, EPI_HEAD = 2 };
+
+struct ConvArgs {
+    int H, W, batch;        // pixel grid of the GEMM rows (input grid for ConvT)
+    int Cin, taps;          // taps = 9 (conv3x3) or 1 (ConvT)
+    int n_total;            // GEMM N: Cout, or 4 * Cout for ConvT
+    int Cout;               // bias length / channel modulus
+    const float* bias;      // [Cout] fp32
+    __nv_bfloat16* out;     // NHWC destination (may be null for EPI_HEAD)
+    int out_cstride, out_coff;
+    __nv_bfloat16* pool;    // optional pooled destination (EPI_STORE), channel stride pool_cstride
+    int pool_cstride;
+    const float* head_w;    // [n_classes][64]
+    const float* head_b;    // [n_classes]
+    int n_classes;          // 1 = binary head (logit > 0), else argmax over n_classes
+    int fg_value;           // value written by the binary head
+    uint8_t* mask;          // [batch][H][W]
+    float* logits;          // optional [batch][n_classes][H][W]
+};
+
+template <int BLOCK_N>
+struct Cfg {
+    static constexpr int B_STAGE_BYTES = BLOCK_N * BLOCK_K * 2;
+    static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
+    static constexpr int STAGES = (BLOCK_N == 256) ? 4 : (BLOCK_N == 128 ? 6 : 8);
+    static constexpr int TMEM_COLS = 2 * BLOCK_N < 32 ? 32 : 2 * BLOCK_N;  // 128 / 256 / 512: powers of two
+    static constexpr int AUX_BYTES = 4096;  // barriers, tmem pointer, head weights
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + AUX_BYTES + 1024;  // + alignment slack
+};
+
+// ------------------------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra WAIT_DONE;\n\t"
+        "bra WAIT_LOOP;\n\t"
+        "WAIT_DONE:\n\t"
+        "}" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* m) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");
+}
+
+__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+        : "memory");
+}
+
+// K-major, 128-byte swizzle, rows of 128 B, 8-row groups 1024 B apart (SBO = 64 x 16 B), LBO unused (1),
+// descriptor version 1 (sm_100), layout type 2 = SWIZZLE_128B.
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+// kind::f16 instruction descriptor: D = f32, A = B = bf16, both K-major, M = 128, N = BLOCK_N.
+__host__ __device__ constexpr uint32_t make_idesc(int n) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BLOCK_M >> 4) << 24);
+}
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
+    __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+    return *reinterpret_cast<uint32_t*>(&v);
+}
+__device__ __forceinline__ uint32_t max_bf16x2(uint32_t a, uint32_t b) {
+    __nv_bfloat162 r = __hmax2(*reinterpret_cast<__nv_bfloat162*>(&a), *reinterpret_cast<__nv_bfloat162*>(&b));
+    return *reinterpret_cast<uint32_t*>(&r);
+}
+
+struct TileCoord {
+    int b, y0, x0, n0;
+};
+__device__ __forceinline__ TileCoord decode_tile(int t, int n_tiles, int tiles_x, int tiles_y, int block_n) {
+    TileCoord c;
+    const int n_idx = t % n_tiles;
+    int m = t / n_tiles;
+    c.x0 = (m % tiles_x) * TILE_W;
+    m /= tiles_x;
+    c.y0 = (m % tiles_y) * TILE_H;
+    c.b = m / tiles_y;
+    c.n0 = n_idx * block_n;
+    return c;
+}
+
+// ------------------------------------------------------------------------------------ the kernel
+template <int BLOCK_N, int EPI>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const ConvArgs args) {
+    using C = Cfg<BLOCK_N>;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* aux = smem + C::STAGES * C::STAGE_BYTES;
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(aux);
+    uint64_t* empty_bar = full_bar + C::STAGES;
+    uint64_t* tmem_full = empty_bar + C::STAGES;
+    uint64_t* tmem_empty = tmem_full + 2;
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+    float* s_head = reinterpret_cast<float*>(aux + 512);  // [n_classes][64] weights then [n_classes] bias
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int tiles_x = args.W / TILE_W, tiles_y = args.H / TILE_H;
+    const int n_tiles = args.n_total / BLOCK_N;
+    const int total = args.batch * tiles_y * tiles_x * n_tiles;
+    const int kchunks = args.Cin / BLOCK_K;
+    const int ksteps = args.taps * kchunks;
+
+    if (threadIdx.x == 0) {
+        prefetch_tmap(&map_a);
+        prefetch_tmap(&map_b);
+        for (int i = 0; i < C::STAGES; ++i) {
+            mbar_init(&full_bar[i], 1);
+            mbar_init(&empty_bar[i], 1);
+        }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&tmem_full[i], 1);
+            mbar_init(&tmem_empty[i], 128);
+        }
+        fence_barrier_init();
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)), "n"(C::TMEM_COLS)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    if (EPI == EPI_HEAD) {
+        for (int i = threadIdx.x; i < args.n_classes * 64 + args.n_classes; i += NUM_THREADS)
+            s_head[i] = i < args.n_classes * 64 ? args.head_w[i] : args.head_b[i - args.n_classes * 64];
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
+
+    if (warp == 0) {
+        // ===================================================================== TMA producer
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int t = blockIdx.x; t < total; t += gridDim.x) {
+                const TileCoord tc = decode_tile(t, n_tiles, tiles_x, tiles_y, BLOCK_N);
+                for (int tap = 0; tap < args.taps; ++tap) {
+                    const int dy = args.taps == 9 ? tap / 3 - 1 : 0;
+                    const int dx = args.taps == 9 ? tap % 3 - 1 : 0;
+                    for (int kc = 0; kc < kchunks; ++kc) {
+                        mbar_wait(&empty_bar[stage], phase ^ 1);
+                        uint8_t* sa = smem + stage * C::STAGE_BYTES;
+                        uint8_t* sb = sa + A_STAGE_BYTES;
+                        mbar_expect_tx(&full_bar[stage], C::STAGE_BYTES);
+                        tma_load_4d(sa, &map_a, &full_bar[stage], kc * BLOCK_K, tc.x0 + dx, tc.y0 + dy, tc.b);
+                        tma_load_2d(sb, &map_b, &full_bar[stage], tap * args.Cin + kc * BLOCK_K, tc.n0);
+                        if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================================================================== MMA issuer
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc(BLOCK_N);
+            int stage = 0;
+            uint32_t phase = 0;
+            int acc = 0;
+            uint32_t acc_phase = 0;
+            for (int t = blockIdx.x; t < total; t += gridDim.x) {
+                mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BLOCK_N);
+                for (int ks = 0; ks < ksteps; ++ks) {
+                    mbar_wait(&full_bar[stage], phase);
+                    tc_fence_after();
+                    const uint32_t sa = smem_u32(smem + stage * C::STAGE_BYTES);
+                    const uint64_t adesc = make_smem_desc(sa);
+                    const uint64_t bdesc = make_smem_desc(sa + A_STAGE_BYTES);
+#pragma unroll
+                    for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+                        // advance 16 elements = 32 bytes along K inside the swizzle atom: +2 in 16-byte units
+                        umma_f16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (ks | k) != 0 ? 1u : 0u);
+                    }
+                    umma_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
+                    if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+                }
+                umma_commit(&tmem_full[acc]);        // accumulator complete -> epilogue
+                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            }
+        }
+    } else {
+        // ===================================================================== epilogue (warps 2..5)
+        const int quarter = warp & 3;           // TMEM lane quarter this warp may access
+        const int row = quarter * 32 + lane;    // GEMM row inside the tile = pixel
+        const int ly = row / TILE_W, lx = row % TILE_W;
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        for (int t = blockIdx.x; t < total; t += gridDim.x) {
+            const TileCoord tcd = decode_tile(t, n_tiles, tiles_x, tiles_y, BLOCK_N);
+            const int y = tcd.y0 + ly, x = tcd.x0 + lx;
+            mbar_wait(&tmem_full[acc], acc_phase);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BLOCK_N);
+
+            if (EPI == EPI_HEAD) {
+                // BLOCK_N == 64: the whole feature vector of this pixel
+                uint32_t r0[32], r1[32];
+                tmem_ld32(taddr, r0);
+                tmem_ld32(taddr + 32, r1);
+                tmem_ld_wait();
+                tc_fence_before();
+                mbar_arrive(&tmem_empty[acc]);
+                float f[64];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    f[j] = fmaxf(__uint_as_float(r0[j]) + __ldg(args.bias + j), 0.0f);
+                    f[32 + j] = fmaxf(__uint_as_float(r1[j]) + __ldg(args.bias + 32 + j), 0.0f);
+                }
+                const size_t pix = ((size_t)tcd.b * args.H + y) * args.W + x;
+                const size_t plane = (size_t)args.H * args.W;
+                float best = -3.402823466e+38f;  // -FLT_MAX, src/process.cpp:159
+                int best_c = 0;
+                for (int c = 0; c < args.n_classes; ++c) {
+                    float s = s_head[args.n_classes * 64 + c];
+#pragma unroll
+                    for (int j = 0; j < 64; ++j) s = fmaf(f[j], s_head[c * 64 + j], s);
+                    if (args.logits) args.logits[((size_t)tcd.b * args.n_classes + c) * plane + (size_t)y * args.W + x] = s;
+                    if (s > best) { best = s; best_c = c; }   // strict >: first max wins, NaN never wins
+                }
+                args.mask[pix] = args.n_classes == 1 ? (uint8_t)(best > 0.0f ? args.fg_value : 0) : (uint8_t)best_c;
+            } else {
+                size_t out_base;
+                if (EPI == EPI_STORE) out_base = (((size_t)tcd.b * args.H + y) * args.W + x) * args.out_cstride + args.out_coff;
+#pragma unroll 1
+                for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+                    uint32_t r[32];
+                    tmem_ld32(taddr + c0, r);
+                    tmem_ld_wait();
+                    if (c0 + 32 >= BLOCK_N) {  // last chunk read: hand the accumulator back to the MMA warp
+                        tc_fence_before();
+                        mbar_arrive(&tmem_empty[acc]);
+                    }
+                    const int col = tcd.n0 + c0;           // first GEMM column of this chunk
+                    const int co = col % args.Cout;        // 32-aligned, never straddles Cout
+                    uint32_t pk[16];
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        float a = __uint_as_float(r[2 * j]) + __ldg(args.bias + co + 2 * j);
+                        float b = __uint_as_float(r[2 * j + 1]) + __ldg(args.bias + co + 2 * j + 1);
+                        if (EPI == EPI_STORE) { a = fmaxf(a, 0.0f); b = fmaxf(b, 0.0f); }
+                        pk[j] = pack_bf16(a, b);
+                    }
+                    __nv_bfloat16* dst;
+                    if (EPI == EPI_STORE) {
+                        dst = args.out + out_base + col;
+                    } else {  // EPI_CONVT: column block (dy, dx) -> pixel (2y+dy, 2x+dx) of the 2H x 2W image
+                        const int q = col / args.Cout;
+                        const int oy = 2 * y + (q >> 1), ox = 2 * x + (q & 1);
+                        dst = args.out + (((size_t)tcd.b * (2 * args.H) + oy) * (2 * args.W) + ox) * args.out_cstride + args.out_coff + co;
+                    }
+                    uint4* d4 = reinterpret_cast<uint4*>(dst);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) d4[j] = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+                    if (EPI == EPI_STORE && args.pool) {
+                        // 2x2 max-pool inside the warp: lanes l, l^1 (x pair), l^16 (y pair)
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) {
+                            uint32_t v = pk[j];
+                            v = max_bf16x2(v, __shfl_xor_sync(0xFFFFFFFFu, v, 1));
+                            v = max_bf16x2(v, __shfl_xor_sync(0xFFFFFFFFu, v, 16));
+                            pk[j] = v;
+                        }
+                        if ((lane & 17) == 0) {
+                            uint4* p4 = reinterpret_cast<uint4*>(args.pool + (((size_t)tcd.b * (args.H / 2) + (y >> 1)) * (args.W / 2) + (x >> 1)) * args.pool_cstride + col);
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) p4[j] = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+                        }
+                    }
+                }
+            }
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        __syncwarp();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(C::TMEM_COLS) : "memory");
+    }
+}
+
+}  // namespace tc
+}  // namespace ms
