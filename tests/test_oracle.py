@@ -1,0 +1,174 @@
+"""CPU suite, part 1: the oracle itself, pinned against the committed golden vectors, and the
+OpenCV-free restatements (plain-C oracle, host build of the device trace code) pinned against cv2."""
+import ctypes
+import hashlib
+import json
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, contours_equal
+from oracle import pipeline as op
+import cases
+
+GOLD = os.path.join(ROOT, "tests", "golden")
+
+
+def _run_contours(fn, mask, thr=127):
+    H, W = mask.shape
+    cap, capc = 4 * H * W + 16, H * W + 1
+    xy = np.zeros(cap * 2, np.int32)
+    cs = np.zeros(capc + 1, np.int32)
+    npts = ctypes.c_int64(0)
+    mask = np.ascontiguousarray(mask)
+    nc = fn(mask.ctypes.data_as(ctypes.c_void_p), H, W, thr, xy.ctypes.data_as(ctypes.c_void_p), ctypes.c_int64(cap),
+            cs.ctypes.data_as(ctypes.c_void_p), capc, ctypes.byref(npts))
+    assert nc >= 0
+    return [xy[2 * cs[i]:2 * cs[i + 1]].reshape(-1, 2) for i in range(nc)]
+
+
+def golden_contours():
+    z = np.load(os.path.join(GOLD, "contours_small.npz"))
+    for i in range(int(z["n"])):
+        h, w = z[f"shape_{i}"]
+        m = np.unpackbits(z[f"bits_{i}"])[:h * w].reshape(h, w).astype(np.uint8) * 255
+        lens = z[f"len_{i}"]
+        xy = z[f"xy_{i}"].astype(np.int32)
+        offs = np.concatenate([[0], np.cumsum(lens)])
+        yield m, [xy[offs[k]:offs[k + 1]] for k in range(len(lens))]
+
+
+def test_oracle_contours_match_golden():
+    n = 0
+    for m, want in golden_contours():
+        assert contours_equal(op.extract_contours(m), want)
+        n += 1
+    assert n == 31
+
+
+def test_golden_inputs_reproducible():
+    masks = cases.contour_case_masks()
+    for (m, _), m2 in zip(golden_contours(), masks):
+        assert (m == m2).all()
+
+
+def test_known_answers():
+    # rectangle -> TL, BL, BR, TR ; 5-px line -> 2 endpoints ; plus sign -> 12 vertices
+    m = np.zeros((8, 8), np.uint8); m[2:6, 2:6] = 255
+    assert op.extract_contours(m)[0].tolist() == [[2, 2], [2, 5], [5, 5], [5, 2]]
+    m = np.zeros((7, 7), np.uint8); m[3, 1:6] = 255
+    assert op.extract_contours(m)[0].tolist() == [[1, 3], [5, 3]]
+    m = np.zeros((7, 7), np.uint8); m[1:6, 3] = 255; m[3, 1:6] = 255
+    assert len(op.extract_contours(m)[0]) == 12
+    m = np.zeros((3, 3), np.uint8); m[1, 1] = 255
+    assert op.extract_contours(m)[0].tolist() == [[1, 1]]
+    m = np.zeros((3, 3), np.uint8); m[1, 1] = 127
+    assert op.extract_contours(m) == []          # threshold(127): 127 -> 0, 128 -> 255
+    m[1, 1] = 128
+    assert len(op.extract_contours(m)) == 1
+
+
+def test_c_oracle_contours(oracle_c):
+    for m, want in golden_contours():
+        assert contours_equal(_run_contours(oracle_c.orc_find_contours, m), want)
+
+
+def _random_masks(n, seed):
+    rng = np.random.default_rng(seed)
+    for it in range(n):
+        H, W = int(rng.integers(1, 48)), int(rng.integers(1, 48))
+        k = it % 5
+        if k == 0:
+            m = rng.random((H, W)) < rng.random()
+        elif k == 1:
+            m = np.zeros((H, W), bool)
+            for q in range(0, min(H, W) // 2, 2):
+                m[q:H - q, q:W - q] = (q // 2) % 2 == 0
+            m ^= rng.random((H, W)) < 0.05
+        elif k == 2:
+            m = np.ones((H, W), bool)
+            m[rng.random((H, W)) < 0.1] = 0
+        elif k == 3:
+            m = rng.random((H, W)) < 0.08
+        else:
+            f = rng.random((H, W))
+            f = (f + np.roll(f, 1, 0) + np.roll(f, 1, 1) + np.roll(f, -1, 0) + np.roll(f, -1, 1)) / 5
+            m = f > 0.5
+        yield m.astype(np.uint8) * 255
+
+
+def test_c_oracle_and_hostsim_trace_vs_cv2(oracle_c):
+    """Pins the closed form and the exact device trace code against cv2."""
+    so = os.path.join(ROOT, "tests", "hostsim", "libtrace_sim.so")
+    subprocess.run(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-o", so,
+                    os.path.join(ROOT, "tests", "hostsim", "trace_sim.cpp")], check=True)
+    sim = ctypes.CDLL(so)
+    total = 0
+    for m in _random_masks(1500, 11):
+        want = op.extract_contours(m)
+        assert contours_equal(_run_contours(oracle_c.orc_find_contours, m), want)
+        assert contours_equal(_run_contours(sim.sim_find_contours, m), want)
+        total += len(want)
+    assert total > 5000
+
+
+def test_oracle_postprocess_golden(oracle_c):
+    z = np.load(os.path.join(GOLD, "postprocess_small.npz"))
+    for i in range(int(z["n"])):
+        h, w = z[f"shape_{i}"]
+        m = z[f"in_{i}"]
+        want = np.unpackbits(z[f"out_{i}"])[:h * w].reshape(h, w).astype(np.uint8) * 2
+        assert (op.postprocess_mask(m) == want).all()
+        out = np.zeros_like(m)
+        mc = np.ascontiguousarray(m)
+        oracle_c.orc_postprocess(mc.ctypes.data_as(ctypes.c_void_p), out.ctypes.data_as(ctypes.c_void_p), int(h), int(w), 2,
+                                 ctypes.c_float(0.06))
+        assert (out == want).all()
+
+
+def test_min_area_thresholds():
+    # int(w*h*0.06f) = 15,728 / 62,914 / 251,658
+    assert [op._min_area(s, s) for s in (512, 1024, 2048)] == [15728, 62914, 251658]
+
+
+def test_oracle_preprocess_golden(oracle_c):
+    with open(os.path.join(GOLD, "preprocess_hashes.json")) as f:
+        want = json.load(f)
+    for name, src in cases.preprocess_cases().items():
+        got = op.preprocess_raw(src)
+        assert hashlib.sha256(got.tobytes()).hexdigest() == want[name], name
+        out = np.zeros((512, 512), np.uint8)
+        s = np.ascontiguousarray(src)
+        oracle_c.orc_preprocess(s.ctypes.data_as(ctypes.c_void_p), s.shape[1], s.shape[0], 512, 512, out.ctypes.data_as(ctypes.c_void_p))
+        assert (out == got).all(), name
+
+
+def test_argmax_first_max_and_nan(oracle_c):
+    lg = np.zeros((3, 2, 2), np.float32)
+    lg[:, 0, 0] = [1, 1, 0]          # tie -> lowest index
+    lg[:, 0, 1] = [0, 2, 2]          # tie -> 1
+    lg[:, 1, 0] = [np.nan, np.nan, np.nan]   # NaN never wins -> 0
+    lg[:, 1, 1] = [-1, -2, 5]
+    assert op.argmax_first3(lg).tolist() == [[0, 1], [0, 2]]
+    out = np.zeros(4, np.uint8)
+    l2 = np.ascontiguousarray(lg.reshape(3, 4))
+    oracle_c.orc_argmax(l2.ctypes.data_as(ctypes.c_void_p), 3, ctypes.c_size_t(4), out.ctypes.data_as(ctypes.c_void_p))
+    assert out.tolist() == [0, 1, 0, 2]
+
+
+def test_oracle_json_matches_nlohmann_golden():
+    for name, (base, w, h, contours) in cases.json_cases().items():
+        with open(os.path.join(GOLD, f"labelme_{name}.json"), "rb") as f:
+            want = f.read().decode()
+        got = op.generate_json([np.array(c, np.int32).reshape(-1, 2) for c in contours], base, w, h)
+        assert got == want, name
+    with open(os.path.join(GOLD, "sidecar_slice_007.json")) as f:
+        assert op.sidecar_json_text("slice_007.raw", 600, 400) == f.read()
+
+
+def test_map_points_truncates():
+    c = [np.array([[3, 5], [511, 511]], np.int32)]
+    m = op.map_contour_points(c, 600 / 512, 400 / 512)
+    assert m[0].tolist() == [[3, 3], [598, 399]]

@@ -1,0 +1,326 @@
+"""medseg_b200 -- host-side mirror of the reference's stage API over libmedseg_b200.so.
+
+The reference is compiled C++ (its host side lives in csrc/facade.cpp with the reference's own
+namespaces); this Python module is the same interface for tests and bench.py, bound with ctypes to
+the C ABI declared in include/medseg_b200.h.  Stage names follow the reference:
+
+    initialize  -> MedicalSeg::initialize_engine      (/root/reference/src/initialize.cpp:26)
+    preprocess  -> Preprocess::preprocess_raw         (src/preprocess.cpp:76)
+    process     -> MedicalSeg::execute_inference      (src/process.cpp:123)   [UNet + head]
+    postprocess -> postprocess_mask                   (src/postprocess.cpp:47)
+    mask2polygon-> Mask2Polygon::extract_contours + map_contour_points (src/mask2polygon.cpp:29,41)
+    cleanup     -> MedicalSeg::cleanup_resources      (src/cleanup.cpp:10)
+
+There is no CPU fallback: if the shared library is missing, or no sm_100 GPU is present, every call
+raises.  (The directory name contains '-', so import it through the `medseg_b200` shim at the
+repository root.)
+"""
+from __future__ import annotations
+
+import ctypes as C
+import json
+import os
+import subprocess
+from typing import List, Optional, Sequence
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libmedseg_b200.so")
+CSRC = os.path.join(_HERE, "csrc")
+
+MS_OK, MS_ERR_ARG, MS_ERR_IO, MS_ERR_FORMAT, MS_ERR_CUDA, MS_ERR_CAPACITY, MS_ERR_STATE, MS_ERR_INTERNAL = 0, -1, -2, -3, -4, -5, -6, -7
+
+
+class MedsegError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"[{code}] {msg}")
+        self.code = code
+
+
+class ms_info(C.Structure):
+    _fields_ = [("device", C.c_int32), ("sm_count", C.c_int32), ("net_h", C.c_int32), ("net_w", C.c_int32),
+                ("n_classes", C.c_int32), ("max_batch", C.c_int32), ("foreground_value", C.c_int32),
+                ("min_area_ratio", C.c_float), ("has_weights", C.c_int32), ("n_params", C.c_int64),
+                ("flops_per_slice", C.c_int64)]
+
+
+class ms_polygons(C.Structure):
+    _fields_ = [("xy", C.c_void_p), ("cap_points", C.c_int64), ("contour_start", C.c_void_p), ("cap_contours", C.c_int64),
+                ("slice_start", C.c_void_p), ("n_points", C.c_int64), ("n_contours", C.c_int64)]
+
+
+# every symbol include/medseg_b200.h declares: name -> (restype, argtypes)
+_P, _I, _L = C.c_void_p, C.c_int, C.c_int64
+ABI = {
+    "ms_init": (_I, [C.c_char_p, C.c_char_p, C.POINTER(_P)]),
+    "ms_init_json": (_I, [C.c_char_p, C.c_char_p, C.POINTER(_P)]),
+    "ms_destroy": (None, [_P]),
+    "ms_last_error": (C.c_char_p, [_P]),
+    "ms_get_info": (_I, [_P, C.POINTER(ms_info)]),
+    "ms_alloc_pinned": (_P, [C.c_size_t]),
+    "ms_free_pinned": (None, [_P]),
+    "ms_preprocess_dev": (_I, [_P, _P, _I, _I, _I, _P, _P, _P]),
+    "ms_preprocess_host": (_I, [_P, _P, _I, _I, _I, _P]),
+    "ms_unet_forward_dev": (_I, [_P, _P, _I, _P, _P, _P]),
+    "ms_unet_forward_host": (_I, [_P, _P, _I, _P, _P]),
+    "ms_postprocess_dev": (_I, [_P, _P, _P, _I, _I, _I, _I, _P]),
+    "ms_postprocess_host": (_I, [_P, _P, _P, _I, _I, _I, _I]),
+    "ms_mask2polygon_host": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, C.POINTER(ms_polygons)]),
+    "ms_mask2polygon_dev": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, C.POINTER(ms_polygons), _P]),
+    "ms_process_batch_host": (_I, [_P, _P, _I, _I, _I, C.POINTER(ms_polygons), _P, _P]),
+    "ms_process_batch_dev": (_I, [_P, _P, _I, _I, _I, C.POINTER(_L), C.POINTER(_L), _P]),
+    "ms_process_raw_file": (_I, [_P, C.c_char_p, _I, _I, C.c_char_p]),
+    "ms_polygons_to_json": (_L, [_P, _P, _I, C.c_char_p, _I, _I, _P, _L]),
+    "ms_launch_count": (_L, [_P]),
+    "ms_time_layer": (_I, [_P, _I, _I, _I, C.POINTER(C.c_float), C.POINTER(C.c_double)]),
+    "ms_layer_count": (_I, [_P]),
+    "ms_layer_name": (C.c_char_p, [_P, _I]),
+    "ms_debug_read_activation": (_L, [_P, C.c_char_p, _I, _P, _L]),
+}
+
+_lib_cache = None
+
+
+def build(verbose: bool = False) -> str:
+    """Compile libmedseg_b200.so in-tree (nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo)."""
+    r = subprocess.run(["make", "-C", CSRC, "-j8"], capture_output=True, text=True)
+    if verbose or r.returncode != 0:
+        print(r.stdout[-4000:], r.stderr[-4000:])
+    if r.returncode != 0:
+        raise RuntimeError("building libmedseg_b200.so failed")
+    return LIB_PATH
+
+
+def lib() -> C.CDLL:
+    """The loaded shared library with typed entry points.  Fails loudly when it is missing."""
+    global _lib_cache
+    if _lib_cache is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                              "(there is no CPU fallback)")
+        l = C.CDLL(LIB_PATH)
+        for name, (res, args) in ABI.items():
+            fn = getattr(l, name)  # AttributeError if the symbol is not exported
+            fn.restype, fn.argtypes = res, args
+        _lib_cache = l
+    return _lib_cache
+
+
+def _ptr(a) -> int:
+    if a is None:
+        return 0
+    if isinstance(a, np.ndarray):
+        return a.ctypes.data
+    return int(a)
+
+
+def _u8(a, name) -> np.ndarray:
+    a = np.ascontiguousarray(a)
+    if a.dtype != np.uint8:
+        raise TypeError(f"{name} must be uint8")
+    return a
+
+
+class Polygons:
+    """CSR polygon set as returned by the C ABI, plus list-of-arrays views."""
+
+    def __init__(self, xy: np.ndarray, contour_start: np.ndarray, slice_start: np.ndarray):
+        self.xy, self.contour_start, self.slice_start = xy, contour_start, slice_start
+
+    @property
+    def n_contours(self) -> int:
+        return int(self.slice_start[-1])
+
+    @property
+    def n_points(self) -> int:
+        return int(self.contour_start[self.n_contours])
+
+    def slice(self, s: int) -> List[np.ndarray]:
+        a, b = int(self.slice_start[s]), int(self.slice_start[s + 1])
+        return [self.xy[self.contour_start[c]:self.contour_start[c + 1]] for c in range(a, b)]
+
+    def per_slice(self) -> List[List[np.ndarray]]:
+        return [self.slice(s) for s in range(len(self.slice_start) - 1)]
+
+
+class Engine:
+    """One handle = one GPU.  `source` is a config dict, a path to a config JSON or weight blob, or
+    None for a stage-only handle (no UNet)."""
+
+    def __init__(self, source=None, log_dir: Optional[str] = None):
+        self._l = lib()
+        self._h = _P()
+        ld = log_dir.encode() if log_dir else None
+        if isinstance(source, dict):
+            rc = self._l.ms_init_json(json.dumps(source).encode(), ld, C.byref(self._h))
+        else:
+            rc = self._l.ms_init(source.encode() if source else None, ld, C.byref(self._h))
+        if rc != MS_OK:
+            self._h = _P()
+            raise MedsegError(rc, self._l.ms_last_error(None).decode(errors="replace"))
+        inf = ms_info()
+        self._l.ms_get_info(self._h, C.byref(inf))
+        self.info = inf
+        self._cap_pts, self._cap_cnt = 1 << 16, 1 << 10
+
+    # reference-style names
+    initialize = classmethod(lambda cls, engine_path, log_dir=None: cls(engine_path, log_dir))
+
+    def _check(self, rc: int):
+        if rc != MS_OK:
+            raise MedsegError(rc, self._l.ms_last_error(self._h).decode(errors="replace"))
+
+    def cleanup(self):
+        if self._h:
+            self._l.ms_destroy(self._h)
+            self._h = _P()
+
+    close = cleanup
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.cleanup()
+
+    def __del__(self):
+        try:
+            self.cleanup()
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------ stages (host buffers)
+    def preprocess(self, src_u16: np.ndarray) -> np.ndarray:
+        src = np.ascontiguousarray(src_u16)
+        if src.dtype != np.uint16:
+            raise TypeError("src must be uint16")
+        if src.ndim == 2:
+            src = src[None]
+        b, h, w = src.shape
+        out = np.empty((b, self.info.net_h, self.info.net_w), np.uint8)
+        self._check(self._l.ms_preprocess_host(self._h, _ptr(src), w, h, b, _ptr(out)))
+        return out
+
+    def process(self, norm_u8: np.ndarray, want_logits: bool = False):
+        """UNet forward + head: u8 [B,H,W] -> class mask u8 [B,H,W] (and fp32 logits [B,C,H,W])."""
+        x = _u8(norm_u8, "norm")
+        if x.ndim == 2:
+            x = x[None]
+        b = x.shape[0]
+        mask = np.empty_like(x)
+        logits = np.empty((b, self.info.n_classes, x.shape[1], x.shape[2]), np.float32) if want_logits else None
+        self._check(self._l.ms_unet_forward_host(self._h, _ptr(x), b, _ptr(mask), _ptr(logits)))
+        return (mask, logits) if want_logits else mask
+
+    def postprocess(self, mask: np.ndarray, fg_value: int = 0) -> np.ndarray:
+        m = _u8(mask, "mask")
+        squeeze = m.ndim == 2
+        if squeeze:
+            m = m[None]
+        out = np.empty_like(m)
+        self._check(self._l.ms_postprocess_host(self._h, _ptr(m), _ptr(out), m.shape[1], m.shape[2], m.shape[0], fg_value))
+        return out[0] if squeeze else out
+
+    def _poly_call(self, call, batch: int) -> Polygons:
+        while True:
+            xy = np.empty((self._cap_pts, 2), np.int32)
+            cs = np.empty(self._cap_cnt + 1, np.int32)
+            ss = np.empty(batch + 1, np.int32)
+            pg = ms_polygons(_ptr(xy), self._cap_pts, _ptr(cs), self._cap_cnt, _ptr(ss), 0, 0)
+            rc = call(C.byref(pg))
+            if rc == MS_ERR_CAPACITY and (pg.n_points > self._cap_pts or pg.n_contours > self._cap_cnt):
+                self._cap_pts = max(self._cap_pts, int(pg.n_points) + 16)
+                self._cap_cnt = max(self._cap_cnt, int(pg.n_contours) + 16)
+                continue
+            self._check(rc)
+            return Polygons(xy[:pg.n_points], cs[:pg.n_contours + 1], ss)
+
+    def mask2polygon(self, mask: np.ndarray, threshold: int = 127, orig_w: Optional[int] = None,
+                     orig_h: Optional[int] = None) -> Polygons:
+        m = _u8(mask, "mask")
+        if m.ndim == 2:
+            m = m[None]
+        b, h, w = m.shape
+        ow, oh = orig_w or w, orig_h or h
+        return self._poly_call(lambda pg: self._l.ms_mask2polygon_host(self._h, _ptr(m), h, w, b, threshold, ow, oh, pg), b)
+
+    def process_batch(self, src_u16: np.ndarray, want_norm: bool = False, want_mask: bool = False):
+        """RAW u16 slices [B,h,w] -> polygons in original coordinates (the whole per-slice path)."""
+        src = src_u16 if isinstance(src_u16, np.ndarray) and src_u16.flags.c_contiguous else np.ascontiguousarray(src_u16)
+        if src.dtype != np.uint16:
+            raise TypeError("src must be uint16")
+        if src.ndim == 2:
+            src = src[None]
+        b, h, w = src.shape
+        norm = np.empty((b, self.info.net_h, self.info.net_w), np.uint8) if want_norm else None
+        mask = np.empty((b, self.info.net_h, self.info.net_w), np.uint8) if want_mask else None
+        polys = self._poly_call(
+            lambda pg: self._l.ms_process_batch_host(self._h, _ptr(src), w, h, b, pg, _ptr(norm), _ptr(mask)), b)
+        return polys, norm, mask
+
+    def process_raw_file(self, raw_path: str, w: int, h: int, out_dir: str) -> None:
+        self._check(self._l.ms_process_raw_file(self._h, raw_path.encode(), w, h, out_dir.encode()))
+
+    # ------------------------------------------------------------------ device-pointer entry points
+    def preprocess_dev(self, d_src: int, w: int, h: int, batch: int, d_out_u8: int, d_out_bf16: int = 0, stream: int = 0):
+        self._check(self._l.ms_preprocess_dev(self._h, d_src, w, h, batch, d_out_u8, d_out_bf16 or None, stream or None))
+
+    def unet_forward_dev(self, d_in: int, batch: int, d_mask: int, d_logits: int = 0, stream: int = 0):
+        self._check(self._l.ms_unet_forward_dev(self._h, d_in, batch, d_mask, d_logits or None, stream or None))
+
+    def postprocess_dev(self, d_in: int, d_out: int, h: int, w: int, batch: int, fg_value: int = 0, stream: int = 0):
+        self._check(self._l.ms_postprocess_dev(self._h, d_in, d_out, h, w, batch, fg_value, stream or None))
+
+    def process_batch_dev(self, d_src: int, w: int, h: int, batch: int, stream: int = 0):
+        npts, ncnt = _L(0), _L(0)
+        self._check(self._l.ms_process_batch_dev(self._h, d_src, w, h, batch, C.byref(npts), C.byref(ncnt), stream or None))
+        return npts.value, ncnt.value
+
+    def mask2polygon_dev(self, d_mask: int, h: int, w: int, batch: int, threshold: int = 127, stream: int = 0) -> Polygons:
+        return self._poly_call(
+            lambda pg: self._l.ms_mask2polygon_dev(self._h, d_mask, h, w, batch, threshold, w, h, pg, stream or None), batch)
+
+    # ------------------------------------------------------------------ instrumentation
+    def launch_count(self) -> int:
+        return int(self._l.ms_launch_count(self._h))
+
+    def layer_names(self) -> List[str]:
+        return [self._l.ms_layer_name(self._h, i).decode() for i in range(self._l.ms_layer_count(self._h))]
+
+    def time_layer(self, layer: int, batch: int, iters: int = 20):
+        ms, fl = C.c_float(0), C.c_double(0)
+        self._check(self._l.ms_time_layer(self._h, layer, batch, iters, C.byref(ms), C.byref(fl)))
+        return ms.value, fl.value
+
+    def read_activation(self, name: str, batch: int) -> np.ndarray:
+        n = self._l.ms_debug_read_activation(self._h, name.encode(), batch, None, 0)
+        if n < 0:
+            self._check(int(n))
+        out = np.empty(n, np.float32)
+        n2 = self._l.ms_debug_read_activation(self._h, name.encode(), batch, _ptr(out), n)
+        if n2 < 0:
+            self._check(int(n2))
+        return out
+
+
+def polygons_to_json(contours: Sequence[np.ndarray], base_name: str, orig_w: int, orig_h: int) -> str:
+    """Byte-exact text of Mask2Polygon::generate_json (src/mask2polygon.cpp:68-109).  Pure host code."""
+    l = lib()
+    cs = np.zeros(len(contours) + 1, np.int32)
+    for i, c in enumerate(contours):
+        cs[i + 1] = cs[i] + len(c)
+    xy = np.ascontiguousarray(np.concatenate([np.asarray(c, np.int32).reshape(-1, 2) for c in contours])
+                              if len(contours) else np.zeros((0, 2), np.int32))
+    n = l.ms_polygons_to_json(_ptr(xy), _ptr(cs), len(contours), base_name.encode(), orig_w, orig_h, None, 0)
+    if n < 0:
+        raise MedsegError(int(n), "ms_polygons_to_json failed")
+    buf = C.create_string_buffer(n)
+    l.ms_polygons_to_json(_ptr(xy), _ptr(cs), len(contours), base_name.encode(), orig_w, orig_h, C.addressof(buf), n)
+    return buf.raw.decode()
+
+
+def make_weight_blob(path: str, n_classes: int = 3, seed: int = 1234) -> str:
+    from . import weights as W
+    W.save_blob(path, W.make_weights(seed, n_classes), n_classes)
+    return path
