@@ -27,39 +27,56 @@ namespace ms {
 namespace {
 
 // ------------------------------------------------------------------ first conv (Cin = 1): direct
-// One thread = one pixel x 8 output channels -> one 16-byte NHWC store; a warp covers 4 pixels x 64 ch
-// = 512 contiguous bytes.  x = float(u8) / 255.0f exactly as src/process.cpp:38.
-__global__ void __launch_bounds__(256) first_conv_kernel(const uint8_t* __restrict__ in, int H, int W, int batch,
+// K = 9 is pure bandwidth (SURVEY.md hard part H5), so this layer stays on the CUDA cores.  One block =
+// one image row.  The three input rows are staged once in shared memory as x = float(u8) / 255.0f
+// (exactly src/process.cpp:38); every thread keeps the 9 x 8 weights of its 8 output channels in
+// registers and walks the row 4 pixels at a time, so the inner loop is FMAs and 16-byte NHWC stores
+// (a warp writes four fully used 128-byte lines per store instruction).
+__global__ void __launch_bounds__(256) first_conv_kernel(const uint8_t* __restrict__ in, int H, int W,
                                                           const float* __restrict__ w /*[64][9]*/, const float* __restrict__ bias,
                                                           __nv_bfloat16* __restrict__ out /*NHWC 64*/) {
+    extern __shared__ float srow[];           // [3][W + 2], column 0 <-> x = -1
     __shared__ float sw[64 * 9 + 64];
+    const int y = blockIdx.x % H;
+    const size_t img = (size_t)(blockIdx.x / H) * H * W;
+    const int pitch = W + 2;
     for (int i = threadIdx.x; i < 64 * 9 + 64; i += 256) sw[i] = i < 576 ? w[i] : bias[i - 576];
+    for (int i = threadIdx.x; i < 3 * pitch; i += 256) {
+        const int r = i / pitch, c = i % pitch;
+        const int yy = y + r - 1, xx = c - 1;
+        srow[i] = (yy >= 0 && yy < H && xx >= 0 && xx < W) ? __fdiv_rn((float)in[img + (size_t)yy * W + xx], 255.0f) : 0.0f;
+    }
     __syncthreads();
-    const size_t gid = (size_t)blockIdx.x * 256 + threadIdx.x;
-    const size_t npix = (size_t)batch * H * W;
-    const size_t pix = gid >> 3;
-    if (pix >= npix) return;
-    const int cg = (int)(gid & 7) * 8;
-    const int x = (int)(pix % W), y = (int)((pix / W) % H);
-    const uint8_t* img = in + (pix / ((size_t)H * W)) * (size_t)H * W;
-    float v[9];
+    const int cg = (threadIdx.x & 7) * 8, g = threadIdx.x >> 3;
+    float wr[8][9], br[8];
 #pragma unroll
-    for (int t = 0; t < 9; ++t) {
-        const int yy = y + t / 3 - 1, xx = x + t % 3 - 1;
-        v[t] = (yy >= 0 && yy < H && xx >= 0 && xx < W) ? __fdiv_rn((float)img[(size_t)yy * W + xx], 255.0f) : 0.0f;
+    for (int j = 0; j < 8; ++j) {
+        br[j] = sw[576 + cg + j];
+#pragma unroll
+        for (int t = 0; t < 9; ++t) wr[j][t] = sw[(cg + j) * 9 + t];
     }
-    uint32_t pk[4];
+    for (int x0 = g * 4; x0 < W; x0 += 128) {
+        float v[3][6];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        float a = sw[576 + cg + 2 * j], b = sw[576 + cg + 2 * j + 1];
+        for (int r = 0; r < 3; ++r)
 #pragma unroll
-        for (int t = 0; t < 9; ++t) {
-            a = fmaf(v[t], sw[(cg + 2 * j) * 9 + t], a);
-            b = fmaf(v[t], sw[(cg + 2 * j + 1) * 9 + t], b);
+            for (int c = 0; c < 6; ++c) v[r][c] = srow[r * pitch + x0 + c];
+#pragma unroll
+        for (int p = 0; p < 4; ++p) {
+            uint32_t pk[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                float a = br[2 * j], b = br[2 * j + 1];
+#pragma unroll
+                for (int t = 0; t < 9; ++t) {
+                    a = fmaf(v[t / 3][p + t % 3], wr[2 * j][t], a);
+                    b = fmaf(v[t / 3][p + t % 3], wr[2 * j + 1][t], b);
+                }
+                pk[j] = tc::pack_bf16(fmaxf(a, 0.0f), fmaxf(b, 0.0f));
+            }
+            *reinterpret_cast<uint4*>(out + (img + (size_t)y * W + x0 + p) * 64 + cg) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
         }
-        pk[j] = tc::pack_bf16(fmaxf(a, 0.0f), fmaxf(b, 0.0f));
     }
-    *reinterpret_cast<uint4*>(out + pix * 64 + cg) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
 }
 
 // ------------------------------------------------------------------ CUDA-core reference kernels
@@ -151,10 +168,10 @@ EncodeTiledFn encode_fn() {
     return fn;
 }
 // activations [B][H][W][C] bf16, box {64, 16, 8, 1}, 128-byte swizzle, OOB -> zero (= conv padding)
-void make_act_map(CUtensorMap* m, const __nv_bfloat16* base, int B, int H, int W, int C) {
+void make_act_map(CUtensorMap* m, const __nv_bfloat16* base, int B, int H, int W, int C, int box_w = tc::TILE_W, int box_h = tc::TILE_H) {
     cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
     cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
-    cuuint32_t box[4] = {(cuuint32_t)tc::BLOCK_K, (cuuint32_t)tc::TILE_W, (cuuint32_t)tc::TILE_H, 1};
+    cuuint32_t box[4] = {(cuuint32_t)tc::BLOCK_K, (cuuint32_t)box_w, (cuuint32_t)box_h, 1};
     cuuint32_t estr[4] = {1, 1, 1, 1};
     CUresult r = encode_fn()(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<__nv_bfloat16*>(base), dims, strides, box, estr,
                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
@@ -185,6 +202,25 @@ void launch_tc(const UNetLayer& L, const tc::ConvArgs& a, int sm_count, cudaStre
     const int grid = std::min(total, sm_count);
     tc::conv_gemm_kernel<BN, EPI><<<grid, tc::NUM_THREADS, C::SMEM_BYTES, st>>>(L.map_a, L.map_b, a);
     MS_LAUNCH_CHECK();
+}
+
+template <int BN, int EPI, int RKC, int PITCH>
+void launch_halo_p(const UNetLayer& L, const tc::ConvArgs& a, int sm_count, cudaStream_t st) {
+    using C = tc::HaloCfg<BN, RKC, PITCH>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        MS_CUDA(cudaFuncSetAttribute(tc::conv_halo_kernel<BN, EPI, RKC, PITCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+        attr_set = true;
+    }
+    const int total = a.batch * (a.H / tc::HALO_TH) * (a.W / tc::HALO_TW);
+    const int grid = std::min(total, sm_count);
+    tc::conv_halo_kernel<BN, EPI, RKC, PITCH><<<grid, tc::NUM_THREADS, C::SMEM_BYTES, st>>>(L.map_a_row, L.map_b, a);
+    MS_LAUNCH_CHECK();
+}
+template <int BN, int EPI, int RKC>
+void launch_halo(const UNetLayer& L, const tc::ConvArgs& a, int sm_count, cudaStream_t st) {
+    if (L.halo_pitch == 16) launch_halo_p<BN, EPI, RKC, 16>(L, a, sm_count, st);
+    else launch_halo_p<BN, EPI, RKC, 10>(L, a, sm_count, st);
 }
 
 struct Blob {
@@ -250,6 +286,12 @@ void UNet::load(const std::string& blob_path, int net_h, int net_w, int n_classe
     H_ = net_h; W_ = net_w; max_batch_ = max_batch; fg_value_ = fg_value; sm_count_ = sm_count;
     const char* nv = std::getenv("MEDSEG_NAIVE_CONV");
     naive_ = nv && nv[0] == '1';
+    const char* hv = std::getenv("MEDSEG_HALO");
+    halo_enabled_ = !(hv && hv[0] == '0');
+    const char* pv = std::getenv("MEDSEG_HALO_PITCH");
+    halo_pitch_ = (pv && std::atoi(pv) == 10) ? 10 : 16;
+    const char* dv = std::getenv("MEDSEG_DESC_MODE");
+    desc_mode_ = dv ? std::atoi(dv) : 0;
     Blob blob = read_blob(blob_path);
     n_classes_ = blob.n_classes;
     MS_REQUIRE(n_classes_cfg <= 0 || n_classes_cfg == n_classes_, MS_ERR_FORMAT, "config n_classes does not match the weight blob");
@@ -319,6 +361,14 @@ void UNet::load(const std::string& blob_path, int net_h, int net_w, int n_classe
         L.flops_per_slice = 2.0 * h * w * (double)cout * 9 * cin;
         make_act_map(&L.map_a, bufs_[src].p, max_batch, h, w, bufs_[src].C);
         make_wgt_map(&L.map_b, L.w, cout, 9 * cin, L.block_n);
+        // halo-stationary kernel for the narrow-N, large-grid layers (kernel 1 is L2-bandwidth bound there)
+        if (halo_enabled_ && cout == L.block_n && L.block_n <= 128 && h % tc::HALO_TH == 0 && w % tc::HALO_TW == 0) {
+            L.halo = 1;
+            const int kc = cin / tc::BLOCK_K;
+            L.resident_kc = (9 * kc * L.block_n * 128 <= 144 * 1024) ? kc : 0;
+            L.halo_pitch = halo_pitch_;
+            make_act_map(&L.map_a_row, bufs_[src].p, max_batch, h, w, bufs_[src].C, tc::HALO_TW + 2, halo_pitch_ == 16 ? 1 : tc::HALO_TH + 2);
+        }
         flops_ += L.flops_per_slice;
         layers_.push_back(L);
     };
@@ -396,8 +446,7 @@ void UNet::run_layer(int li, const uint8_t* d_in_u8, int batch, uint8_t* d_mask,
     const UNetLayer& L = layers_[li];
     const int h = H_ >> L.level, w = W_ >> L.level;
     if (L.kind == 0) {
-        const size_t threads = (size_t)batch * h * w * 8;
-        first_conv_kernel<<<(unsigned)cdiv64((int64_t)threads, 256), 256, 0, st>>>(d_in_u8, h, w, batch, L.w_f32, L.bias, bufs_[L.dst].p);
+        first_conv_kernel<<<(unsigned)(batch * h), 256, 3 * (w + 2) * sizeof(float), st>>>(d_in_u8, h, w, L.w_f32, L.bias, bufs_[L.dst].p);
         MS_LAUNCH_CHECK();
         return;
     }
@@ -408,6 +457,7 @@ void UNet::run_layer(int li, const uint8_t* d_in_u8, int batch, uint8_t* d_mask,
     a.head_w = head_w_; a.head_b = head_b_; a.n_classes = n_classes_; a.fg_value = fg_value_;
     a.mask = d_mask ? d_mask : scratch_mask_.as<uint8_t>();
     a.logits = d_logits;
+    a.desc_mode = desc_mode_;
     if (naive_) {
         const __nv_bfloat16* src = bufs_[L.src].p;
         if (L.kind == 3) {
@@ -427,7 +477,14 @@ void UNet::run_layer(int li, const uint8_t* d_in_u8, int batch, uint8_t* d_mask,
         }
         return;
     }
-    if (L.kind == 3) {
+    if (L.halo) {
+        if (L.kind == 3) launch_halo<64, tc::EPI_HEAD, 1>(L, a, sm_count_, st);
+        else if (L.block_n == 64 && L.resident_kc == 1) launch_halo<64, tc::EPI_STORE, 1>(L, a, sm_count_, st);
+        else if (L.block_n == 64 && L.resident_kc == 2) launch_halo<64, tc::EPI_STORE, 2>(L, a, sm_count_, st);
+        else if (L.block_n == 128 && L.resident_kc == 1) launch_halo<128, tc::EPI_STORE, 1>(L, a, sm_count_, st);
+        else if (L.block_n == 128 && L.resident_kc == 0) launch_halo<128, tc::EPI_STORE, 0>(L, a, sm_count_, st);
+        else fail(MS_ERR_INTERNAL, "no halo kernel instantiation for layer " + L.name);
+    } else if (L.kind == 3) {
         launch_tc<64, tc::EPI_HEAD>(L, a, sm_count_, st);
     } else if (L.kind == 2) {
         if (L.block_n == 256) launch_tc<256, tc::EPI_CONVT>(L, a, sm_count_, st);

@@ -64,6 +64,7 @@ struct ConvArgs {
     int fg_value;           // value written by the binary head
     uint8_t* mask;          // [batch][H][W]
     float* logits;          // optional [batch][n_classes][H][W]
+    int desc_mode;          // halo kernel: 0 = base_offset 0, 1 = base_offset (addr >> 7) & 7 (bring-up switch)
 };
 
 template <int BLOCK_N>
@@ -140,6 +141,15 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
     d |= (uint64_t)2 << 61;
     return d;
 }
+__device__ __forceinline__ uint64_t make_smem_desc_sbo(uint32_t smem_addr, uint32_t sbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(sbo_bytes >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
 // kind::f16 instruction descriptor: D = f32, A = B = bf16, both K-major, M = 128, N = BLOCK_N.
 __host__ __device__ constexpr uint32_t make_idesc(int n) {
     return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BLOCK_M >> 4) << 24);
@@ -179,22 +189,129 @@ __device__ __forceinline__ uint32_t max_bf16x2(uint32_t a, uint32_t b) {
     return *reinterpret_cast<uint32_t*>(&r);
 }
 
+
+// ------------------------------------------------------------------------------------ shared epilogue
+// One epilogue thread owns one GEMM row (= one pixel (y, x) of image b) and walks its BLOCK_N columns in
+// chunks of 32.  TW is the tile width in pixels: lane l of a warp holds pixel (l / TW, l % TW) of the
+// warp's 32-row slab, so the 2x2 pool partners are lanes l^1 and l^TW.
+template <int BLOCK_N, int EPI, int TW>
+__device__ __forceinline__ void epilogue_tile(const ConvArgs& args, const float* s_head, uint32_t taddr, int b, int y, int x, int n0,
+                                              int lane, uint64_t* tmem_empty_bar) {
+    if (EPI == EPI_HEAD) {
+        // BLOCK_N == 64: the whole feature vector of this pixel
+        uint32_t r0[32], r1[32];
+        tmem_ld32(taddr, r0);
+        tmem_ld32(taddr + 32, r1);
+        tmem_ld_wait();
+        tc_fence_before();
+        mbar_arrive(tmem_empty_bar);
+        float f[64];
+        const float4* b4 = reinterpret_cast<const float4*>(args.bias);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const float4 lo = __ldg(b4 + j), hi = __ldg(b4 + 8 + j);
+            f[4 * j + 0] = fmaxf(__uint_as_float(r0[4 * j + 0]) + lo.x, 0.0f);
+            f[4 * j + 1] = fmaxf(__uint_as_float(r0[4 * j + 1]) + lo.y, 0.0f);
+            f[4 * j + 2] = fmaxf(__uint_as_float(r0[4 * j + 2]) + lo.z, 0.0f);
+            f[4 * j + 3] = fmaxf(__uint_as_float(r0[4 * j + 3]) + lo.w, 0.0f);
+            f[32 + 4 * j + 0] = fmaxf(__uint_as_float(r1[4 * j + 0]) + hi.x, 0.0f);
+            f[32 + 4 * j + 1] = fmaxf(__uint_as_float(r1[4 * j + 1]) + hi.y, 0.0f);
+            f[32 + 4 * j + 2] = fmaxf(__uint_as_float(r1[4 * j + 2]) + hi.z, 0.0f);
+            f[32 + 4 * j + 3] = fmaxf(__uint_as_float(r1[4 * j + 3]) + hi.w, 0.0f);
+        }
+        const size_t pix = ((size_t)b * args.H + y) * args.W + x;
+        const size_t plane = (size_t)args.H * args.W;
+        float best = -3.402823466e+38f;  // -FLT_MAX, src/process.cpp:159
+        int best_c = 0;
+        for (int c = 0; c < args.n_classes; ++c) {
+            float s = s_head[args.n_classes * 64 + c];
+#pragma unroll
+            for (int j = 0; j < 64; ++j) s = fmaf(f[j], s_head[c * 64 + j], s);
+            if (args.logits) args.logits[((size_t)b * args.n_classes + c) * plane + (size_t)y * args.W + x] = s;
+            if (s > best) { best = s; best_c = c; }   // strict >: first max wins, NaN never wins
+        }
+        args.mask[pix] = args.n_classes == 1 ? (uint8_t)(best > 0.0f ? args.fg_value : 0) : (uint8_t)best_c;
+    } else {
+        size_t out_base = 0;
+        if (EPI == EPI_STORE) out_base = (((size_t)b * args.H + y) * args.W + x) * args.out_cstride + args.out_coff;
+#pragma unroll 1
+        for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+            uint32_t r[32];
+            tmem_ld32(taddr + c0, r);
+            tmem_ld_wait();
+            if (c0 + 32 >= BLOCK_N) {  // last chunk read: hand the accumulator back to the MMA warp
+                tc_fence_before();
+                mbar_arrive(tmem_empty_bar);
+            }
+            const int col = n0 + c0;               // first GEMM column of this chunk
+            const int co = col % args.Cout;        // 32-aligned, never straddles Cout
+            const float4* b4 = reinterpret_cast<const float4*>(args.bias + co);
+            uint32_t pk[16];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float4 bv = __ldg(b4 + j);
+                float v0 = __uint_as_float(r[4 * j + 0]) + bv.x, v1 = __uint_as_float(r[4 * j + 1]) + bv.y;
+                float v2 = __uint_as_float(r[4 * j + 2]) + bv.z, v3 = __uint_as_float(r[4 * j + 3]) + bv.w;
+                if (EPI == EPI_STORE) { v0 = fmaxf(v0, 0.0f); v1 = fmaxf(v1, 0.0f); v2 = fmaxf(v2, 0.0f); v3 = fmaxf(v3, 0.0f); }
+                pk[2 * j] = pack_bf16(v0, v1);
+                pk[2 * j + 1] = pack_bf16(v2, v3);
+            }
+            __nv_bfloat16* dst;
+            if (EPI == EPI_STORE) {
+                dst = args.out + out_base + col;
+            } else {  // EPI_CONVT: column block (dy, dx) -> pixel (2y+dy, 2x+dx) of the 2H x 2W image
+                const int q = col / args.Cout;
+                const int oy = 2 * y + (q >> 1), ox = 2 * x + (q & 1);
+                dst = args.out + (((size_t)b * (2 * args.H) + oy) * (2 * args.W) + ox) * args.out_cstride + args.out_coff + co;
+            }
+            uint4* d4 = reinterpret_cast<uint4*>(dst);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) d4[j] = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+            if (EPI == EPI_STORE && args.pool) {
+                // 2x2 max-pool inside the warp: lanes l, l^1 (x pair), l^TW (y pair)
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    uint32_t v = pk[j];
+                    v = max_bf16x2(v, __shfl_xor_sync(0xFFFFFFFFu, v, 1));
+                    v = max_bf16x2(v, __shfl_xor_sync(0xFFFFFFFFu, v, TW));
+                    pk[j] = v;
+                }
+                if ((lane & (TW | 1)) == 0) {
+                    uint4* p4 = reinterpret_cast<uint4*>(args.pool + (((size_t)b * (args.H / 2) + (y >> 1)) * (args.W / 2) + (x >> 1)) * args.pool_cstride + col);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) p4[j] = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+                }
+            }
+        }
+    }
+}
+
 struct TileCoord {
     int b, y0, x0, n0;
 };
-__device__ __forceinline__ TileCoord decode_tile(int t, int n_tiles, int tiles_x, int tiles_y, int block_n) {
+__device__ __forceinline__ TileCoord decode_tile(int t, int n_tiles, int tiles_x, int tiles_y, int block_n, int tw, int th) {
     TileCoord c;
     const int n_idx = t % n_tiles;
     int m = t / n_tiles;
-    c.x0 = (m % tiles_x) * TILE_W;
+    c.x0 = (m % tiles_x) * tw;
     m /= tiles_x;
-    c.y0 = (m % tiles_y) * TILE_H;
+    c.y0 = (m % tiles_y) * th;
     c.b = m / tiles_y;
     c.n0 = n_idx * block_n;
     return c;
 }
 
-// ------------------------------------------------------------------------------------ the kernel
+__device__ __forceinline__ void tmem_alloc_warp(uint32_t* slot, uint32_t cols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)), "r"(cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_warp(uint32_t base, uint32_t cols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(base), "r"(cols) : "memory");
+}
+
+// ==================================================================================== kernel 1
+// Per-tap operand streaming: every k-step loads one shifted 16x8-pixel A box and one B box.  Used where
+// N >= 256 keeps the tensor pipe busy per byte fetched (deep layers) and for the ConvT GEMMs (one tap).
 template <int BLOCK_N, int EPI>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const ConvArgs args) {
@@ -229,11 +346,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         }
         fence_barrier_init();
     }
-    if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)), "n"(C::TMEM_COLS)
-                     : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-    }
+    if (warp == 1) tmem_alloc_warp(tmem_ptr, C::TMEM_COLS);
     if (EPI == EPI_HEAD) {
         for (int i = threadIdx.x; i < args.n_classes * 64 + args.n_classes; i += NUM_THREADS)
             s_head[i] = i < args.n_classes * 64 ? args.head_w[i] : args.head_b[i - args.n_classes * 64];
@@ -249,7 +362,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             int stage = 0;
             uint32_t phase = 0;
             for (int t = blockIdx.x; t < total; t += gridDim.x) {
-                const TileCoord tc = decode_tile(t, n_tiles, tiles_x, tiles_y, BLOCK_N);
+                const TileCoord tc = decode_tile(t, n_tiles, tiles_x, tiles_y, BLOCK_N, TILE_W, TILE_H);
                 for (int tap = 0; tap < args.taps; ++tap) {
                     const int dy = args.taps == 9 ? tap / 3 - 1 : 0;
                     const int dx = args.taps == 9 ? tap % 3 - 1 : 0;
@@ -303,88 +416,11 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         int acc = 0;
         uint32_t acc_phase = 0;
         for (int t = blockIdx.x; t < total; t += gridDim.x) {
-            const TileCoord tcd = decode_tile(t, n_tiles, tiles_x, tiles_y, BLOCK_N);
-            const int y = tcd.y0 + ly, x = tcd.x0 + lx;
+            const TileCoord tcd = decode_tile(t, n_tiles, tiles_x, tiles_y, BLOCK_N, TILE_W, TILE_H);
             mbar_wait(&tmem_full[acc], acc_phase);
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BLOCK_N);
-
-            if (EPI == EPI_HEAD) {
-                // BLOCK_N == 64: the whole feature vector of this pixel
-                uint32_t r0[32], r1[32];
-                tmem_ld32(taddr, r0);
-                tmem_ld32(taddr + 32, r1);
-                tmem_ld_wait();
-                tc_fence_before();
-                mbar_arrive(&tmem_empty[acc]);
-                float f[64];
-#pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    f[j] = fmaxf(__uint_as_float(r0[j]) + __ldg(args.bias + j), 0.0f);
-                    f[32 + j] = fmaxf(__uint_as_float(r1[j]) + __ldg(args.bias + 32 + j), 0.0f);
-                }
-                const size_t pix = ((size_t)tcd.b * args.H + y) * args.W + x;
-                const size_t plane = (size_t)args.H * args.W;
-                float best = -3.402823466e+38f;  // -FLT_MAX, src/process.cpp:159
-                int best_c = 0;
-                for (int c = 0; c < args.n_classes; ++c) {
-                    float s = s_head[args.n_classes * 64 + c];
-#pragma unroll
-                    for (int j = 0; j < 64; ++j) s = fmaf(f[j], s_head[c * 64 + j], s);
-                    if (args.logits) args.logits[((size_t)tcd.b * args.n_classes + c) * plane + (size_t)y * args.W + x] = s;
-                    if (s > best) { best = s; best_c = c; }   // strict >: first max wins, NaN never wins
-                }
-                args.mask[pix] = args.n_classes == 1 ? (uint8_t)(best > 0.0f ? args.fg_value : 0) : (uint8_t)best_c;
-            } else {
-                size_t out_base;
-                if (EPI == EPI_STORE) out_base = (((size_t)tcd.b * args.H + y) * args.W + x) * args.out_cstride + args.out_coff;
-#pragma unroll 1
-                for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
-                    uint32_t r[32];
-                    tmem_ld32(taddr + c0, r);
-                    tmem_ld_wait();
-                    if (c0 + 32 >= BLOCK_N) {  // last chunk read: hand the accumulator back to the MMA warp
-                        tc_fence_before();
-                        mbar_arrive(&tmem_empty[acc]);
-                    }
-                    const int col = tcd.n0 + c0;           // first GEMM column of this chunk
-                    const int co = col % args.Cout;        // 32-aligned, never straddles Cout
-                    uint32_t pk[16];
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) {
-                        float a = __uint_as_float(r[2 * j]) + __ldg(args.bias + co + 2 * j);
-                        float b = __uint_as_float(r[2 * j + 1]) + __ldg(args.bias + co + 2 * j + 1);
-                        if (EPI == EPI_STORE) { a = fmaxf(a, 0.0f); b = fmaxf(b, 0.0f); }
-                        pk[j] = pack_bf16(a, b);
-                    }
-                    __nv_bfloat16* dst;
-                    if (EPI == EPI_STORE) {
-                        dst = args.out + out_base + col;
-                    } else {  // EPI_CONVT: column block (dy, dx) -> pixel (2y+dy, 2x+dx) of the 2H x 2W image
-                        const int q = col / args.Cout;
-                        const int oy = 2 * y + (q >> 1), ox = 2 * x + (q & 1);
-                        dst = args.out + (((size_t)tcd.b * (2 * args.H) + oy) * (2 * args.W) + ox) * args.out_cstride + args.out_coff + co;
-                    }
-                    uint4* d4 = reinterpret_cast<uint4*>(dst);
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) d4[j] = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
-                    if (EPI == EPI_STORE && args.pool) {
-                        // 2x2 max-pool inside the warp: lanes l, l^1 (x pair), l^16 (y pair)
-#pragma unroll
-                        for (int j = 0; j < 16; ++j) {
-                            uint32_t v = pk[j];
-                            v = max_bf16x2(v, __shfl_xor_sync(0xFFFFFFFFu, v, 1));
-                            v = max_bf16x2(v, __shfl_xor_sync(0xFFFFFFFFu, v, 16));
-                            pk[j] = v;
-                        }
-                        if ((lane & 17) == 0) {
-                            uint4* p4 = reinterpret_cast<uint4*>(args.pool + (((size_t)tcd.b * (args.H / 2) + (y >> 1)) * (args.W / 2) + (x >> 1)) * args.pool_cstride + col);
-#pragma unroll
-                            for (int j = 0; j < 4; ++j) p4[j] = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
-                        }
-                    }
-                }
-            }
+            epilogue_tile<BLOCK_N, EPI, TILE_W>(args, s_head, taddr, tcd.b, tcd.y0 + ly, tcd.x0 + lx, tcd.n0, lane, &tmem_empty[acc]);
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
     }
@@ -393,7 +429,197 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     __syncthreads();
     if (warp == 1) {
         __syncwarp();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(C::TMEM_COLS) : "memory");
+        tmem_dealloc_warp(tmem_base, C::TMEM_COLS);
+    }
+}
+
+// ==================================================================================== kernel 2
+// Halo-stationary conv3x3 for the large-grid, narrow-N layers (levels 0-1: N = 64 / 128), which kernel 1
+// leaves L2-bandwidth bound: it re-fetches the same input pixels for each of the 9 taps.
+// Here one CTA tile is 8 (x) x 16 (y) pixels and, per 64-channel chunk, the (8+2) x (16+2) input halo is
+// loaded ONCE (one TMA box {64 ch, 10 px, 18 rows} = 180 rows of 128 B).  The nine taps are nine UMMA A
+// descriptors into that one buffer, start address shifted by ((dy+1) * 10 + (dx+1)) rows of 128 B: an
+// 8-pixel tile row is exactly one 8-row group and consecutive tile rows are one halo row (1280 B) apart,
+// so SBO = 1280.  The 128-byte swizzle is a function of the absolute shared-memory address bits, which TMA
+// (writer) and UMMA (reader) share, so 128-byte-aligned start addresses need no descriptor base offset
+// (measured on B200: base_offset = 0 is bit-correct, base_offset = (addr >> 7) & 7 is not).  Weights are either resident in shared memory for the whole
+// persistent CTA (RESIDENT_KC = Cin / 64 > 0: all 9 * RESIDENT_KC B tiles, loaded once) or streamed
+// through their own ring (RESIDENT_KC == 0).
+constexpr int HALO_TW = 8, HALO_TH = 16;
+constexpr int HALO_ROWS = HALO_TH + 2;
+constexpr int HALO_BOX_BYTES = HALO_ROWS * (HALO_TW + 2) * 128;  // 23,040 B of pixels per halo tile
+// PITCH = rows of 128 B per halo image row in shared memory:
+//   10 : dense, one TMA box {64, 10, 18} per chunk (SBO = 1280 B)
+//   16 : every halo row starts a fresh 2048 B line group (SBO = 2048 B), 18 row boxes {64, 10, 1} per chunk
+template <int PITCH>
+struct HaloGeom {
+    static constexpr int STAGE_BYTES = (HALO_ROWS * PITCH * 128 + 1023) / 1024 * 1024;
+};
+
+template <int BLOCK_N, int RESIDENT_KC, int PITCH>
+struct HaloCfg {
+    static constexpr int HALO_STAGE_BYTES = HaloGeom<PITCH>::STAGE_BYTES;
+    static constexpr int B_TILE_BYTES = BLOCK_N * BLOCK_K * 2;
+    static constexpr int RES_BYTES = 9 * RESIDENT_KC * B_TILE_BYTES;
+    static constexpr int B_STAGES = RESIDENT_KC > 0 ? 0 : (BLOCK_N == 64 ? 8 : 5);
+    static constexpr int BUDGET = 227 * 1024 - 4096 - 1024;
+    static constexpr int A_STAGES_RAW = (BUDGET - RES_BYTES - B_STAGES * B_TILE_BYTES) / HALO_STAGE_BYTES;
+    static constexpr int A_STAGES = A_STAGES_RAW > 4 ? 4 : A_STAGES_RAW;
+    static constexpr int TMEM_COLS = 2 * BLOCK_N;
+    static constexpr int SMEM_BYTES = RES_BYTES + B_STAGES * B_TILE_BYTES + A_STAGES * HALO_STAGE_BYTES + 4096 + 1024;
+    static_assert(A_STAGES >= 2, "halo kernel needs at least two A stages");
+};
+
+template <int BLOCK_N, int EPI, int RESIDENT_KC, int PITCH>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+conv_halo_kernel(const __grid_constant__ CUtensorMap map_a_row, const __grid_constant__ CUtensorMap map_b, const ConvArgs args) {
+    using C = HaloCfg<BLOCK_N, RESIDENT_KC, PITCH>;
+    constexpr int HALO_STAGE_BYTES = C::HALO_STAGE_BYTES;
+    constexpr int HALO_PITCH = PITCH;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* s_res = smem;                                            // resident weights (or nothing)
+    uint8_t* s_b = smem + C::RES_BYTES;                               // streamed B ring
+    uint8_t* s_a = s_b + C::B_STAGES * C::B_TILE_BYTES;               // halo ring
+    uint8_t* aux = s_a + C::A_STAGES * HALO_STAGE_BYTES;
+    uint64_t* a_full = reinterpret_cast<uint64_t*>(aux);
+    uint64_t* a_empty = a_full + 4;
+    uint64_t* b_full = a_empty + 4;
+    uint64_t* b_empty = b_full + 8;
+    uint64_t* res_full = b_empty + 8;
+    uint64_t* tmem_full = res_full + 1;
+    uint64_t* tmem_empty = tmem_full + 2;
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+    float* s_head = reinterpret_cast<float*>(aux + 512);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int tiles_x = args.W / HALO_TW, tiles_y = args.H / HALO_TH;
+    const int total = args.batch * tiles_y * tiles_x;                 // n_total == BLOCK_N
+    const int kchunks = args.Cin / BLOCK_K;
+
+    if (threadIdx.x == 0) {
+        prefetch_tmap(&map_a_row);
+        prefetch_tmap(&map_b);
+        for (int i = 0; i < 4; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
+        for (int i = 0; i < 8; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
+        mbar_init(res_full, 1);
+        for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 128); }
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc_warp(tmem_ptr, C::TMEM_COLS);
+    if (EPI == EPI_HEAD) {
+        for (int i = threadIdx.x; i < args.n_classes * 64 + args.n_classes; i += NUM_THREADS)
+            s_head[i] = i < args.n_classes * 64 ? args.head_w[i] : args.head_b[i - args.n_classes * 64];
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
+
+    if (warp == 0) {
+        // ===================================================================== TMA producer
+        if (lane == 0 && blockIdx.x < total) {
+            if (RESIDENT_KC > 0) {   // all weights of the layer, once per CTA: tile index = tap * kchunks + kc
+                mbar_expect_tx(res_full, C::RES_BYTES);
+                for (int i = 0; i < 9 * RESIDENT_KC; ++i)
+                    tma_load_2d(s_res + i * C::B_TILE_BYTES, &map_b, res_full, (i / RESIDENT_KC) * args.Cin + (i % RESIDENT_KC) * BLOCK_K, 0);
+            }
+            int sa = 0, sb = 0;
+            uint32_t pa = 0, pb = 0;
+            for (int t = blockIdx.x; t < total; t += gridDim.x) {
+                const TileCoord tc = decode_tile(t, 1, tiles_x, tiles_y, BLOCK_N, HALO_TW, HALO_TH);
+                for (int kc = 0; kc < kchunks; ++kc) {
+                    mbar_wait(&a_empty[sa], pa ^ 1);
+                    uint8_t* dst = s_a + sa * HALO_STAGE_BYTES;
+                    mbar_expect_tx(&a_full[sa], HALO_BOX_BYTES);
+                    if (PITCH == HALO_TW + 2) {
+                        tma_load_4d(dst, &map_a_row, &a_full[sa], kc * BLOCK_K, tc.x0 - 1, tc.y0 - 1, tc.b);
+                    } else {
+                        for (int r = 0; r < HALO_ROWS; ++r)
+                            tma_load_4d(dst + r * HALO_PITCH * 128, &map_a_row, &a_full[sa], kc * BLOCK_K, tc.x0 - 1, tc.y0 - 1 + r, tc.b);
+                    }
+                    if (++sa == C::A_STAGES) { sa = 0; pa ^= 1; }
+                    if (RESIDENT_KC == 0) {
+                        for (int tap = 0; tap < 9; ++tap) {
+                            mbar_wait(&b_empty[sb], pb ^ 1);
+                            mbar_expect_tx(&b_full[sb], C::B_TILE_BYTES);
+                            tma_load_2d(s_b + sb * C::B_TILE_BYTES, &map_b, &b_full[sb], tap * args.Cin + kc * BLOCK_K, 0);
+                            if (++sb == C::B_STAGES) { sb = 0; pb ^= 1; }
+                        }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================================================================== MMA issuer
+        if (lane == 0 && blockIdx.x < total) {
+            constexpr uint32_t idesc = make_idesc(BLOCK_N);
+            int sa = 0, sb = 0, acc = 0;
+            uint32_t pa = 0, pb = 0, acc_phase = 0;
+            if (RESIDENT_KC > 0) {
+                mbar_wait(res_full, 0);
+                tc_fence_after();
+            }
+            for (int t = blockIdx.x; t < total; t += gridDim.x) {
+                mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BLOCK_N);
+                for (int kc = 0; kc < kchunks; ++kc) {
+                    mbar_wait(&a_full[sa], pa);
+                    tc_fence_after();
+                    const uint32_t a_base = smem_u32(s_a + sa * HALO_STAGE_BYTES);
+#pragma unroll 1
+                    for (int tap = 0; tap < 9; ++tap) {
+                        uint32_t b_addr;
+                        if (RESIDENT_KC > 0) {
+                            b_addr = smem_u32(s_res + (tap * RESIDENT_KC + kc) * C::B_TILE_BYTES);
+                        } else {
+                            mbar_wait(&b_full[sb], pb);
+                            tc_fence_after();
+                            b_addr = smem_u32(s_b + sb * C::B_TILE_BYTES);
+                        }
+                        // shifted view of the halo buffer: tile row ty lives at halo row ty + (dy+1), column dx+1
+                        const uint32_t a_addr = a_base + (uint32_t)(((tap / 3) * HALO_PITCH + (tap % 3)) * 128);
+                        uint64_t adesc = make_smem_desc_sbo(a_addr, HALO_PITCH * 128);
+                        if (args.desc_mode == 1) adesc |= (uint64_t)((a_addr >> 7) & 7u) << 49;
+                        const uint64_t bdesc = make_smem_desc(b_addr);
+#pragma unroll
+                        for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
+                            umma_f16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kc | tap | k) != 0 ? 1u : 0u);
+                        if (RESIDENT_KC == 0) {
+                            umma_commit(&b_empty[sb]);
+                            if (++sb == C::B_STAGES) { sb = 0; pb ^= 1; }
+                        }
+                    }
+                    umma_commit(&a_empty[sa]);
+                    if (++sa == C::A_STAGES) { sa = 0; pa ^= 1; }
+                }
+                umma_commit(&tmem_full[acc]);
+                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            }
+        }
+    } else {
+        // ===================================================================== epilogue (warps 2..5)
+        const int quarter = warp & 3;
+        const int row = quarter * 32 + lane;
+        const int ly = row / HALO_TW, lx = row % HALO_TW;
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        for (int t = blockIdx.x; t < total; t += gridDim.x) {
+            const TileCoord tcd = decode_tile(t, 1, tiles_x, tiles_y, BLOCK_N, HALO_TW, HALO_TH);
+            mbar_wait(&tmem_full[acc], acc_phase);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BLOCK_N);
+            epilogue_tile<BLOCK_N, EPI, HALO_TW>(args, s_head, taddr, tcd.b, tcd.y0 + ly, tcd.x0 + lx, 0, lane, &tmem_empty[acc]);
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        __syncwarp();
+        tmem_dealloc_warp(tmem_base, C::TMEM_COLS);
     }
 }
 
