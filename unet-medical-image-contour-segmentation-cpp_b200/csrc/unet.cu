@@ -178,6 +178,21 @@ void make_act_map(CUtensorMap* m, const __nv_bfloat16* base, int B, int H, int W
                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     MS_REQUIRE(r == CUDA_SUCCESS, MS_ERR_CUDA, "cuTensorMapEncodeTiled(activation) failed: " + std::to_string((int)r));
 }
+// destination of EPI_STORE: [B][H][W][C] bf16, box {64 ch, tw px, 32/tw rows, 1} (one epilogue warp's slab)
+void make_out_map(CUtensorMap* m, const __nv_bfloat16* base, int B, int H, int W, int C, int tw) {
+    make_act_map(m, base, B, H, W, C, tw, 32 / tw);
+}
+// destination of EPI_CONVT: the (2H x 2W) image viewed as (C, dx:2, W, dy:2, B*H); box {64, 1, 16, 1, 2}
+void make_convt_out_map(CUtensorMap* m, const __nv_bfloat16* base, int B, int H_in, int W_in, int C) {
+    cuuint64_t dims[5] = {(cuuint64_t)C, 2, (cuuint64_t)W_in, 2, (cuuint64_t)B * H_in};
+    cuuint64_t strides[4] = {(cuuint64_t)C * 2, (cuuint64_t)2 * C * 2, (cuuint64_t)2 * W_in * C * 2, (cuuint64_t)4 * W_in * C * 2};
+    cuuint32_t box[5] = {(cuuint32_t)tc::BLOCK_K, 1, (cuuint32_t)tc::TILE_W, 1, (cuuint32_t)(32 / tc::TILE_W)};
+    cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    CUresult r = encode_fn()(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<__nv_bfloat16*>(base), dims, strides, box, estr,
+                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    MS_REQUIRE(r == CUDA_SUCCESS, MS_ERR_CUDA, "cuTensorMapEncodeTiled(convT output) failed: " + std::to_string((int)r));
+}
 // weights [N][K] bf16, box {64, block_n}
 void make_wgt_map(CUtensorMap* m, const __nv_bfloat16* base, int N, int K, int block_n) {
     cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)N};
@@ -200,7 +215,7 @@ void launch_tc(const UNetLayer& L, const tc::ConvArgs& a, int sm_count, cudaStre
     }
     const int total = a.batch * (a.H / tc::TILE_H) * (a.W / tc::TILE_W) * (a.n_total / BN);
     const int grid = std::min(total, sm_count);
-    tc::conv_gemm_kernel<BN, EPI><<<grid, tc::NUM_THREADS, C::SMEM_BYTES, st>>>(L.map_a, L.map_b, a);
+    tc::conv_gemm_kernel<BN, EPI><<<grid, tc::NUM_THREADS, C::SMEM_BYTES, st>>>(L.map_a, L.map_b, L.map_out, a);
     MS_LAUNCH_CHECK();
 }
 
@@ -214,13 +229,12 @@ void launch_halo_p(const UNetLayer& L, const tc::ConvArgs& a, int sm_count, cuda
     }
     const int total = a.batch * (a.H / tc::HALO_TH) * (a.W / tc::HALO_TW);
     const int grid = std::min(total, sm_count);
-    tc::conv_halo_kernel<BN, EPI, RKC, PITCH><<<grid, tc::NUM_THREADS, C::SMEM_BYTES, st>>>(L.map_a_row, L.map_b, a);
+    tc::conv_halo_kernel<BN, EPI, RKC, PITCH><<<grid, tc::NUM_THREADS, C::SMEM_BYTES, st>>>(L.map_a_row, L.map_b, L.map_out, a);
     MS_LAUNCH_CHECK();
 }
 template <int BN, int EPI, int RKC>
 void launch_halo(const UNetLayer& L, const tc::ConvArgs& a, int sm_count, cudaStream_t st) {
-    if (L.halo_pitch == 16) launch_halo_p<BN, EPI, RKC, 16>(L, a, sm_count, st);
-    else launch_halo_p<BN, EPI, RKC, 10>(L, a, sm_count, st);
+    launch_halo_p<BN, EPI, RKC, 10>(L, a, sm_count, st);   // dense halo box (the 2048-byte pitch variant measured the same)
 }
 
 struct Blob {
@@ -289,7 +303,8 @@ void UNet::load(const std::string& blob_path, int net_h, int net_w, int n_classe
     const char* hv = std::getenv("MEDSEG_HALO");
     halo_enabled_ = !(hv && hv[0] == '0');
     const char* pv = std::getenv("MEDSEG_HALO_PITCH");
-    halo_pitch_ = (pv && std::atoi(pv) == 10) ? 10 : 16;
+    halo_pitch_ = 10;
+    (void)pv;
     const char* dv = std::getenv("MEDSEG_DESC_MODE");
     desc_mode_ = dv ? std::atoi(dv) : 0;
     Blob blob = read_blob(blob_path);
@@ -369,6 +384,8 @@ void UNet::load(const std::string& blob_path, int net_h, int net_w, int n_classe
             L.halo_pitch = halo_pitch_;
             make_act_map(&L.map_a_row, bufs_[src].p, max_batch, h, w, bufs_[src].C, tc::HALO_TW + 2, halo_pitch_ == 16 ? 1 : tc::HALO_TH + 2);
         }
+        if (dst >= 0) make_out_map(&L.map_out, bufs_[dst].p, max_batch, h, w, bufs_[dst].C, L.halo ? tc::HALO_TW : tc::TILE_W);
+        else L.map_out = L.map_b;  // head layer: no bf16 output
         flops_ += L.flops_per_slice;
         layers_.push_back(L);
     };
@@ -389,6 +406,7 @@ void UNet::load(const std::string& blob_path, int net_h, int net_w, int n_classe
         L.flops_per_slice = 2.0 * h * wd * 4.0 * cout * cin;
         make_act_map(&L.map_a, bufs_[src].p, max_batch, h, wd, bufs_[src].C);
         make_wgt_map(&L.map_b, L.w, 4 * cout, cin, L.block_n);
+        make_convt_out_map(&L.map_out, bufs_[dst].p, max_batch, h, wd, bufs_[dst].C);
         n_params_ += (int64_t)cin * cout * 4 + cout;
         flops_ += L.flops_per_slice;
         layers_.push_back(L);

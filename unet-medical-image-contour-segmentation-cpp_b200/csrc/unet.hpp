@@ -21,6 +21,7 @@ struct UNetLayer {
     float* w_f32 = nullptr;      // device [64][9] fp32 (kind 0)
     float* bias = nullptr;       // device [Cout] fp32
     CUtensorMap map_a, map_b;
+    CUtensorMap map_out;         // TMA store of the epilogue (one epilogue warp's 32-pixel x 64-channel slab)
     CUtensorMap map_a_row;       // halo kernel: box {64 ch, 10 px, 18 rows}
     int halo = 0;                // 0 = per-tap streaming kernel, 1 = halo-stationary kernel
     int resident_kc = 0;         // halo kernel: > 0 when all weights stay in shared memory

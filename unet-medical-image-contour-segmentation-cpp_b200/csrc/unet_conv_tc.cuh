@@ -74,7 +74,8 @@ struct Cfg {
     static constexpr int STAGES = (BLOCK_N == 256) ? 4 : (BLOCK_N == 128 ? 6 : 8);
     static constexpr int TMEM_COLS = 2 * BLOCK_N < 32 ? 32 : 2 * BLOCK_N;  // 128 / 256 / 512: powers of two
     static constexpr int AUX_BYTES = 4096;  // barriers, tmem pointer, head weights
-    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + AUX_BYTES + 1024;  // + alignment slack
+    static constexpr int STG_BYTES = 4 * 4096;  // one 4 KiB output staging slab per epilogue warp
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STG_BYTES + AUX_BYTES + 1024;  // + alignment slack
 };
 
 // ------------------------------------------------------------------------------------ PTX wrappers
@@ -128,6 +129,23 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, u
         "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
         ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
         : "memory");
+}
+
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, uint32_t src_smem, int c0, int c1, int c2, int c3) {
+    asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+                 ::"l"(reinterpret_cast<uint64_t>(map)), "r"(src_smem), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_store_5d(const CUtensorMap* map, uint32_t src_smem, int c0, int c1, int c2, int c3, int c4) {
+    asm volatile("cp.async.bulk.tensor.5d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5, %6}], [%1];"
+                 ::"l"(reinterpret_cast<uint64_t>(map)), "r"(src_smem), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
 
 // K-major, 128-byte swizzle, rows of 128 B, 8-row groups 1024 B apart (SBO = 64 x 16 B), LBO unused (1),
@@ -191,12 +209,26 @@ __device__ __forceinline__ uint32_t max_bf16x2(uint32_t a, uint32_t b) {
 
 
 // ------------------------------------------------------------------------------------ shared epilogue
-// One epilogue thread owns one GEMM row (= one pixel (y, x) of image b) and walks its BLOCK_N columns in
-// chunks of 32.  TW is the tile width in pixels: lane l of a warp holds pixel (l / TW, l % TW) of the
-// warp's 32-row slab, so the 2x2 pool partners are lanes l^1 and l^TW.
+// One epilogue thread owns one GEMM row (= one pixel of image b) and walks its BLOCK_N columns 64 at a
+// time.  TW is the tile width in pixels: lane l of a warp holds pixel (l / TW, l % TW) of the warp's
+// 32-row slab (32 / TW tile rows), so the 2x2 pool partners are lanes l^1 and l^TW.
+//
+// Stores: the 32 pixels x 64 channels of a warp (4 KiB) are staged in the warp's own shared-memory slab
+// in the 128-byte-swizzled layout and written with ONE TMA tensor store (full 128-byte lines, channel
+// offset / stride of the concat buffers and the (2y+dy, 2x+dx) scatter of the transposed conv are all
+// in the tensor map), instead of 16-byte stores that each touch 32 different lines.
+struct EpiCtx {
+    const CUtensorMap* map_out;
+    uint32_t slab;       // shared-memory address of this warp's 4 KiB staging slab (1024-aligned)
+    int b, y0, x0, n0;   // tile origin
+    int slab_y;          // first tile row of this warp's slab, relative to y0
+    int y, x;            // this thread's pixel
+    int lane;
+};
+
 template <int BLOCK_N, int EPI, int TW>
-__device__ __forceinline__ void epilogue_tile(const ConvArgs& args, const float* s_head, uint32_t taddr, int b, int y, int x, int n0,
-                                              int lane, uint64_t* tmem_empty_bar) {
+__device__ __forceinline__ void epilogue_tile(const ConvArgs& args, const float* s_head, uint32_t taddr, const EpiCtx& e,
+                                              uint64_t* tmem_empty_bar) {
     if (EPI == EPI_HEAD) {
         // BLOCK_N == 64: the whole feature vector of this pixel
         uint32_t r0[32], r1[32];
@@ -219,7 +251,7 @@ __device__ __forceinline__ void epilogue_tile(const ConvArgs& args, const float*
             f[32 + 4 * j + 2] = fmaxf(__uint_as_float(r1[4 * j + 2]) + hi.z, 0.0f);
             f[32 + 4 * j + 3] = fmaxf(__uint_as_float(r1[4 * j + 3]) + hi.w, 0.0f);
         }
-        const size_t pix = ((size_t)b * args.H + y) * args.W + x;
+        const size_t pix = ((size_t)e.b * args.H + e.y) * args.W + e.x;
         const size_t plane = (size_t)args.H * args.W;
         float best = -3.402823466e+38f;  // -FLT_MAX, src/process.cpp:159
         int best_c = 0;
@@ -227,59 +259,74 @@ __device__ __forceinline__ void epilogue_tile(const ConvArgs& args, const float*
             float s = s_head[args.n_classes * 64 + c];
 #pragma unroll
             for (int j = 0; j < 64; ++j) s = fmaf(f[j], s_head[c * 64 + j], s);
-            if (args.logits) args.logits[((size_t)b * args.n_classes + c) * plane + (size_t)y * args.W + x] = s;
+            if (args.logits) args.logits[((size_t)e.b * args.n_classes + c) * plane + (size_t)e.y * args.W + e.x] = s;
             if (s > best) { best = s; best_c = c; }   // strict >: first max wins, NaN never wins
         }
         args.mask[pix] = args.n_classes == 1 ? (uint8_t)(best > 0.0f ? args.fg_value : 0) : (uint8_t)best_c;
     } else {
-        size_t out_base = 0;
-        if (EPI == EPI_STORE) out_base = (((size_t)b * args.H + y) * args.W + x) * args.out_cstride + args.out_coff;
 #pragma unroll 1
-        for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
-            uint32_t r[32];
-            tmem_ld32(taddr + c0, r);
+        for (int c0 = 0; c0 < BLOCK_N; c0 += 64) {
+            uint32_t r0[32], r1[32];
+            tmem_ld32(taddr + c0, r0);
+            tmem_ld32(taddr + c0 + 32, r1);
             tmem_ld_wait();
-            if (c0 + 32 >= BLOCK_N) {  // last chunk read: hand the accumulator back to the MMA warp
+            if (c0 + 64 >= BLOCK_N) {  // last block read: hand the accumulator back to the MMA warp
                 tc_fence_before();
                 mbar_arrive(tmem_empty_bar);
             }
-            const int col = n0 + c0;               // first GEMM column of this chunk
-            const int co = col % args.Cout;        // 32-aligned, never straddles Cout
+            const int col = e.n0 + c0;             // first GEMM column of this 64-block
+            const int co = col % args.Cout;        // 64-aligned, never straddles Cout
             const float4* b4 = reinterpret_cast<const float4*>(args.bias + co);
-            uint32_t pk[16];
+            uint32_t pk[32];
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-                const float4 bv = __ldg(b4 + j);
-                float v0 = __uint_as_float(r[4 * j + 0]) + bv.x, v1 = __uint_as_float(r[4 * j + 1]) + bv.y;
-                float v2 = __uint_as_float(r[4 * j + 2]) + bv.z, v3 = __uint_as_float(r[4 * j + 3]) + bv.w;
-                if (EPI == EPI_STORE) { v0 = fmaxf(v0, 0.0f); v1 = fmaxf(v1, 0.0f); v2 = fmaxf(v2, 0.0f); v3 = fmaxf(v3, 0.0f); }
+                const float4 lo = __ldg(b4 + j), hi = __ldg(b4 + 8 + j);
+                float v0 = __uint_as_float(r0[4 * j + 0]) + lo.x, v1 = __uint_as_float(r0[4 * j + 1]) + lo.y;
+                float v2 = __uint_as_float(r0[4 * j + 2]) + lo.z, v3 = __uint_as_float(r0[4 * j + 3]) + lo.w;
+                float w0 = __uint_as_float(r1[4 * j + 0]) + hi.x, w1 = __uint_as_float(r1[4 * j + 1]) + hi.y;
+                float w2 = __uint_as_float(r1[4 * j + 2]) + hi.z, w3 = __uint_as_float(r1[4 * j + 3]) + hi.w;
+                if (EPI == EPI_STORE) {
+                    v0 = fmaxf(v0, 0.0f); v1 = fmaxf(v1, 0.0f); v2 = fmaxf(v2, 0.0f); v3 = fmaxf(v3, 0.0f);
+                    w0 = fmaxf(w0, 0.0f); w1 = fmaxf(w1, 0.0f); w2 = fmaxf(w2, 0.0f); w3 = fmaxf(w3, 0.0f);
+                }
                 pk[2 * j] = pack_bf16(v0, v1);
                 pk[2 * j + 1] = pack_bf16(v2, v3);
+                pk[16 + 2 * j] = pack_bf16(w0, w1);
+                pk[16 + 2 * j + 1] = pack_bf16(w2, w3);
             }
-            __nv_bfloat16* dst;
-            if (EPI == EPI_STORE) {
-                dst = args.out + out_base + col;
-            } else {  // EPI_CONVT: column block (dy, dx) -> pixel (2y+dy, 2x+dx) of the 2H x 2W image
-                const int q = col / args.Cout;
-                const int oy = 2 * y + (q >> 1), ox = 2 * x + (q & 1);
-                dst = args.out + (((size_t)b * (2 * args.H) + oy) * (2 * args.W) + ox) * args.out_cstride + args.out_coff + co;
-            }
-            uint4* d4 = reinterpret_cast<uint4*>(dst);
+            // the previous TMA store must have finished reading the slab before it is overwritten
+            if (e.lane == 0) tma_store_wait_read();
+            __syncwarp();
+            const uint32_t row_addr = e.slab + (uint32_t)e.lane * 128u;
 #pragma unroll
-            for (int j = 0; j < 4; ++j) d4[j] = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+            for (int j = 0; j < 8; ++j)   // 16-byte chunk j of row `lane` lives at chunk j ^ (lane & 7)
+                st_shared_v4(row_addr + (uint32_t)((j ^ (e.lane & 7)) << 4), pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (e.lane == 0) {
+                if (EPI == EPI_STORE) {
+                    // box {64 ch, TW px, 32/TW rows, 1 image}
+                    tma_store_4d(e.map_out, e.slab, args.out_coff + col, e.x0, e.y0 + e.slab_y, e.b);
+                } else {
+                    // EPI_CONVT: destination viewed as (C, dx, W, dy, B*H); box {64, 1, TW, 1, 32/TW}
+                    const int q = col / args.Cout;
+                    tma_store_5d(e.map_out, e.slab, args.out_coff + co, q & 1, e.x0, q >> 1, e.b * args.H + e.y0 + e.slab_y);
+                }
+                tma_store_commit();
+            }
             if (EPI == EPI_STORE && args.pool) {
                 // 2x2 max-pool inside the warp: lanes l, l^1 (x pair), l^TW (y pair)
 #pragma unroll
-                for (int j = 0; j < 16; ++j) {
+                for (int j = 0; j < 32; ++j) {
                     uint32_t v = pk[j];
                     v = max_bf16x2(v, __shfl_xor_sync(0xFFFFFFFFu, v, 1));
                     v = max_bf16x2(v, __shfl_xor_sync(0xFFFFFFFFu, v, TW));
                     pk[j] = v;
                 }
-                if ((lane & (TW | 1)) == 0) {
-                    uint4* p4 = reinterpret_cast<uint4*>(args.pool + (((size_t)b * (args.H / 2) + (y >> 1)) * (args.W / 2) + (x >> 1)) * args.pool_cstride + col);
+                if ((e.lane & (TW | 1)) == 0) {
+                    uint4* p4 = reinterpret_cast<uint4*>(args.pool + (((size_t)e.b * (args.H / 2) + (e.y >> 1)) * (args.W / 2) + (e.x >> 1)) * args.pool_cstride + col);
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) p4[j] = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+                    for (int j = 0; j < 8; ++j) p4[j] = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
                 }
             }
         }
@@ -314,11 +361,13 @@ __device__ __forceinline__ void tmem_dealloc_warp(uint32_t base, uint32_t cols) 
 // N >= 256 keeps the tensor pipe busy per byte fetched (deep layers) and for the ConvT GEMMs (one tap).
 template <int BLOCK_N, int EPI>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
-conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const ConvArgs args) {
+conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                 const __grid_constant__ CUtensorMap map_out, const ConvArgs args) {
     using C = Cfg<BLOCK_N>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint8_t* aux = smem + C::STAGES * C::STAGE_BYTES;
+    uint8_t* s_stg = smem + C::STAGES * C::STAGE_BYTES;
+    uint8_t* aux = s_stg + C::STG_BYTES;
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(aux);
     uint64_t* empty_bar = full_bar + C::STAGES;
     uint64_t* tmem_full = empty_bar + C::STAGES;
@@ -336,6 +385,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     if (threadIdx.x == 0) {
         prefetch_tmap(&map_a);
         prefetch_tmap(&map_b);
+        if (EPI != EPI_HEAD) prefetch_tmap(&map_out);
         for (int i = 0; i < C::STAGES; ++i) {
             mbar_init(&full_bar[i], 1);
             mbar_init(&empty_bar[i], 1);
@@ -413,16 +463,23 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         const int quarter = warp & 3;           // TMEM lane quarter this warp may access
         const int row = quarter * 32 + lane;    // GEMM row inside the tile = pixel
         const int ly = row / TILE_W, lx = row % TILE_W;
+        EpiCtx e;
+        e.map_out = &map_out;
+        e.slab = smem_u32(s_stg + quarter * 4096);
+        e.slab_y = quarter * (32 / TILE_W);
+        e.lane = lane;
         int acc = 0;
         uint32_t acc_phase = 0;
         for (int t = blockIdx.x; t < total; t += gridDim.x) {
             const TileCoord tcd = decode_tile(t, n_tiles, tiles_x, tiles_y, BLOCK_N, TILE_W, TILE_H);
+            e.b = tcd.b; e.y0 = tcd.y0; e.x0 = tcd.x0; e.n0 = tcd.n0; e.y = tcd.y0 + ly; e.x = tcd.x0 + lx;
             mbar_wait(&tmem_full[acc], acc_phase);
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BLOCK_N);
-            epilogue_tile<BLOCK_N, EPI, TILE_W>(args, s_head, taddr, tcd.b, tcd.y0 + ly, tcd.x0 + lx, tcd.n0, lane, &tmem_empty[acc]);
+            epilogue_tile<BLOCK_N, EPI, TILE_W>(args, s_head, taddr, e, &tmem_empty[acc]);
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
+        if (EPI != EPI_HEAD && lane == 0) tma_store_wait_read();   // the slab must outlive the last store's read
     }
 
     tc_fence_before();
@@ -462,17 +519,19 @@ struct HaloCfg {
     static constexpr int B_TILE_BYTES = BLOCK_N * BLOCK_K * 2;
     static constexpr int RES_BYTES = 9 * RESIDENT_KC * B_TILE_BYTES;
     static constexpr int B_STAGES = RESIDENT_KC > 0 ? 0 : (BLOCK_N == 64 ? 8 : 5);
-    static constexpr int BUDGET = 227 * 1024 - 4096 - 1024;
+    static constexpr int STG_BYTES = 4 * 4096;  // one 4 KiB output staging slab per epilogue warp
+    static constexpr int BUDGET = 227 * 1024 - 4096 - 1024 - STG_BYTES;
     static constexpr int A_STAGES_RAW = (BUDGET - RES_BYTES - B_STAGES * B_TILE_BYTES) / HALO_STAGE_BYTES;
     static constexpr int A_STAGES = A_STAGES_RAW > 4 ? 4 : A_STAGES_RAW;
     static constexpr int TMEM_COLS = 2 * BLOCK_N;
-    static constexpr int SMEM_BYTES = RES_BYTES + B_STAGES * B_TILE_BYTES + A_STAGES * HALO_STAGE_BYTES + 4096 + 1024;
+    static constexpr int SMEM_BYTES = RES_BYTES + B_STAGES * B_TILE_BYTES + A_STAGES * HALO_STAGE_BYTES + STG_BYTES + 4096 + 1024;
     static_assert(A_STAGES >= 2, "halo kernel needs at least two A stages");
 };
 
 template <int BLOCK_N, int EPI, int RESIDENT_KC, int PITCH>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
-conv_halo_kernel(const __grid_constant__ CUtensorMap map_a_row, const __grid_constant__ CUtensorMap map_b, const ConvArgs args) {
+conv_halo_kernel(const __grid_constant__ CUtensorMap map_a_row, const __grid_constant__ CUtensorMap map_b,
+                 const __grid_constant__ CUtensorMap map_out, const ConvArgs args) {
     using C = HaloCfg<BLOCK_N, RESIDENT_KC, PITCH>;
     constexpr int HALO_STAGE_BYTES = C::HALO_STAGE_BYTES;
     constexpr int HALO_PITCH = PITCH;
@@ -481,7 +540,8 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a_row, const __grid_con
     uint8_t* s_res = smem;                                            // resident weights (or nothing)
     uint8_t* s_b = smem + C::RES_BYTES;                               // streamed B ring
     uint8_t* s_a = s_b + C::B_STAGES * C::B_TILE_BYTES;               // halo ring
-    uint8_t* aux = s_a + C::A_STAGES * HALO_STAGE_BYTES;
+    uint8_t* s_stg = s_a + C::A_STAGES * HALO_STAGE_BYTES;            // output staging slabs
+    uint8_t* aux = s_stg + C::STG_BYTES;
     uint64_t* a_full = reinterpret_cast<uint64_t*>(aux);
     uint64_t* a_empty = a_full + 4;
     uint64_t* b_full = a_empty + 4;
@@ -500,6 +560,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a_row, const __grid_con
     if (threadIdx.x == 0) {
         prefetch_tmap(&map_a_row);
         prefetch_tmap(&map_b);
+        if (EPI != EPI_HEAD) prefetch_tmap(&map_out);
         for (int i = 0; i < 4; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
         for (int i = 0; i < 8; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
         mbar_init(res_full, 1);
@@ -603,16 +664,24 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a_row, const __grid_con
         const int quarter = warp & 3;
         const int row = quarter * 32 + lane;
         const int ly = row / HALO_TW, lx = row % HALO_TW;
+        EpiCtx e;
+        e.map_out = &map_out;
+        e.slab = smem_u32(s_stg + quarter * 4096);
+        e.slab_y = quarter * (32 / HALO_TW);
+        e.lane = lane;
+        e.n0 = 0;
         int acc = 0;
         uint32_t acc_phase = 0;
         for (int t = blockIdx.x; t < total; t += gridDim.x) {
             const TileCoord tcd = decode_tile(t, 1, tiles_x, tiles_y, BLOCK_N, HALO_TW, HALO_TH);
+            e.b = tcd.b; e.y0 = tcd.y0; e.x0 = tcd.x0; e.y = tcd.y0 + ly; e.x = tcd.x0 + lx;
             mbar_wait(&tmem_full[acc], acc_phase);
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BLOCK_N);
-            epilogue_tile<BLOCK_N, EPI, HALO_TW>(args, s_head, taddr, tcd.b, tcd.y0 + ly, tcd.x0 + lx, 0, lane, &tmem_empty[acc]);
+            epilogue_tile<BLOCK_N, EPI, HALO_TW>(args, s_head, taddr, e, &tmem_empty[acc]);
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
+        if (EPI != EPI_HEAD && lane == 0) tma_store_wait_read();
     }
 
     tc_fence_before();
