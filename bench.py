@@ -182,7 +182,9 @@ def run_ours(args, rank, world, local):
     # synthetic input: R distinct batches per rank, slices seeded by global slice index (cfg3 sharding:
     # contiguous block of slices per rank)
     R = 2
-    host = [torch.from_numpy(synth.ct_volume(B, S, S, first_seed=(rank * R + r) * B)).pin_memory() for r in range(R)]
+    lo, hi = shard_range(world * R * B, world, rank)   # this rank's contiguous block of the synthetic volume
+    host = [torch.from_numpy(synth.ct_volume(B, S, S, first_seed=lo + r * B)).pin_memory() for r in range(R)]
+    assert hi - lo == R * B
     dev = [h.cuda(non_blocking=True) for h in host]
     torch.cuda.synchronize()
 
@@ -192,12 +194,10 @@ def run_ours(args, rank, world, local):
             dist.barrier()
         torch.cuda.synchronize()
 
+    from medseg_b200.sharding import max_over_ranks as _max_over_ranks, shard_range
+
     def max_over_ranks(x):
-        if not use_dist:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
+        return _max_over_ranks(x, device="cuda")
 
     # ---------------- device-resident throughput ("value")
     for i in range(args.warmup):
