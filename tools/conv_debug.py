@@ -19,14 +19,13 @@ BUFS = ["e1a", "cat1", "p1", "e2a", "cat2", "p2", "e3a", "cat3", "p3", "e4a", "c
         "d3b", "d2a", "d2b", "d1a"]
 CONFIGS = {
     "pertap": {"MEDSEG_HALO": "0"},
-    "halo_m0": {"MEDSEG_HALO": "1", "MEDSEG_DESC_MODE": "0"},
-    "halo_p10": {"MEDSEG_HALO": "1", "MEDSEG_HALO_PITCH": "10"},
-    "halo_m1": {"MEDSEG_HALO": "1", "MEDSEG_DESC_MODE": "1"},
+    "halo1": {"MEDSEG_HALO": "1", "MEDSEG_CTA2": "0"},
+    "halo2": {"MEDSEG_HALO": "1", "MEDSEG_CTA2": "1"},
 }
 
 
 def make_engine(blob, nb, env):
-    for k in ("MEDSEG_NAIVE_CONV", "MEDSEG_HALO", "MEDSEG_DESC_MODE", "MEDSEG_HALO_PITCH"):
+    for k in ("MEDSEG_NAIVE_CONV", "MEDSEG_HALO", "MEDSEG_DESC_MODE", "MEDSEG_HALO_PITCH", "MEDSEG_CTA2"):
         os.environ.pop(k, None)
     os.environ.update(env)
     return ms.Engine({"weights": blob, "max_batch": nb})

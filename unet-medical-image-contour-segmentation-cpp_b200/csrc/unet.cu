@@ -237,6 +237,20 @@ void launch_halo(const UNetLayer& L, const tc::ConvArgs& a, int sm_count, cudaSt
     launch_halo_p<BN, EPI, RKC, 10>(L, a, sm_count, st);   // dense halo box (the 2048-byte pitch variant measured the same)
 }
 
+template <int BN, int EPI, int RKC>
+void launch_halo2(const UNetLayer& L, const tc::ConvArgs& a, int sm_count, cudaStream_t st) {
+    using C = tc::Halo2Cfg<BN, RKC>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        MS_CUDA(cudaFuncSetAttribute(tc::conv_halo2_kernel<BN, EPI, RKC>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+        attr_set = true;
+    }
+    const int pairs = a.batch * (a.H / tc::HALO_TH) * (a.W / tc::HALO_TW) / 2;
+    const int grid = 2 * std::min(pairs, sm_count / 2);
+    tc::conv_halo2_kernel<BN, EPI, RKC><<<grid, tc::NUM_THREADS, C::SMEM_BYTES, st>>>(L.map_a_row, L.map_b_half, L.map_out, a);
+    MS_LAUNCH_CHECK();
+}
+
 struct Blob {
     std::vector<char> raw;
     size_t base = 0;
@@ -302,6 +316,9 @@ void UNet::load(const std::string& blob_path, int net_h, int net_w, int n_classe
     naive_ = nv && nv[0] == '1';
     const char* hv = std::getenv("MEDSEG_HALO");
     halo_enabled_ = !(hv && hv[0] == '0');
+    const char* cv = std::getenv("MEDSEG_CTA2");
+    cta2_enabled_ = !(cv && cv[0] == '0');
+    cta2_force_ = cv && cv[0] == '2';   // MEDSEG_CTA2=2: prefer the pair kernel wherever it applies (A/B measurements)
     const char* pv = std::getenv("MEDSEG_HALO_PITCH");
     halo_pitch_ = 10;
     (void)pv;
@@ -376,13 +393,23 @@ void UNet::load(const std::string& blob_path, int net_h, int net_w, int n_classe
         L.flops_per_slice = 2.0 * h * w * (double)cout * 9 * cin;
         make_act_map(&L.map_a, bufs_[src].p, max_batch, h, w, bufs_[src].C);
         make_wgt_map(&L.map_b, L.w, cout, 9 * cin, L.block_n);
-        // halo-stationary kernel for the narrow-N, large-grid layers (kernel 1 is L2-bandwidth bound there)
+        // Halo-stationary kernels for the narrow-N, large-grid layers, used only when the layer's weights can
+        // stay resident in shared memory (measured A/B, profiles/r1_ab_kernel_variants.log): single CTA when
+        // all 9 * kc weight tiles fit in 144 KiB, the cta_group::2 pair when half of them do; otherwise the
+        // per-tap streaming kernel is faster.
         if (halo_enabled_ && cout == L.block_n && L.block_n <= 128 && h % tc::HALO_TH == 0 && w % tc::HALO_TW == 0) {
-            L.halo = 1;
             const int kc = cin / tc::BLOCK_K;
-            L.resident_kc = (9 * kc * L.block_n * 128 <= 144 * 1024) ? kc : 0;
-            L.halo_pitch = halo_pitch_;
-            make_act_map(&L.map_a_row, bufs_[src].p, max_batch, h, w, bufs_[src].C, tc::HALO_TW + 2, halo_pitch_ == 16 ? 1 : tc::HALO_TH + 2);
+            const bool fits1 = 9 * kc * L.block_n * 128 <= 144 * 1024;
+            const bool fits2 = 9 * kc * (L.block_n / 2) * 128 <= 144 * 1024 && ((h / tc::HALO_TH) * (w / tc::HALO_TW)) % 2 == 0;
+            if (fits1 && !(cta2_force_ && fits2)) {
+                L.halo = 1;
+                L.resident_kc = kc;
+            } else if (fits2 && cta2_enabled_) {
+                L.halo = 2;
+                L.resident_kc = kc;
+                make_wgt_map(&L.map_b_half, L.w, cout, 9 * cin, L.block_n / 2);
+            }
+            if (L.halo) make_act_map(&L.map_a_row, bufs_[src].p, max_batch, h, w, bufs_[src].C, tc::HALO_TW + 2, tc::HALO_TH + 2);
         }
         if (dst >= 0) make_out_map(&L.map_out, bufs_[dst].p, max_batch, h, w, bufs_[dst].C, L.halo ? tc::HALO_TW : tc::TILE_W);
         else L.map_out = L.map_b;  // head layer: no bf16 output
@@ -495,12 +522,19 @@ void UNet::run_layer(int li, const uint8_t* d_in_u8, int batch, uint8_t* d_mask,
         }
         return;
     }
-    if (L.halo) {
+    if (L.halo == 2) {
+        const int rk = L.resident_kc;
+        if (L.kind == 3 && rk == 1) launch_halo2<64, tc::EPI_HEAD, 1>(L, a, sm_count_, st);
+        else if (L.kind != 3 && L.block_n == 64 && rk == 1) launch_halo2<64, tc::EPI_STORE, 1>(L, a, sm_count_, st);
+        else if (L.kind != 3 && L.block_n == 64 && rk == 2) launch_halo2<64, tc::EPI_STORE, 2>(L, a, sm_count_, st);
+        else if (L.kind != 3 && L.block_n == 128 && rk == 1) launch_halo2<128, tc::EPI_STORE, 1>(L, a, sm_count_, st);
+        else if (L.kind != 3 && L.block_n == 128 && rk == 2) launch_halo2<128, tc::EPI_STORE, 2>(L, a, sm_count_, st);
+        else fail(MS_ERR_INTERNAL, "no halo2 kernel instantiation for layer " + L.name);
+    } else if (L.halo) {
         if (L.kind == 3) launch_halo<64, tc::EPI_HEAD, 1>(L, a, sm_count_, st);
         else if (L.block_n == 64 && L.resident_kc == 1) launch_halo<64, tc::EPI_STORE, 1>(L, a, sm_count_, st);
         else if (L.block_n == 64 && L.resident_kc == 2) launch_halo<64, tc::EPI_STORE, 2>(L, a, sm_count_, st);
         else if (L.block_n == 128 && L.resident_kc == 1) launch_halo<128, tc::EPI_STORE, 1>(L, a, sm_count_, st);
-        else if (L.block_n == 128 && L.resident_kc == 0) launch_halo<128, tc::EPI_STORE, 0>(L, a, sm_count_, st);
         else fail(MS_ERR_INTERNAL, "no halo kernel instantiation for layer " + L.name);
     } else if (L.kind == 3) {
         launch_tc<64, tc::EPI_HEAD>(L, a, sm_count_, st);

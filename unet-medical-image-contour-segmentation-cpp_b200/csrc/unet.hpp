@@ -21,9 +21,10 @@ struct UNetLayer {
     float* w_f32 = nullptr;      // device [64][9] fp32 (kind 0)
     float* bias = nullptr;       // device [Cout] fp32
     CUtensorMap map_a, map_b;
+    CUtensorMap map_b_half;      // cta_group::2 kernel: box {64 k, block_n / 2 rows}
     CUtensorMap map_out;         // TMA store of the epilogue (one epilogue warp's 32-pixel x 64-channel slab)
     CUtensorMap map_a_row;       // halo kernel: box {64 ch, 10 px, 18 rows}
-    int halo = 0;                // 0 = per-tap streaming kernel, 1 = halo-stationary kernel
+    int halo = 0;                // 0 = per-tap streaming kernel, 1 = halo-stationary kernel, 2 = its cta_group::2 version
     int resident_kc = 0;         // halo kernel: > 0 when all weights stay in shared memory
     int halo_pitch = 16;         // halo kernel: shared-memory rows per halo image row (10 dense / 16 aligned)
     double flops_per_slice = 0;  // 2 * MAC
@@ -58,6 +59,8 @@ class UNet {
     int H_ = 0, W_ = 0, n_classes_ = 0, max_batch_ = 0, fg_value_ = 2, sm_count_ = 148;
     bool naive_ = false;  // MEDSEG_NAIVE_CONV=1: CUDA-core reference kernels (debug / validation only)
     bool halo_enabled_ = true;  // MEDSEG_HALO=0: force the per-tap kernel everywhere (A/B measurements)
+    bool cta2_enabled_ = true;  // MEDSEG_CTA2=0: single-CTA halo kernel only
+    bool cta2_force_ = false;
     int halo_pitch_ = 16;       // MEDSEG_HALO_PITCH
     int desc_mode_ = 0;         // MEDSEG_DESC_MODE: UMMA descriptor base-offset convention of the halo kernel
     int64_t n_params_ = 0;

@@ -226,9 +226,11 @@ struct EpiCtx {
     int lane;
 };
 
-template <int BLOCK_N, int EPI, int TW>
+__device__ __forceinline__ void mbar_arrive_cluster_fwd(uint32_t cluster_addr);
+
+template <int BLOCK_N, int EPI, int TW, bool REMOTE = false>
 __device__ __forceinline__ void epilogue_tile(const ConvArgs& args, const float* s_head, uint32_t taddr, const EpiCtx& e,
-                                              uint64_t* tmem_empty_bar) {
+                                              uint64_t* tmem_empty_bar, uint32_t remote_empty = 0) {
     if (EPI == EPI_HEAD) {
         // BLOCK_N == 64: the whole feature vector of this pixel
         uint32_t r0[32], r1[32];
@@ -236,7 +238,7 @@ __device__ __forceinline__ void epilogue_tile(const ConvArgs& args, const float*
         tmem_ld32(taddr + 32, r1);
         tmem_ld_wait();
         tc_fence_before();
-        mbar_arrive(tmem_empty_bar);
+        if (REMOTE) mbar_arrive_cluster_fwd(remote_empty); else mbar_arrive(tmem_empty_bar);
         float f[64];
         const float4* b4 = reinterpret_cast<const float4*>(args.bias);
 #pragma unroll
@@ -272,7 +274,7 @@ __device__ __forceinline__ void epilogue_tile(const ConvArgs& args, const float*
             tmem_ld_wait();
             if (c0 + 64 >= BLOCK_N) {  // last block read: hand the accumulator back to the MMA warp
                 tc_fence_before();
-                mbar_arrive(tmem_empty_bar);
+                if (REMOTE) mbar_arrive_cluster_fwd(remote_empty); else mbar_arrive(tmem_empty_bar);
             }
             const int col = e.n0 + c0;             // first GEMM column of this 64-block
             const int co = col % args.Cout;        // 64-aligned, never straddles Cout
@@ -689,6 +691,246 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a_row, const __grid_con
     if (warp == 1) {
         __syncwarp();
         tmem_dealloc_warp(tmem_base, C::TMEM_COLS);
+    }
+}
+
+
+// ==================================================================================== kernel 3
+// cta_group::2 version of the halo-stationary kernel: a CTA pair (cluster of 2, one TPC) works on two
+// adjacent 8x16-pixel tiles as ONE UMMA of M = 256.  Each CTA stages its own halo tile (its 128 rows of A)
+// and only HALF of the weight tile (N/2 rows of B), so per CTA the weights take half the shared memory
+// (144 KiB layers become resident, resident layers get a deeper A ring) and half the operand bandwidth.
+// The leader CTA (rank 0) issues tcgen05.mma.cta_group::2; both CTAs' TMA loads signal the leader's "full"
+// barriers, tcgen05.commit multicasts "empty" / "accumulator ready" to both CTAs, and both epilogues report
+// "accumulator drained" to the leader.
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t mapa_rank(uint32_t smem_addr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster_fwd(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;   // clears the CTA-rank bit of a shared::cluster address -> CTA 0 of the pair
+__device__ __forceinline__ void tma2_load_4d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar) & kPeerBitMask), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
+__device__ __forceinline__ void tma2_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar) & kPeerBitMask), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void umma2_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma2_commit_mc(uint64_t* bar) {   // arrives on `bar` in both CTAs of the pair
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(smem_u32(bar)), "h"((uint16_t)3)
+                 : "memory");
+}
+__host__ __device__ constexpr uint32_t make_idesc_m256(int n) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+}
+
+template <int BLOCK_N, int RESIDENT_KC>
+struct Halo2Cfg {
+    static constexpr int HALO_STAGE_BYTES = HaloGeom<10>::STAGE_BYTES;
+    static constexpr int B_TILE_BYTES = (BLOCK_N / 2) * BLOCK_K * 2;      // this CTA's half of one weight tile
+    static constexpr int RES_BYTES = 9 * RESIDENT_KC * B_TILE_BYTES;
+    static constexpr int B_STAGES = RESIDENT_KC > 0 ? 0 : 8;
+    static constexpr int STG_BYTES = 4 * 4096;
+    static constexpr int BUDGET = 227 * 1024 - 4096 - 1024 - STG_BYTES;
+    static constexpr int A_STAGES_RAW = (BUDGET - RES_BYTES - B_STAGES * B_TILE_BYTES) / HALO_STAGE_BYTES;
+    static constexpr int A_STAGES = A_STAGES_RAW > 4 ? 4 : A_STAGES_RAW;
+    static constexpr int TMEM_COLS = 2 * BLOCK_N;
+    static constexpr int SMEM_BYTES = RES_BYTES + B_STAGES * B_TILE_BYTES + A_STAGES * HALO_STAGE_BYTES + STG_BYTES + 4096 + 1024;
+    static_assert(A_STAGES >= 2, "halo2 kernel needs at least two A stages");
+};
+
+template <int BLOCK_N, int EPI, int RESIDENT_KC>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
+conv_halo2_kernel(const __grid_constant__ CUtensorMap map_a_halo, const __grid_constant__ CUtensorMap map_b_half,
+                  const __grid_constant__ CUtensorMap map_out, const ConvArgs args) {
+    using C = Halo2Cfg<BLOCK_N, RESIDENT_KC>;
+    constexpr int HALO_STAGE_BYTES = C::HALO_STAGE_BYTES;
+    constexpr int HALO_PITCH = 10;
+    extern __shared__ uint8_t smem_raw[];
+    // identical carve-up in both CTAs: the UMMA descriptors and multicast barrier addresses are CTA-relative offsets
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* s_res = smem;
+    uint8_t* s_b = smem + C::RES_BYTES;
+    uint8_t* s_a = s_b + C::B_STAGES * C::B_TILE_BYTES;
+    uint8_t* s_stg = s_a + C::A_STAGES * HALO_STAGE_BYTES;
+    uint8_t* aux = s_stg + C::STG_BYTES;
+    uint64_t* a_full = reinterpret_cast<uint64_t*>(aux);
+    uint64_t* a_empty = a_full + 4;
+    uint64_t* b_full = a_empty + 4;
+    uint64_t* b_empty = b_full + 8;
+    uint64_t* res_full = b_empty + 8;
+    uint64_t* tmem_full = res_full + 1;
+    uint64_t* tmem_empty = tmem_full + 2;
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+    float* s_head = reinterpret_cast<float*>(aux + 512);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const bool leader = rank == 0;
+    const int pair_id = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
+    const int tiles_x = args.W / HALO_TW, tiles_y = args.H / HALO_TH;
+    const int total_pairs = (args.batch * tiles_y * tiles_x) >> 1;     // host guarantees an even tile count
+    const int kchunks = args.Cin / BLOCK_K;
+
+    if (threadIdx.x == 0) {
+        prefetch_tmap(&map_a_halo);
+        prefetch_tmap(&map_b_half);
+        if (EPI != EPI_HEAD) prefetch_tmap(&map_out);
+        for (int i = 0; i < 4; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
+        for (int i = 0; i < 8; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
+        mbar_init(res_full, 1);
+        for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 256); }
+        fence_barrier_init();
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)), "r"((uint32_t)C::TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    if (EPI == EPI_HEAD) {
+        for (int i = threadIdx.x; i < args.n_classes * 64 + args.n_classes; i += NUM_THREADS)
+            s_head[i] = i < args.n_classes * 64 ? args.head_w[i] : args.head_b[i - args.n_classes * 64];
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();          // barrier inits of both CTAs are visible before any remote arrive / TMA signal
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
+
+    if (warp == 0) {
+        // ===================================================================== TMA producer (both CTAs)
+        if (lane == 0 && pair_id < total_pairs) {
+            const int n_half0 = (int)rank * (BLOCK_N / 2);
+            if (RESIDENT_KC > 0) {
+                if (leader) mbar_expect_tx(res_full, 2 * C::RES_BYTES);
+                for (int i = 0; i < 9 * RESIDENT_KC; ++i)
+                    tma2_load_2d(s_res + i * C::B_TILE_BYTES, &map_b_half, res_full, (i / RESIDENT_KC) * args.Cin + (i % RESIDENT_KC) * BLOCK_K, n_half0);
+            }
+            int sa = 0, sb = 0;
+            uint32_t pa = 0, pb = 0;
+            for (int p = pair_id; p < total_pairs; p += n_pairs) {
+                const TileCoord tc = decode_tile(2 * p + (int)rank, 1, tiles_x, tiles_y, BLOCK_N, HALO_TW, HALO_TH);
+                for (int kc = 0; kc < kchunks; ++kc) {
+                    mbar_wait(&a_empty[sa], pa ^ 1);
+                    if (leader) mbar_expect_tx(&a_full[sa], 2 * HALO_BOX_BYTES);
+                    tma2_load_4d(s_a + sa * HALO_STAGE_BYTES, &map_a_halo, &a_full[sa], kc * BLOCK_K, tc.x0 - 1, tc.y0 - 1, tc.b);
+                    if (++sa == C::A_STAGES) { sa = 0; pa ^= 1; }
+                    if (RESIDENT_KC == 0) {
+                        for (int tap = 0; tap < 9; ++tap) {
+                            mbar_wait(&b_empty[sb], pb ^ 1);
+                            if (leader) mbar_expect_tx(&b_full[sb], 2 * C::B_TILE_BYTES);
+                            tma2_load_2d(s_b + sb * C::B_TILE_BYTES, &map_b_half, &b_full[sb], tap * args.Cin + kc * BLOCK_K, n_half0);
+                            if (++sb == C::B_STAGES) { sb = 0; pb ^= 1; }
+                        }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================================================================== MMA issuer (leader CTA only)
+        if (leader && lane == 0 && pair_id < total_pairs) {
+            constexpr uint32_t idesc = make_idesc_m256(BLOCK_N);
+            int sa = 0, sb = 0, acc = 0;
+            uint32_t pa = 0, pb = 0, acc_phase = 0;
+            if (RESIDENT_KC > 0) {
+                mbar_wait(res_full, 0);
+                tc_fence_after();
+            }
+            for (int p = pair_id; p < total_pairs; p += n_pairs) {
+                mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BLOCK_N);
+                for (int kc = 0; kc < kchunks; ++kc) {
+                    mbar_wait(&a_full[sa], pa);
+                    tc_fence_after();
+                    const uint32_t a_base = smem_u32(s_a + sa * HALO_STAGE_BYTES);
+#pragma unroll 1
+                    for (int tap = 0; tap < 9; ++tap) {
+                        uint32_t b_addr;
+                        if (RESIDENT_KC > 0) {
+                            b_addr = smem_u32(s_res + (tap * RESIDENT_KC + kc) * C::B_TILE_BYTES);
+                        } else {
+                            mbar_wait(&b_full[sb], pb);
+                            tc_fence_after();
+                            b_addr = smem_u32(s_b + sb * C::B_TILE_BYTES);
+                        }
+                        const uint32_t a_addr = a_base + (uint32_t)(((tap / 3) * HALO_PITCH + (tap % 3)) * 128);
+                        const uint64_t adesc = make_smem_desc_sbo(a_addr, HALO_PITCH * 128);
+                        const uint64_t bdesc = make_smem_desc(b_addr);
+#pragma unroll
+                        for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
+                            umma2_f16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kc | tap | k) != 0 ? 1u : 0u);
+                        if (RESIDENT_KC == 0) {
+                            umma2_commit_mc(&b_empty[sb]);
+                            if (++sb == C::B_STAGES) { sb = 0; pb ^= 1; }
+                        }
+                    }
+                    umma2_commit_mc(&a_empty[sa]);
+                    if (++sa == C::A_STAGES) { sa = 0; pa ^= 1; }
+                }
+                umma2_commit_mc(&tmem_full[acc]);
+                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            }
+        }
+    } else {
+        // ===================================================================== epilogue (both CTAs, own 128 rows)
+        const int quarter = warp & 3;
+        const int row = quarter * 32 + lane;
+        const int ly = row / HALO_TW, lx = row % HALO_TW;
+        EpiCtx e;
+        e.map_out = &map_out;
+        e.slab = smem_u32(s_stg + quarter * 4096);
+        e.slab_y = quarter * (32 / HALO_TW);
+        e.lane = lane;
+        e.n0 = 0;
+        const uint32_t empty0 = mapa_rank(smem_u32(&tmem_empty[0]), 0), empty1 = mapa_rank(smem_u32(&tmem_empty[1]), 0);
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        for (int p = pair_id; p < total_pairs; p += n_pairs) {
+            const TileCoord tcd = decode_tile(2 * p + (int)rank, 1, tiles_x, tiles_y, BLOCK_N, HALO_TW, HALO_TH);
+            e.b = tcd.b; e.y0 = tcd.y0; e.x0 = tcd.x0; e.y = tcd.y0 + ly; e.x = tcd.x0 + lx;
+            mbar_wait(&tmem_full[acc], acc_phase);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BLOCK_N);
+            epilogue_tile<BLOCK_N, EPI, HALO_TW, true>(args, s_head, taddr, e, nullptr, acc ? empty1 : empty0);
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+        if (EPI != EPI_HEAD && lane == 0) tma_store_wait_read();
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();          // neither CTA may free TMEM / exit while its partner can still touch it
+    if (warp == 1) {
+        __syncwarp();
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)C::TMEM_COLS) : "memory");
     }
 }
 
