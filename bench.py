@@ -161,6 +161,7 @@ def run_ours(args, rank, world, local):
     import torch.distributed as dist
     import medseg_b200 as ms
     from medseg_b200 import synth
+    from medseg_b200.sharding import max_over_ranks as _max_over_ranks, shard_range
 
     use_dist = world > 1
     if not torch.cuda.is_available():
@@ -177,7 +178,12 @@ def run_ours(args, rank, world, local):
     if args.head == "binary":
         cfg["head"] = "binary"
     eng = ms.Engine(cfg)
-    stream = torch.cuda.current_stream().cuda_stream
+    # a dedicated (non-default) stream: the library launches on the stream handle it is given and
+    # torch.cuda.Event only sees torch's current stream, so both must be this one
+    tstream = torch.cuda.Stream()
+    torch.cuda.set_stream(tstream)
+    stream = tstream.cuda_stream
+    assert stream != 0
 
     # synthetic input: R distinct batches per rank, slices seeded by global slice index (cfg3 sharding:
     # contiguous block of slices per rank)
@@ -193,8 +199,6 @@ def run_ours(args, rank, world, local):
         if use_dist:
             dist.barrier()
         torch.cuda.synchronize()
-
-    from medseg_b200.sharding import max_over_ranks as _max_over_ranks, shard_range
 
     def max_over_ranks(x):
         return _max_over_ranks(x, device="cuda")

@@ -17,7 +17,8 @@ from medseg_b200 import synth  # noqa: E402
 CONFIGS = {
     "pertap": {"MEDSEG_HALO": "0"},
     "halo1": {"MEDSEG_HALO": "1", "MEDSEG_CTA2": "0"},
-    "halo2": {"MEDSEG_HALO": "1", "MEDSEG_CTA2": "1"},
+    "halo2": {"MEDSEG_HALO": "1", "MEDSEG_CTA2": "2"},
+    "auto": {},
 }
 ENV_KEYS = ("MEDSEG_NAIVE_CONV", "MEDSEG_HALO", "MEDSEG_DESC_MODE", "MEDSEG_HALO_PITCH", "MEDSEG_CTA2")
 
