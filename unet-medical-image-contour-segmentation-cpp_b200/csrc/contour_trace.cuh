@@ -48,12 +48,13 @@ MS_HD uint8_t trace_load(const uint8_t* nb, int i) {
 #endif
 }
 
-// Walks one outer border.  `emit(x, y)` is called for every kept vertex, in order.
+// Walks one outer border.  `code(p, x, y)` returns the 8-neighbour foreground code of pixel p = y * W + x;
+// `emit(x, y)` is called for every kept vertex, in order.
 // Returns the number of kept vertices, or -1 if `max_steps` was exhausted (corrupt input).
-template <class Emit>
-MS_HD int trace_contour(const uint8_t* nb, int W, int start, int max_steps, Emit emit) {
+template <class Code, class Emit>
+MS_HD int trace_contour_fn(Code code, int W, int start, int max_steps, Emit emit) {
     int x = start % W, y = start / W;
-    const unsigned c0 = trace_load(nb, start);
+    const unsigned c0 = code(start, x, y);
     if (c0 == 0) {  // isolated pixel
         emit(x, y);
         return 1;
@@ -66,7 +67,7 @@ MS_HD int trace_contour(const uint8_t* nb, int W, int start, int max_steps, Emit
     const int last = start + trace_dy(dL) * W + trace_dx(dL);
     int p = start, d_prev = dL, prev_out = (dL + 4) & 7, n = 0;
     for (int step = 0; step < max_steps; ++step) {
-        const unsigned cc = trace_load(nb, p);
+        const unsigned cc = code(p, x, y);
         const unsigned rot = ((cc | (cc << 8)) >> ((d_prev + 1) & 7)) & 0xFFu;  // bit k <-> direction d_prev+1+k
         const int d = (d_prev + 1 + trace_first_set(rot)) & 7;                  // rot != 0: the way back is always set
         if (d != prev_out) {
@@ -83,6 +84,15 @@ MS_HD int trace_contour(const uint8_t* nb, int W, int start, int max_steps, Emit
         d_prev = (d + 4) & 7;
     }
     return -1;
+}
+
+struct NbImageCode {   // neighbour codes precomputed per pixel in global memory
+    const uint8_t* nb;
+    MS_HD unsigned operator()(int p, int, int) const { return trace_load(nb, p); }
+};
+template <class Emit>
+MS_HD int trace_contour(const uint8_t* nb, int W, int start, int max_steps, Emit emit) {
+    return trace_contour_fn(NbImageCode{nb}, W, start, max_steps, emit);
 }
 
 }  // namespace ms

@@ -22,12 +22,14 @@ namespace ms {
 namespace {
 
 constexpr int TW = 32, TH = 8;
+constexpr size_t kTraceSmemMax = 200 * 1024;   // slices up to ~1264 x 1264 trace out of shared memory
 
 // Fused: threshold -> 8-neighbour code, foreground label init, background label init + flag clear.
 // grid = (ceil(W/32), ceil(H/8), batch), block = 256.
 __global__ void __launch_bounds__(256) m2p_init_kernel(const uint8_t* __restrict__ mask, int H, int W, int thr,
                                                         int* __restrict__ Lfg, int* __restrict__ Lbg,
-                                                        uint8_t* __restrict__ bg_flag, uint8_t* __restrict__ nb) {
+                                                        uint8_t* __restrict__ bg_flag, uint8_t* __restrict__ nb,
+                                                        uint32_t* __restrict__ fgbits, int wpitch) {
     __shared__ uint8_t S[TH + 2][TW + 2];
     const size_t slice = (size_t)blockIdx.z * H * W;
     const int x0 = blockIdx.x * TW, y0 = blockIdx.y * TH;
@@ -44,6 +46,8 @@ __global__ void __launch_bounds__(256) m2p_init_kernel(const uint8_t* __restrict
     const bool bg = in && !fg;
     const unsigned fbits = __ballot_sync(0xFFFFFFFFu, fg);
     const unsigned bbits = __ballot_sync(0xFFFFFFFFu, bg);
+    // bit-packed foreground, one word per 32-pixel segment (the trace kernels keep a whole slice of it in smem)
+    if (lx == 0 && y < H) fgbits[((size_t)blockIdx.z * H + y) * wpitch + blockIdx.x] = fbits;
     if (!in) return;
     const int p = y * W + x;
     const unsigned below = (1u << lx) - 1u;
@@ -202,6 +206,56 @@ __global__ void __launch_bounds__(128) trace_count_kernel(const uint8_t* __restr
     npts[c] = cnt < 0 ? 0 : cnt;
 }
 
+// ---- shared-memory variant: one CTA per slice keeps the slice's bit-packed foreground (H*W/8 bytes, padded by a
+// zero word / zero row on every side) in shared memory, so a border-following step costs six LDS instead of a
+// dependent global load.  Thread t traces contours slice_start[b] + t, + blockDim, ...
+struct BitsCode {
+    const uint32_t* bits;   // (H + 2) rows x pitch words, row 0 / word 0 are the zero frame
+    int pitch;
+    __device__ __forceinline__ unsigned operator()(int, int x, int y) const {
+        // bits x-1 .. x+1 of rows y-1, y, y+1; pixel x lives at bit position x + 32 of the padded row
+        const int X = x + 31, w = X >> 5, sh = X & 31;
+        const uint32_t* r = bits + (size_t)y * pitch + w;          // padded row y   <-> image row y-1
+        const unsigned up = __funnelshift_r(r[0], r[1], sh) & 7u;
+        const unsigned cu = __funnelshift_r(r[pitch], r[pitch + 1], sh) & 7u;
+        const unsigned dn = __funnelshift_r(r[2 * pitch], r[2 * pitch + 1], sh) & 7u;
+        // 0=E 1=NE 2=N 3=NW 4=W 5=SW 6=S 7=SE ; bit0 = x-1, bit1 = x, bit2 = x+1
+        return ((cu >> 2) & 1u) | (((up >> 2) & 1u) << 1) | (((up >> 1) & 1u) << 2) | ((up & 1u) << 3) | ((cu & 1u) << 4) |
+               ((dn & 1u) << 5) | (((dn >> 1) & 1u) << 6) | (((dn >> 2) & 1u) << 7);
+    }
+};
+
+template <bool EMIT>
+__global__ void __launch_bounds__(128) trace_smem_kernel(const uint32_t* __restrict__ fgbits, int H, int W, int wpitch,
+                                                          const int* __restrict__ starts, const int* __restrict__ slice_start,
+                                                          long long* __restrict__ header, int cap_contours, int* __restrict__ npts,
+                                                          long long cap_points, double sx, double sy, int2* __restrict__ xy) {
+    extern __shared__ uint32_t sbits[];
+    const int b = blockIdx.x;
+    const int pitch = wpitch + 2;
+    const int c_lo = slice_start[b], c_hi = min(slice_start[b + 1], cap_contours);
+    if (c_lo >= c_hi) return;
+    if (EMIT && header[1] > cap_points) {
+        if (threadIdx.x == 0) header[2] |= 2;
+        return;
+    }
+    for (int i = threadIdx.x; i < (H + 2) * pitch; i += blockDim.x) {
+        const int r = i / pitch, c = i % pitch;
+        sbits[i] = (r >= 1 && r <= H && c >= 1 && c <= wpitch) ? fgbits[((size_t)b * H + (r - 1)) * wpitch + (c - 1)] : 0u;
+    }
+    __syncthreads();
+    const BitsCode code{sbits, pitch};
+    for (int c = c_lo + threadIdx.x; c < c_hi; c += blockDim.x) {
+        if (EMIT) {
+            trace_contour_fn(code, W, starts[c], 8 * H * W + 8, WriteEmit{xy + npts[c], sx, sy, 0});
+        } else {
+            const int cnt = trace_contour_fn(code, W, starts[c], 8 * H * W + 8, CountEmit{});
+            if (cnt < 0) atomicAdd((unsigned long long*)&header[3], 1ull);
+            npts[c] = cnt < 0 ? 0 : cnt;
+        }
+    }
+}
+
 // 1 block of 1024: in-place exclusive scan of npts[0..n) ; npts[n] = header[1] = total
 __global__ void __launch_bounds__(1024) scan_points_kernel(int* __restrict__ npts, int cap_contours, long long* __restrict__ header) {
     const long long n64 = header[0];
@@ -253,6 +307,8 @@ void m2p_phase_a(M2pWs& ws, const uint8_t* d_mask, int h, int w, int batch, int 
     ws.bg.labels.reserve(nb * 4);
     ws.bg.flag.reserve(nb);
     ws.nb.reserve(nb);
+    const int wpitch = cdiv(w, 32);
+    ws.fgbits.reserve((size_t)batch * h * wpitch * 4);
     const int bps = cdiv(n, 256);
     P.block_counts.reserve(((size_t)bps * batch + batch + 1) * 4);
     P.slice_start.reserve(((size_t)batch + 1) * 4);
@@ -269,7 +325,8 @@ void m2p_phase_a(M2pWs& ws, const uint8_t* d_mask, int h, int w, int batch, int 
     int* slice_total = bc + (size_t)bps * batch;
     long long* header = P.header.as<long long>();
 
-    m2p_init_kernel<<<dim3(cdiv(w, TW), cdiv(h, TH), batch), 256, 0, st>>>(d_mask, h, w, threshold, Lfg, Lbg, flag, nbc);
+    m2p_init_kernel<<<dim3(cdiv(w, TW), cdiv(h, TH), batch), 256, 0, st>>>(d_mask, h, w, threshold, Lfg, Lbg, flag, nbc,
+                                                                          ws.fgbits.as<uint32_t>(), wpitch);
     MS_LAUNCH_CHECK();
     const dim3 g = ccl::grid_for(h, w, batch);
     ccl::merge_kernel<8><<<g, ccl::kThreads, 0, st>>>(Lfg, h, w);
@@ -289,24 +346,44 @@ void m2p_phase_a(M2pWs& ws, const uint8_t* d_mask, int h, int w, int batch, int 
     write_starts_kernel<<<dim3(bps, batch), 256, 0, st>>>(Lfg, Lbg, flag, w, n, bc, P.slice_start.as<int>(), (int)P.cap_contours,
                                                           P.starts.as<int>(), P.start_slice.as<int>());
     MS_LAUNCH_CHECK();
-    trace_count_kernel<<<cdiv((int)P.cap_contours, 128), 128, 0, st>>>(nbc, w, n, P.starts.as<int>(), P.start_slice.as<int>(), header,
-                                                                     (int)P.cap_contours, P.npts.as<int>());
+    const size_t trace_smem = (size_t)(h + 2) * (wpitch + 2) * 4;
+    if (trace_smem <= kTraceSmemMax) {
+        static bool attr = false;
+        if (!attr) {
+            MS_CUDA(cudaFuncSetAttribute(trace_smem_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTraceSmemMax));
+            MS_CUDA(cudaFuncSetAttribute(trace_smem_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTraceSmemMax));
+            attr = true;
+        }
+        trace_smem_kernel<false><<<batch, 128, trace_smem, st>>>(ws.fgbits.as<uint32_t>(), h, w, wpitch, P.starts.as<int>(),
+                                                                P.slice_start.as<int>(), header, (int)P.cap_contours, P.npts.as<int>(),
+                                                                0, 1.0, 1.0, nullptr);
+    } else {
+        trace_count_kernel<<<cdiv((int)P.cap_contours, 128), 128, 0, st>>>(nbc, w, n, P.starts.as<int>(), P.start_slice.as<int>(), header,
+                                                                         (int)P.cap_contours, P.npts.as<int>());
+    }
     MS_LAUNCH_CHECK();
     scan_points_kernel<<<1, 1024, 0, st>>>(P.npts.as<int>(), (int)P.cap_contours, header);
     MS_LAUNCH_CHECK();
 }
 
 void m2p_phase_b(M2pWs& ws, int h, int w, int batch, int orig_w, int orig_h, cudaStream_t st) {
-    (void)batch;
     PolyDev& P = ws.poly;
     const int n = h * w;
     // src/mask2polygon.cpp:199-200
     const double sx = static_cast<double>(orig_w) / w;
     const double sy = static_cast<double>(orig_h) / h;
-    trace_emit_kernel<<<cdiv((int)P.cap_contours, 128), 128, 0, st>>>(ws.nb.as<uint8_t>(), w, n, P.starts.as<int>(),
-                                                                    P.start_slice.as<int>(), P.npts.as<int>(),
-                                                                    P.header.as<long long>(), (int)P.cap_contours,
-                                                                    (long long)P.cap_points, sx, sy, P.xy.as<int2>());
+    const int wpitch = cdiv(w, 32);
+    const size_t trace_smem = (size_t)(h + 2) * (wpitch + 2) * 4;
+    if (trace_smem <= kTraceSmemMax) {
+        trace_smem_kernel<true><<<batch, 128, trace_smem, st>>>(ws.fgbits.as<uint32_t>(), h, w, wpitch, P.starts.as<int>(),
+                                                               P.slice_start.as<int>(), P.header.as<long long>(), (int)P.cap_contours,
+                                                               P.npts.as<int>(), (long long)P.cap_points, sx, sy, P.xy.as<int2>());
+    } else {
+        trace_emit_kernel<<<cdiv((int)P.cap_contours, 128), 128, 0, st>>>(ws.nb.as<uint8_t>(), w, n, P.starts.as<int>(),
+                                                                        P.start_slice.as<int>(), P.npts.as<int>(),
+                                                                        P.header.as<long long>(), (int)P.cap_contours,
+                                                                        (long long)P.cap_points, sx, sy, P.xy.as<int2>());
+    }
     MS_LAUNCH_CHECK();
 }
 

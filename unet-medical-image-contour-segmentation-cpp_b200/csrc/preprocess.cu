@@ -128,6 +128,43 @@ __global__ void __launch_bounds__(128) resample_kernel(const uint16_t* __restric
     }
 }
 
+// Fast path for the identity geometry (w == out_w, h == out_h; BASELINE cfg1-3): step = 1.0, so dx = dy = 0 and the
+// reference's bilinear expression collapses to v00 exactly (the other three products are +0.0).  One thread =
+// 8 consecutive pixels: one 16-byte load, one 8-byte u8 store, one 16-byte bf16 store.
+__global__ void __launch_bounds__(256) normalise_identity_kernel(const uint16_t* __restrict__ src, size_t n_per_slice,
+                                                                  const uint32_t* __restrict__ mm, uint8_t* __restrict__ out_u8,
+                                                                  __nv_bfloat16* __restrict__ out_bf16) {
+    const int b = blockIdx.y;
+    const size_t i8 = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i8 * 8 >= n_per_slice) return;
+    int mn = 0xFFFF - (int)mm[2 * b], mx = (int)mm[2 * b + 1];
+    if (mn == mx) mx = mn + 1;
+    const double scale8 = __ddiv_rn(255.0, (double)(mx - mn));
+    const size_t o = (size_t)b * n_per_slice + i8 * 8;
+    const uint4 q = __ldg(reinterpret_cast<const uint4*>(src + o));
+    const uint32_t wds[4] = {q.x, q.y, q.z, q.w};
+    uint32_t lo = 0, hi = 0;
+    float f[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const int v = (int)((wds[j >> 1] >> (16 * (j & 1))) & 0xFFFFu);
+        const double qd = __dadd_rn(__dmul_rn((double)(v - mn), scale8), 0.5);   // preprocess.cpp:116 with v == v00
+        const uint32_t r = (uint32_t)__double2int_rz(qd) & 0xFFu;
+        if (j < 4) lo |= r << (8 * j); else hi |= r << (8 * (j - 4));
+        f[j] = __fdiv_rn((float)r, 255.0f);
+    }
+    *reinterpret_cast<uint2*>(out_u8 + o) = make_uint2(lo, hi);
+    if (out_bf16) {
+        uint4 st;
+        __nv_bfloat162 t;
+        t = __floats2bfloat162_rn(f[0], f[1]); st.x = *reinterpret_cast<uint32_t*>(&t);
+        t = __floats2bfloat162_rn(f[2], f[3]); st.y = *reinterpret_cast<uint32_t*>(&t);
+        t = __floats2bfloat162_rn(f[4], f[5]); st.z = *reinterpret_cast<uint32_t*>(&t);
+        t = __floats2bfloat162_rn(f[6], f[7]); st.w = *reinterpret_cast<uint32_t*>(&t);
+        *reinterpret_cast<uint4*>(out_bf16 + o) = st;
+    }
+}
+
 }  // namespace
 
 void preprocess_launch(PreprocessWs& ws, const uint16_t* d_src, int w, int h, int batch, int out_w, int out_h,
@@ -143,8 +180,14 @@ void preprocess_launch(PreprocessWs& ws, const uint16_t* d_src, int w, int h, in
     bx = std::max(bx, 1);
     minmax_kernel<<<dim3(bx, batch), 256, 0, st>>>(d_src, n, mm);
     MS_LAUNCH_CHECK();
-    dim3 grid(cdiv(cdiv(out_w, 4), 128), out_h, batch);
-    resample_kernel<<<grid, 128, 0, st>>>(d_src, w, h, out_w, out_h, mm, d_out_u8, d_out_bf16);
+    const bool aligned = (reinterpret_cast<uintptr_t>(d_src) & 15) == 0 && (reinterpret_cast<uintptr_t>(d_out_u8) & 7) == 0 &&
+                         (reinterpret_cast<uintptr_t>(d_out_bf16) & 15) == 0 && n % 8 == 0;
+    if (w == out_w && h == out_h && aligned) {
+        normalise_identity_kernel<<<dim3((unsigned)cdiv64((int64_t)(n / 8), 256), batch), 256, 0, st>>>(d_src, n, mm, d_out_u8, d_out_bf16);
+    } else {
+        dim3 grid(cdiv(cdiv(out_w, 4), 128), out_h, batch);
+        resample_kernel<<<grid, 128, 0, st>>>(d_src, w, h, out_w, out_h, mm, d_out_u8, d_out_bf16);
+    }
     MS_LAUNCH_CHECK();
 }
 
