@@ -96,7 +96,7 @@ class ClockSampler(threading.Thread):
                         self.reasons.add(name)
             except Exception:
                 pass
-            time.sleep(0.05)
+            time.sleep(0.01)
 
     def result(self):
         self.stop_flag = True

@@ -1,0 +1,60 @@
+"""GPU parity tests for the remaining BASELINE.json configurations: cfg3 (a slice-sharded volume) and
+cfg4 (1024 x 1024, four labels, per-class contours)."""
+import numpy as np
+import pytest
+
+from conftest import contours_equal
+from oracle import pipeline as op
+
+pytestmark = pytest.mark.gpu
+
+
+def test_cfg3_volume_sharded_equals_unsharded(unet_engine, ms):
+    """cfg3: a synthetic volume split into contiguous per-rank blocks gives, block by block, exactly the polygons
+    of the unsharded run (slices are independent; ranks never communicate)."""
+    from medseg_b200 import synth
+    from medseg_b200.sharding import shard_range
+    vol = synth.ct_volume(8, first_seed=100)
+    whole = []
+    for i in range(0, 8, 4):                       # max_batch of the fixture engine is 4
+        whole += unet_engine.process_batch(vol[i:i + 4])[0].per_slice()
+    for world in (2, 4):
+        got = []
+        for rank in range(world):
+            lo, hi = shard_range(8, world, rank)
+            got += unet_engine.process_batch(vol[lo:hi])[0].per_slice()
+        assert len(got) == 8
+        for a, b in zip(got, whole):
+            assert contours_equal(a, b)
+    assert all(len(c) >= 1 for c in whole)
+
+
+def test_cfg4_1024_four_labels_per_class_contours(ms, tmp_path):
+    from medseg_b200 import synth, weights as W
+    from oracle.unet_torch import load_unet, unet_logits
+    blob = ms.make_weight_blob(str(tmp_path / "u4.msegw"), n_classes=4, seed=77)
+    eng = ms.Engine({"weights": blob, "max_batch": 1, "net_h": 1024, "net_w": 1024, "n_classes": 4})
+    assert eng.info.flops_per_slice == 1_539_343_122_432
+    src = synth.ct_slice(7, w=1024, h=1024)
+    norm = eng.preprocess(src)
+    assert (norm[0] == op.preprocess_raw(src, 1024, 1024)).all()
+    mask, logits = eng.process(norm, want_logits=True)
+    arch, w = W.load_blob(blob)
+    want = unet_logits(load_unet(w, 4), norm)
+    err = np.abs(logits - want)
+    print("1024^2 logits: max err %.4g p99.9 %.4g" % (err.max(), np.quantile(err, 0.999)))
+    assert np.quantile(err, 0.999) < 2e-2
+    assert (mask[0] == op.argmax_first3(logits[0], 4)).all()
+    assert (mask[0] == op.argmax_first3(want[0], 4)).mean() >= 0.995
+    assert len(np.unique(mask)) >= 3                               # several labels are present
+    raw, per_class = eng.process_multiclass(src, classes=(1, 2, 3))
+    assert (raw == mask).all()
+    n_found = 0
+    for k, (clean, polys) in per_class.items():
+        ref_clean = op.postprocess_mask(raw[0], fg=k)
+        assert (clean[0] == ref_clean).all(), k
+        ref = op.extract_contours(np.where(ref_clean == k, 255, 0).astype(np.uint8))
+        assert contours_equal(polys.slice(0), ref), k
+        n_found += len(ref)
+    assert n_found >= 1
+    eng.cleanup()

@@ -259,6 +259,21 @@ class Engine:
             lambda pg: self._l.ms_process_batch_host(self._h, _ptr(src), w, h, b, pg, _ptr(norm), _ptr(mask)), b)
         return polys, norm, mask
 
+    def process_multiclass(self, src_u16: np.ndarray, classes: Sequence[int]):
+        """cfg4 extension: per-class contours.  preprocess -> UNet argmax -> for each class k: postprocess with
+        FOREGROUND_VALUE = k (src/postprocess.cpp:5 made a parameter) -> contours of (mask == k), mapped to
+        the original size.  Returns (raw_mask [B,H,W], {k: (clean_mask, Polygons)})."""
+        src = np.ascontiguousarray(src_u16)
+        if src.ndim == 2:
+            src = src[None]
+        b, h, w = src.shape
+        raw = self.process(self.preprocess(src))
+        out = {}
+        for k in classes:
+            clean = self.postprocess(raw, fg_value=int(k))
+            out[int(k)] = (clean, self.mask2polygon(clean, threshold=int(k) - 1, orig_w=w, orig_h=h))
+        return raw, out
+
     def process_raw_file(self, raw_path: str, w: int, h: int, out_dir: str) -> None:
         self._check(self._l.ms_process_raw_file(self._h, raw_path.encode(), w, h, out_dir.encode()))
 
