@@ -158,6 +158,15 @@ MS_API int ms_process_batch_host(ms_handle* h, const uint16_t* h_src, int w, int
 MS_API int ms_process_batch_dev(ms_handle* h, const uint16_t* d_src, int w, int hgt, int batch,
                                 int64_t* n_points, int64_t* n_contours, void* stream);
 
+/* Asynchronous, double-buffered form of ms_process_batch_host for streaming a volume (the serial per-file loop at
+ * src/main.cpp:148-164): submit batch i+1 on the other slot before collecting batch i, and the H2D copy of i+1 and
+ * the host-side collection of i overlap the GPU work.  slot is 0 or 1.  h_src should be pinned (ms_alloc_pinned);
+ * it must stay valid until the matching ms_wait_batch returns.  Polygon capacities are fixed per slot
+ * (64 contours and 8,192 points per slice on average); a batch that exceeds them fails with MS_ERR_CAPACITY in
+ * ms_wait_batch and can be re-run through ms_process_batch_host. */
+MS_API int ms_submit_batch_host(ms_handle* h, int slot, const uint16_t* h_src, int w, int hgt, int batch);
+MS_API int ms_wait_batch(ms_handle* h, int slot, ms_polygons* out);
+
 /* Replaces MedicalSeg::process_single_image(raw_path, width, height, output_dir) including its
  * artefacts: <stem>_normalized.png, <stem>_original_sizes.json, <stem>_mask.png,
  * <stem>_contour_overlay.png, <stem>.json (src/process.cpp:207-242, src/mask2polygon.cpp:134-222). */

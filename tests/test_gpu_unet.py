@@ -167,3 +167,21 @@ def test_binary_head(ms, tmp_path):
     polys, _, m = e.process_batch(src, want_mask=True)
     assert contours_equal(polys.slice(0), op.extract_contours(op.mask_to_image(m[0])))
     e.cleanup()
+
+
+def test_async_pipeline_matches_sync(unet_engine, ms):
+    """ms_submit_batch_host / ms_wait_batch (double buffered) returns exactly what ms_process_batch_host returns."""
+    vols = [_slices(ms, 4, first=60 + 4 * i) for i in range(3)]
+    want = [unet_engine.process_batch(v)[0] for v in vols]
+    unet_engine.submit_batch(0, vols[0])
+    got = []
+    for i in range(3):
+        if i + 1 < 3:
+            unet_engine.submit_batch((i + 1) % 2, vols[i + 1])
+        got.append(unet_engine.wait_batch(i % 2))
+    for a, b in zip(got, want):
+        assert a.n_contours == b.n_contours and a.n_points == b.n_points
+        assert (a.slice_start == b.slice_start).all() and (a.contour_start == b.contour_start).all() and (a.xy == b.xy).all()
+    with pytest.raises(ms.MedsegError) as ei:
+        unet_engine.wait_batch(0)                  # nothing submitted
+    assert ei.value.code == ms.MS_ERR_STATE

@@ -70,6 +70,8 @@ ABI = {
     "ms_mask2polygon_dev": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, C.POINTER(ms_polygons), _P]),
     "ms_process_batch_host": (_I, [_P, _P, _I, _I, _I, C.POINTER(ms_polygons), _P, _P]),
     "ms_process_batch_dev": (_I, [_P, _P, _I, _I, _I, C.POINTER(_L), C.POINTER(_L), _P]),
+    "ms_submit_batch_host": (_I, [_P, _I, _P, _I, _I, _I]),
+    "ms_wait_batch": (_I, [_P, _I, C.POINTER(ms_polygons)]),
     "ms_process_raw_file": (_I, [_P, C.c_char_p, _I, _I, C.c_char_p]),
     "ms_polygons_to_json": (_L, [_P, _P, _I, C.c_char_p, _I, _I, _P, _L]),
     "ms_launch_count": (_L, [_P]),
@@ -222,7 +224,9 @@ class Engine:
         self._check(self._l.ms_postprocess_host(self._h, _ptr(m), _ptr(out), m.shape[1], m.shape[2], m.shape[0], fg_value))
         return out[0] if squeeze else out
 
-    def _poly_call(self, call, batch: int) -> Polygons:
+    def _poly_call(self, call, batch: int, retry: bool = True) -> Polygons:
+        if not retry:   # one-shot calls (the result is consumed by the call): size the buffers generously up front
+            self._cap_pts, self._cap_cnt = max(self._cap_pts, batch * 8192), max(self._cap_cnt, batch * 64)
         while True:
             xy = np.empty((self._cap_pts, 2), np.int32)
             cs = np.empty(self._cap_cnt + 1, np.int32)
@@ -258,6 +262,19 @@ class Engine:
         polys = self._poly_call(
             lambda pg: self._l.ms_process_batch_host(self._h, _ptr(src), w, h, b, pg, _ptr(norm), _ptr(mask)), b)
         return polys, norm, mask
+
+    def submit_batch(self, slot: int, src_u16: np.ndarray) -> None:
+        """Asynchronous half of the double-buffered pipeline: enqueue H2D + the whole path for `src_u16` [B,h,w]
+        (keep the array alive until wait_batch(slot) returns)."""
+        if src_u16.dtype != np.uint16 or not src_u16.flags.c_contiguous or src_u16.ndim != 3:
+            raise TypeError("src must be a C-contiguous uint16 [B,h,w] array")
+        b, h, w = src_u16.shape
+        self._check(self._l.ms_submit_batch_host(self._h, slot, _ptr(src_u16), w, h, b))
+        self._slot_batch = getattr(self, "_slot_batch", {})
+        self._slot_batch[slot] = b
+
+    def wait_batch(self, slot: int) -> Polygons:
+        return self._poly_call(lambda pg: self._l.ms_wait_batch(self._h, slot, pg), self._slot_batch[slot], retry=False)
 
     def process_multiclass(self, src_u16: np.ndarray, classes: Sequence[int]):
         """cfg4 extension: per-class contours.  preprocess -> UNet argmax -> for each class k: postprocess with

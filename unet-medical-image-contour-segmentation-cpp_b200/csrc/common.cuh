@@ -127,6 +127,9 @@ struct PolyDev {              // device-resident polygon set + counters
     DevBuf xy;                // int32 [cap_points * 2]
     DevBuf header;            // int64 [4]: n_contours, n_points, overflow, trace_error
     int64_t cap_contours = 0, cap_points = 0;
+    void release() {
+        for (DevBuf* b : {&starts, &start_slice, &npts, &slice_start, &block_counts, &xy, &header}) b->release();
+    }
 };
 struct M2pWs {
     CclWs fg, bg;
@@ -136,8 +139,8 @@ struct M2pWs {
     PinBuf h_header;          // pinned int64[4]
 };
 // Phase A: labels, external starts (descending raster order per slice), per-contour vertex counts, offsets.
-void m2p_phase_a(M2pWs& ws, const uint8_t* d_mask, int h, int w, int batch, int threshold, cudaStream_t st);
+void m2p_phase_a(M2pWs& ws, PolyDev& poly, const uint8_t* d_mask, int h, int w, int batch, int threshold, cudaStream_t st);
 // Phase B: emit mapped vertices into ws.poly.xy (requires cap_points >= n_points).
-void m2p_phase_b(M2pWs& ws, int h, int w, int batch, int orig_w, int orig_h, cudaStream_t st);
+void m2p_phase_b(M2pWs& ws, PolyDev& poly, int h, int w, int batch, int orig_w, int orig_h, cudaStream_t st);
 
 }  // namespace ms

@@ -48,6 +48,16 @@ struct ms_handle {
     // pipeline buffers
     DevBuf d_src, d_norm, d_mask_raw, d_mask, d_logits, d_scratch_in, d_scratch_out;
     PinBuf staging, h_header;
+    // double-buffered asynchronous pipeline (ms_submit_batch_host / ms_wait_batch)
+    struct Slot {
+        DevBuf d_src;
+        PolyDev poly;
+        PinBuf h_src, h_header, h_slice_start, h_cstart, h_xy;
+        cudaEvent_t ev_h2d = nullptr, ev_m2p = nullptr, ev_done = nullptr;
+        int batch = 0;
+        bool busy = false;
+    } slots[2];
+    cudaStream_t copy_stream = nullptr, d2h_stream = nullptr;
     // log: every line is appended with open/append/close, so the C++ facade's own std::ofstream
     // (opened with ios::app on the same file, see facade.cpp) interleaves correctly with it
     std::string log_path;
@@ -219,8 +229,8 @@ void finish_init(ms_handle* h, const char* log_dir) {
 void run_m2p(ms_handle* h, const uint8_t* d_mask, int hgt, int w, int batch, int threshold, int orig_w, int orig_h, cudaStream_t st) {
     long long* hh = h->h_header.as<long long>();
     for (int attempt = 0; attempt < 3; ++attempt) {
-        m2p_phase_a(h->m2p, d_mask, hgt, w, batch, threshold, st);
-        m2p_phase_b(h->m2p, hgt, w, batch, orig_w, orig_h, st);
+        m2p_phase_a(h->m2p, h->m2p.poly, d_mask, hgt, w, batch, threshold, st);
+        m2p_phase_b(h->m2p, h->m2p.poly, hgt, w, batch, orig_w, orig_h, st);
         download_sync(h, hh, h->m2p.poly.header.p, 4 * sizeof(long long), st);
         MS_REQUIRE(hh[3] == 0, MS_ERR_INTERNAL, "mask2polygon: border following did not terminate");
         MS_REQUIRE((hh[2] & 4) == 0, MS_ERR_CAPACITY, "mask2polygon: more than 2^31 points");
@@ -336,6 +346,17 @@ void ms_destroy(ms_handle* h) {
                       &h->m2p.poly.starts, &h->m2p.poly.start_slice, &h->m2p.poly.npts, &h->m2p.poly.slice_start,
                       &h->m2p.poly.block_counts, &h->m2p.poly.xy, &h->m2p.poly.header})
         b->release();
+    for (auto& S : h->slots) {
+        if (S.ev_done) cudaEventSynchronize(S.ev_done);
+        S.d_src.release();
+        S.poly.release();
+        for (PinBuf* b : {&S.h_src, &S.h_header, &S.h_slice_start, &S.h_cstart, &S.h_xy}) b->release();
+        if (S.ev_h2d) cudaEventDestroy(S.ev_h2d);
+        if (S.ev_m2p) cudaEventDestroy(S.ev_m2p);
+        if (S.ev_done) cudaEventDestroy(S.ev_done);
+    }
+    if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
+    if (h->d2h_stream) cudaStreamDestroy(h->d2h_stream);
     h->staging.release();
     h->h_header.release();
     h->m2p.h_header.release();
@@ -570,7 +591,7 @@ int ms_process_raw_file(ms_handle* h, const char* raw_path, int w, int hgt, cons
             std::cout << "Extracted " << nc << " Contours" << std::endl;                  // :187
             // overlay with unmapped (network-space) contours, red, 1 px (src/mask2polygon.cpp:114-129, 189-193)
             std::vector<int32_t> uxy((size_t)hh[1] * 2);
-            m2p_phase_b(h->m2p, h->net_h, h->net_w, 1, h->net_w, h->net_h, h->stream);
+            m2p_phase_b(h->m2p, h->m2p.poly, h->net_h, h->net_w, 1, h->net_w, h->net_h, h->stream);
             download_sync(h, uxy.data(), h->m2p.poly.xy.p, (size_t)hh[1] * 8, h->stream);
             std::vector<uint8_t> rgb(npx * 3);
             for (size_t i = 0; i < npx; ++i) rgb[3 * i] = rgb[3 * i + 1] = rgb[3 * i + 2] = norm[i];
@@ -588,6 +609,91 @@ int ms_process_raw_file(ms_handle* h, const char* raw_path, int w, int hgt, cons
         h->log("Total processing time: " + std::to_string(total_ms) + " ms");            // src/process.cpp:249
         h->log("Processing completed for: " + base);                                      // :250
         std::cout << "Total processing time: " << total_ms << " ms" << std::endl;         // :253
+    });
+}
+
+// ---------------------------------------------------------------- asynchronous double-buffered pipeline
+int ms_submit_batch_host(ms_handle* h, int slot, const uint16_t* h_src, int w, int hgt, int batch) {
+    if (!h) return MS_ERR_ARG;
+    return guarded(h, [&] {
+        MS_REQUIRE(slot >= 0 && slot < 2 && h_src && w > 0 && hgt > 0, MS_ERR_ARG, "submit_batch: bad argument");
+        MS_REQUIRE(h->unet.loaded(), MS_ERR_STATE, "no weights loaded");
+        MS_REQUIRE(batch >= 1 && batch <= h->max_batch, MS_ERR_ARG, "batch exceeds max_batch of this handle");
+        ms_handle::Slot& S = h->slots[slot];
+        MS_REQUIRE(!S.busy, MS_ERR_STATE, "submit_batch: slot still holds an uncollected batch (call ms_wait_batch)");
+        if (!h->copy_stream) {
+            MS_CUDA(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+            MS_CUDA(cudaStreamCreateWithFlags(&h->d2h_stream, cudaStreamNonBlocking));
+        }
+        if (!S.ev_h2d) {
+            MS_CUDA(cudaEventCreateWithFlags(&S.ev_h2d, cudaEventDisableTiming));
+            MS_CUDA(cudaEventCreateWithFlags(&S.ev_m2p, cudaEventDisableTiming));
+            MS_CUDA(cudaEventCreateWithFlags(&S.ev_done, cudaEventDisableTiming));
+        }
+        // fixed capacities: at most floor(1 / min_area_ratio) components survive postprocess per slice
+        if (S.poly.cap_contours == 0) {
+            S.poly.cap_contours = (int64_t)h->max_batch * 64;
+            S.poly.cap_points = (int64_t)h->max_batch * 8192;
+            S.h_header.reserve(4 * sizeof(long long));
+            S.h_slice_start.reserve(((size_t)h->max_batch + 1) * 4);
+            S.h_cstart.reserve(((size_t)S.poly.cap_contours + 1) * 4);
+            S.h_xy.reserve((size_t)S.poly.cap_points * 8);
+        }
+        const size_t in_bytes = (size_t)w * hgt * 2 * batch;
+        S.d_src.reserve(in_bytes);
+        const void* src = h_src;
+        if (!is_cuda_host_ptr(h_src)) {          // pageable memory: stage through this slot's pinned buffer
+            S.h_src.reserve(in_bytes);
+            std::memcpy(S.h_src.p, h_src, in_bytes);
+            src = S.h_src.p;
+        }
+        MS_CUDA(cudaMemcpyAsync(S.d_src.p, src, in_bytes, cudaMemcpyHostToDevice, h->copy_stream));
+        MS_CUDA(cudaEventRecord(S.ev_h2d, h->copy_stream));
+        cudaStream_t st = h->stream;
+        MS_CUDA(cudaStreamWaitEvent(st, S.ev_h2d, 0));
+        uint8_t* norm = h->d_norm.as<uint8_t>();
+        uint8_t* raw = h->d_mask_raw.as<uint8_t>();
+        uint8_t* mask = h->d_mask.as<uint8_t>();
+        preprocess_launch(h->pre, S.d_src.as<uint16_t>(), w, hgt, batch, h->net_w, h->net_h, norm, nullptr, st);
+        h->unet.forward(norm, batch, raw, nullptr, st);
+        postprocess_launch(h->post, raw, mask, h->net_h, h->net_w, batch, h->fg_value, h->min_area_ratio, st);
+        m2p_phase_a(h->m2p, S.poly, mask, h->net_h, h->net_w, batch, h->fg_value - 1, st);
+        m2p_phase_b(h->m2p, S.poly, h->net_h, h->net_w, batch, w, hgt, st);
+        // results leave on their own stream so the next batch's kernels are not held up; sizes are not known on the
+        // host yet, so the capacity-sized buffers are copied and trimmed in ms_wait_batch
+        MS_CUDA(cudaEventRecord(S.ev_m2p, st));
+        cudaStream_t ds = h->d2h_stream;
+        MS_CUDA(cudaStreamWaitEvent(ds, S.ev_m2p, 0));
+        MS_CUDA(cudaMemcpyAsync(S.h_header.p, S.poly.header.p, 4 * sizeof(long long), cudaMemcpyDeviceToHost, ds));
+        MS_CUDA(cudaMemcpyAsync(S.h_slice_start.p, S.poly.slice_start.p, ((size_t)batch + 1) * 4, cudaMemcpyDeviceToHost, ds));
+        MS_CUDA(cudaMemcpyAsync(S.h_cstart.p, S.poly.npts.p, ((size_t)S.poly.cap_contours + 1) * 4, cudaMemcpyDeviceToHost, ds));
+        MS_CUDA(cudaMemcpyAsync(S.h_xy.p, S.poly.xy.p, (size_t)S.poly.cap_points * 8, cudaMemcpyDeviceToHost, ds));
+        MS_CUDA(cudaEventRecord(S.ev_done, ds));
+        S.batch = batch;
+        S.busy = true;
+    });
+}
+
+int ms_wait_batch(ms_handle* h, int slot, ms_polygons* out) {
+    if (!h) return MS_ERR_ARG;
+    return guarded(h, [&] {
+        MS_REQUIRE(slot >= 0 && slot < 2, MS_ERR_ARG, "wait_batch: bad slot");
+        ms_handle::Slot& S = h->slots[slot];
+        MS_REQUIRE(S.busy, MS_ERR_STATE, "wait_batch: nothing was submitted on this slot");
+        check_polys(out, S.batch);
+        MS_CUDA(cudaEventSynchronize(S.ev_done));
+        S.busy = false;
+        const long long* hh = S.h_header.as<long long>();
+        MS_REQUIRE(hh[3] == 0, MS_ERR_INTERNAL, "mask2polygon: border following did not terminate");
+        MS_REQUIRE(hh[2] == 0 && hh[0] <= S.poly.cap_contours && hh[1] <= S.poly.cap_points, MS_ERR_CAPACITY,
+                   "async pipeline: polygon set exceeds the slot capacity (use ms_process_batch_host for this batch)");
+        out->n_contours = hh[0];
+        out->n_points = hh[1];
+        MS_REQUIRE(out->cap_contours >= hh[0] && out->cap_points >= hh[1], MS_ERR_CAPACITY,
+                   "polygon buffers too small: need " + std::to_string(hh[0]) + " contours, " + std::to_string(hh[1]) + " points");
+        std::memcpy(out->slice_start, S.h_slice_start.p, ((size_t)S.batch + 1) * 4);
+        std::memcpy(out->contour_start, S.h_cstart.p, ((size_t)hh[0] + 1) * 4);
+        if (hh[1] > 0) std::memcpy(out->xy, S.h_xy.p, (size_t)hh[1] * 8);
     });
 }
 

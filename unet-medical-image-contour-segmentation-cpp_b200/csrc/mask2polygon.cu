@@ -295,12 +295,11 @@ __global__ void __launch_bounds__(128) trace_emit_kernel(const uint8_t* __restri
 
 }  // namespace
 
-void m2p_phase_a(M2pWs& ws, const uint8_t* d_mask, int h, int w, int batch, int threshold, cudaStream_t st) {
+void m2p_phase_a(M2pWs& ws, PolyDev& P, const uint8_t* d_mask, int h, int w, int batch, int threshold, cudaStream_t st) {
     MS_REQUIRE(h > 0 && w > 0 && batch > 0 && h <= 65535 && batch <= 32767, MS_ERR_ARG, "mask2polygon: bad shape");
     MS_REQUIRE((int64_t)h * w <= (int64_t)(0x7FFFFFFF - 8) / 8, MS_ERR_ARG, "mask2polygon: slice too large");
     const int n = h * w;
     const size_t nb = (size_t)n * batch;
-    PolyDev& P = ws.poly;
     if (P.cap_contours == 0) P.cap_contours = std::max<int64_t>(1024, 64 * (int64_t)batch);
     if (P.cap_points == 0) P.cap_points = std::max<int64_t>(65536, 4096 * (int64_t)batch);
     ws.fg.labels.reserve(nb * 4);
@@ -366,8 +365,7 @@ void m2p_phase_a(M2pWs& ws, const uint8_t* d_mask, int h, int w, int batch, int 
     MS_LAUNCH_CHECK();
 }
 
-void m2p_phase_b(M2pWs& ws, int h, int w, int batch, int orig_w, int orig_h, cudaStream_t st) {
-    PolyDev& P = ws.poly;
+void m2p_phase_b(M2pWs& ws, PolyDev& P, int h, int w, int batch, int orig_w, int orig_h, cudaStream_t st) {
     const int n = h * w;
     // src/mask2polygon.cpp:199-200
     const double sx = static_cast<double>(orig_w) / w;
