@@ -19,8 +19,9 @@ CONFIGS = {
     "halo1": {"MEDSEG_HALO": "1", "MEDSEG_CTA2": "0"},
     "halo2": {"MEDSEG_HALO": "1", "MEDSEG_CTA2": "2"},
     "auto": {},
+    "nostream2": {"MEDSEG_STREAM2": "0"},
 }
-ENV_KEYS = ("MEDSEG_NAIVE_CONV", "MEDSEG_HALO", "MEDSEG_DESC_MODE", "MEDSEG_HALO_PITCH", "MEDSEG_CTA2")
+ENV_KEYS = ("MEDSEG_NAIVE_CONV", "MEDSEG_HALO", "MEDSEG_DESC_MODE", "MEDSEG_HALO_PITCH", "MEDSEG_CTA2", "MEDSEG_STREAM2")
 
 
 def sm_clock():

@@ -20,12 +20,14 @@ BUFS = ["e1a", "cat1", "p1", "e2a", "cat2", "p2", "e3a", "cat3", "p3", "e4a", "c
 CONFIGS = {
     "pertap": {"MEDSEG_HALO": "0"},
     "halo1": {"MEDSEG_HALO": "1", "MEDSEG_CTA2": "0"},
-    "halo2": {"MEDSEG_HALO": "1", "MEDSEG_CTA2": "1"},
+    "halo2": {"MEDSEG_HALO": "1", "MEDSEG_CTA2": "2"},
+    "auto": {},
+    "nostream2": {"MEDSEG_STREAM2": "0"},
 }
 
 
 def make_engine(blob, nb, env):
-    for k in ("MEDSEG_NAIVE_CONV", "MEDSEG_HALO", "MEDSEG_DESC_MODE", "MEDSEG_HALO_PITCH", "MEDSEG_CTA2"):
+    for k in ("MEDSEG_NAIVE_CONV", "MEDSEG_HALO", "MEDSEG_DESC_MODE", "MEDSEG_HALO_PITCH", "MEDSEG_CTA2", "MEDSEG_STREAM2"):
         os.environ.pop(k, None)
     os.environ.update(env)
     return ms.Engine({"weights": blob, "max_batch": nb})

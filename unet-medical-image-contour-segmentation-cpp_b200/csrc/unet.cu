@@ -247,7 +247,7 @@ void launch_halo2(const UNetLayer& L, const tc::ConvArgs& a, int sm_count, cudaS
     }
     const int pairs = a.batch * (a.H / tc::HALO_TH) * (a.W / tc::HALO_TW) / 2;
     const int grid = 2 * std::min(pairs, sm_count / 2);
-    tc::conv_halo2_kernel<BN, EPI, RKC><<<grid, tc::NUM_THREADS, C::SMEM_BYTES, st>>>(L.map_a_row, L.map_b_half, L.map_out, a);
+    tc::conv_halo2_kernel<BN, EPI, RKC><<<grid, tc::HALO2_THREADS, C::SMEM_BYTES, st>>>(L.map_a_row, L.map_b_half, L.map_out, a);
     MS_LAUNCH_CHECK();
 }
 
@@ -318,7 +318,9 @@ void UNet::load(const std::string& blob_path, int net_h, int net_w, int n_classe
     halo_enabled_ = !(hv && hv[0] == '0');
     const char* cv = std::getenv("MEDSEG_CTA2");
     cta2_enabled_ = !(cv && cv[0] == '0');
-    cta2_force_ = cv && cv[0] == '2';   // MEDSEG_CTA2=2: prefer the pair kernel wherever it applies (A/B measurements)
+    cta2_force_ = cv && cv[0] == '2';
+    const char* sv = std::getenv("MEDSEG_STREAM2");
+    stream2_enabled_ = !(sv && sv[0] == '0');   // MEDSEG_CTA2=2: prefer the pair kernel wherever it applies (A/B measurements)
     const char* pv = std::getenv("MEDSEG_HALO_PITCH");
     halo_pitch_ = 10;
     (void)pv;
@@ -407,6 +409,10 @@ void UNet::load(const std::string& blob_path, int net_h, int net_w, int n_classe
             } else if (fits2 && cta2_enabled_) {
                 L.halo = 2;
                 L.resident_kc = kc;
+                make_wgt_map(&L.map_b_half, L.w, cout, 9 * cin, L.block_n / 2);
+            } else if (cta2_enabled_ && stream2_enabled_ && L.block_n == 128 && ((h / tc::HALO_TH) * (w / tc::HALO_TW)) % 2 == 0) {
+                L.halo = 2;             // weights too large to stay resident: streamed by their own producer warp
+                L.resident_kc = 0;
                 make_wgt_map(&L.map_b_half, L.w, cout, 9 * cin, L.block_n / 2);
             }
             if (L.halo) make_act_map(&L.map_a_row, bufs_[src].p, max_batch, h, w, bufs_[src].C, tc::HALO_TW + 2, tc::HALO_TH + 2);
@@ -529,6 +535,7 @@ void UNet::run_layer(int li, const uint8_t* d_in_u8, int batch, uint8_t* d_mask,
         else if (L.kind != 3 && L.block_n == 64 && rk == 2) launch_halo2<64, tc::EPI_STORE, 2>(L, a, sm_count_, st);
         else if (L.kind != 3 && L.block_n == 128 && rk == 1) launch_halo2<128, tc::EPI_STORE, 1>(L, a, sm_count_, st);
         else if (L.kind != 3 && L.block_n == 128 && rk == 2) launch_halo2<128, tc::EPI_STORE, 2>(L, a, sm_count_, st);
+        else if (L.kind != 3 && L.block_n == 128 && rk == 0) launch_halo2<128, tc::EPI_STORE, 0>(L, a, sm_count_, st);
         else fail(MS_ERR_INTERNAL, "no halo2 kernel instantiation for layer " + L.name);
     } else if (L.halo) {
         if (L.kind == 3) launch_halo<64, tc::EPI_HEAD, 1>(L, a, sm_count_, st);

@@ -111,6 +111,21 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         if (clock64() - t0 > 4000000000ll) __trap();   // ~2 s at 2 GHz; real waits are microseconds
     }
 }
+// One lane of a fully converged warp (the same lane every time).  Issuing tcgen05 / TMA instructions under this
+// predicate inside warp-convergent control flow lets ptxas emit them straight-line; issuing them from a
+// divergent `if (lane == 0)` region makes it wrap every UTCHMMA in an ELECT / BRA.U.ANY loop (measured:
+// ~17 issue-slot instructions per MMA, the issuing thread became the bottleneck of the N <= 128 kernels).
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "elect.sync _|p, 0xFFFFFFFF;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}"
+        : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -431,8 +446,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             }
         }
     } else if (warp == 1) {
-        // ===================================================================== MMA issuer
-        if (lane == 0) {
+        // ===================================================================== MMA issuer (whole warp walks the
+        // pipeline, one elected lane issues)
+        {
             constexpr uint32_t idesc = make_idesc(BLOCK_N);
             int stage = 0;
             uint32_t phase = 0;
@@ -445,18 +461,20 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                 for (int ks = 0; ks < ksteps; ++ks) {
                     mbar_wait(&full_bar[stage], phase);
                     tc_fence_after();
-                    const uint32_t sa = smem_u32(smem + stage * C::STAGE_BYTES);
-                    const uint64_t adesc = make_smem_desc(sa);
-                    const uint64_t bdesc = make_smem_desc(sa + A_STAGE_BYTES);
-#pragma unroll
-                    for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+                    if (elect_one()) {
+                        const uint32_t sa = smem_u32(smem + stage * C::STAGE_BYTES);
+                        const uint64_t adesc = make_smem_desc(sa);
+                        const uint64_t bdesc = make_smem_desc(sa + A_STAGE_BYTES);
                         // advance 16 elements = 32 bytes along K inside the swizzle atom: +2 in 16-byte units
-                        umma_f16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (ks | k) != 0 ? 1u : 0u);
+                        umma_f16(d_tmem, adesc, bdesc, idesc, ks != 0 ? 1u : 0u);
+#pragma unroll
+                        for (int k = 1; k < BLOCK_K / UMMA_K; ++k) umma_f16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, 1u);
+                        umma_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
+                        if (ks == ksteps - 1) umma_commit(&tmem_full[acc]);   // accumulator complete -> epilogue
                     }
-                    umma_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
+                    __syncwarp();
                     if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
                 }
-                umma_commit(&tmem_full[acc]);        // accumulator complete -> epilogue
                 if (++acc == 2) { acc = 0; acc_phase ^= 1; }
             }
         }
@@ -535,6 +553,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
 conv_halo_kernel(const __grid_constant__ CUtensorMap map_a_row, const __grid_constant__ CUtensorMap map_b,
                  const __grid_constant__ CUtensorMap map_out, const ConvArgs args) {
     using C = HaloCfg<BLOCK_N, RESIDENT_KC, PITCH>;
+    static_assert(RESIDENT_KC > 0, "the single-CTA halo kernel keeps the layer's weights resident in shared memory");
     constexpr int HALO_STAGE_BYTES = C::HALO_STAGE_BYTES;
     constexpr int HALO_PITCH = PITCH;
     extern __shared__ uint8_t smem_raw[];
@@ -614,15 +633,14 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a_row, const __grid_con
             }
         }
     } else if (warp == 1) {
-        // ===================================================================== MMA issuer
-        if (lane == 0 && blockIdx.x < total) {
+        // ===================================================================== MMA issuer (whole warp walks the
+        // pipeline, one elected lane issues; the nine taps are straight-line code with immediate offsets)
+        if (blockIdx.x < total) {
             constexpr uint32_t idesc = make_idesc(BLOCK_N);
-            int sa = 0, sb = 0, acc = 0;
-            uint32_t pa = 0, pb = 0, acc_phase = 0;
-            if (RESIDENT_KC > 0) {
-                mbar_wait(res_full, 0);
-                tc_fence_after();
-            }
+            int sa = 0, acc = 0;
+            uint32_t pa = 0, acc_phase = 0;
+            mbar_wait(res_full, 0);
+            tc_fence_after();
             for (int t = blockIdx.x; t < total; t += gridDim.x) {
                 mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
                 tc_fence_after();
@@ -630,34 +648,26 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a_row, const __grid_con
                 for (int kc = 0; kc < kchunks; ++kc) {
                     mbar_wait(&a_full[sa], pa);
                     tc_fence_after();
-                    const uint32_t a_base = smem_u32(s_a + sa * HALO_STAGE_BYTES);
-#pragma unroll 1
-                    for (int tap = 0; tap < 9; ++tap) {
-                        uint32_t b_addr;
-                        if (RESIDENT_KC > 0) {
-                            b_addr = smem_u32(s_res + (tap * RESIDENT_KC + kc) * C::B_TILE_BYTES);
-                        } else {
-                            mbar_wait(&b_full[sb], pb);
-                            tc_fence_after();
-                            b_addr = smem_u32(s_b + sb * C::B_TILE_BYTES);
-                        }
-                        // shifted view of the halo buffer: tile row ty lives at halo row ty + (dy+1), column dx+1
-                        const uint32_t a_addr = a_base + (uint32_t)(((tap / 3) * HALO_PITCH + (tap % 3)) * 128);
-                        uint64_t adesc = make_smem_desc_sbo(a_addr, HALO_PITCH * 128);
-                        if (args.desc_mode == 1) adesc |= (uint64_t)((a_addr >> 7) & 7u) << 49;
-                        const uint64_t bdesc = make_smem_desc(b_addr);
+                    if (elect_one()) {
+                        // shifted views of the halo buffer: tile row ty lives at halo row ty + (dy+1), column dx+1
+                        const uint64_t a0 = make_smem_desc_sbo(smem_u32(s_a + sa * HALO_STAGE_BYTES), HALO_PITCH * 128);
+                        const uint64_t b0 = make_smem_desc(smem_u32(s_res + kc * C::B_TILE_BYTES));
 #pragma unroll
-                        for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
-                            umma_f16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kc | tap | k) != 0 ? 1u : 0u);
-                        if (RESIDENT_KC == 0) {
-                            umma_commit(&b_empty[sb]);
-                            if (++sb == C::B_STAGES) { sb = 0; pb ^= 1; }
+                        for (int tap = 0; tap < 9; ++tap) {
+                            constexpr int kAUnit = 128 / 16;                        // one 128-byte row in descriptor units
+                            const uint64_t adesc = a0 + (uint64_t)(((tap / 3) * HALO_PITCH + (tap % 3)) * kAUnit);
+                            const uint64_t bdesc = b0 + (uint64_t)(tap * RESIDENT_KC * (C::B_TILE_BYTES / 16));
+#pragma unroll
+                            for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
+                                umma_f16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc,
+                                         (tap | k) != 0 ? 1u : (kc != 0 ? 1u : 0u));
                         }
+                        umma_commit(&a_empty[sa]);
+                        if (kc == kchunks - 1) umma_commit(&tmem_full[acc]);
                     }
-                    umma_commit(&a_empty[sa]);
+                    __syncwarp();
                     if (++sa == C::A_STAGES) { sa = 0; pa ^= 1; }
                 }
-                umma_commit(&tmem_full[acc]);
                 if (++acc == 2) { acc = 0; acc_phase ^= 1; }
             }
         }
@@ -720,6 +730,7 @@ __device__ __forceinline__ uint32_t mapa_rank(uint32_t smem_addr, uint32_t rank)
 __device__ __forceinline__ void mbar_arrive_cluster_fwd(uint32_t cluster_addr) {
     asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
+constexpr int HALO2_THREADS = 224;   // warps 0/1 producer + MMA, 2..5 epilogue, 6 weight-tile producer (streaming mode)
 constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;   // clears the CTA-rank bit of a shared::cluster address -> CTA 0 of the pair
 __device__ __forceinline__ void tma2_load_4d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3) {
     asm volatile(
@@ -757,18 +768,21 @@ struct Halo2Cfg {
     static constexpr int HALO_STAGE_BYTES = HaloGeom<10>::STAGE_BYTES;
     static constexpr int B_TILE_BYTES = (BLOCK_N / 2) * BLOCK_K * 2;      // this CTA's half of one weight tile
     static constexpr int RES_BYTES = 9 * RESIDENT_KC * B_TILE_BYTES;
-    static constexpr int B_STAGES = RESIDENT_KC > 0 ? 0 : 8;
+    // streaming mode: one B stage = the three weight tiles of one filter row (3 taps), so a stage is worth
+    // 12 MMAs (~900 cycles) and five stages cover the TMA latency comfortably
+    static constexpr int B_STAGE_BYTES = 3 * B_TILE_BYTES;
+    static constexpr int B_STAGES = RESIDENT_KC > 0 ? 0 : 5;
     static constexpr int STG_BYTES = 4 * 4096;
     static constexpr int BUDGET = 227 * 1024 - 4096 - 1024 - STG_BYTES;
-    static constexpr int A_STAGES_RAW = (BUDGET - RES_BYTES - B_STAGES * B_TILE_BYTES) / HALO_STAGE_BYTES;
+    static constexpr int A_STAGES_RAW = (BUDGET - RES_BYTES - B_STAGES * B_STAGE_BYTES) / HALO_STAGE_BYTES;
     static constexpr int A_STAGES = A_STAGES_RAW > 4 ? 4 : A_STAGES_RAW;
     static constexpr int TMEM_COLS = 2 * BLOCK_N;
-    static constexpr int SMEM_BYTES = RES_BYTES + B_STAGES * B_TILE_BYTES + A_STAGES * HALO_STAGE_BYTES + STG_BYTES + 4096 + 1024;
+    static constexpr int SMEM_BYTES = RES_BYTES + B_STAGES * B_STAGE_BYTES + A_STAGES * HALO_STAGE_BYTES + STG_BYTES + 4096 + 1024;
     static_assert(A_STAGES >= 2, "halo2 kernel needs at least two A stages");
 };
 
 template <int BLOCK_N, int EPI, int RESIDENT_KC>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(HALO2_THREADS, 1)
 conv_halo2_kernel(const __grid_constant__ CUtensorMap map_a_halo, const __grid_constant__ CUtensorMap map_b_half,
                   const __grid_constant__ CUtensorMap map_out, const ConvArgs args) {
     using C = Halo2Cfg<BLOCK_N, RESIDENT_KC>;
@@ -779,7 +793,7 @@ conv_halo2_kernel(const __grid_constant__ CUtensorMap map_a_halo, const __grid_c
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* s_res = smem;
     uint8_t* s_b = smem + C::RES_BYTES;
-    uint8_t* s_a = s_b + C::B_STAGES * C::B_TILE_BYTES;
+    uint8_t* s_a = s_b + C::B_STAGES * C::B_STAGE_BYTES;
     uint8_t* s_stg = s_a + C::A_STAGES * HALO_STAGE_BYTES;
     uint8_t* aux = s_stg + C::STG_BYTES;
     uint64_t* a_full = reinterpret_cast<uint64_t*>(aux);
@@ -815,7 +829,7 @@ conv_halo2_kernel(const __grid_constant__ CUtensorMap map_a_halo, const __grid_c
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
     }
     if (EPI == EPI_HEAD) {
-        for (int i = threadIdx.x; i < args.n_classes * 64 + args.n_classes; i += NUM_THREADS)
+        for (int i = threadIdx.x; i < args.n_classes * 64 + args.n_classes; i += HALO2_THREADS)
             s_head[i] = i < args.n_classes * 64 ? args.head_w[i] : args.head_b[i - args.n_classes * 64];
     }
     tc_fence_before();
@@ -833,8 +847,8 @@ conv_halo2_kernel(const __grid_constant__ CUtensorMap map_a_halo, const __grid_c
                 for (int i = 0; i < 9 * RESIDENT_KC; ++i)
                     tma2_load_2d(s_res + i * C::B_TILE_BYTES, &map_b_half, res_full, (i / RESIDENT_KC) * args.Cin + (i % RESIDENT_KC) * BLOCK_K, n_half0);
             }
-            int sa = 0, sb = 0;
-            uint32_t pa = 0, pb = 0;
+            int sa = 0;
+            uint32_t pa = 0;
             for (int p = pair_id; p < total_pairs; p += n_pairs) {
                 const TileCoord tc = decode_tile(2 * p + (int)rank, 1, tiles_x, tiles_y, BLOCK_N, HALO_TW, HALO_TH);
                 for (int kc = 0; kc < kchunks; ++kc) {
@@ -842,20 +856,34 @@ conv_halo2_kernel(const __grid_constant__ CUtensorMap map_a_halo, const __grid_c
                     if (leader) mbar_expect_tx(&a_full[sa], 2 * HALO_BOX_BYTES);
                     tma2_load_4d(s_a + sa * HALO_STAGE_BYTES, &map_a_halo, &a_full[sa], kc * BLOCK_K, tc.x0 - 1, tc.y0 - 1, tc.b);
                     if (++sa == C::A_STAGES) { sa = 0; pa ^= 1; }
-                    if (RESIDENT_KC == 0) {
-                        for (int tap = 0; tap < 9; ++tap) {
-                            mbar_wait(&b_empty[sb], pb ^ 1);
-                            if (leader) mbar_expect_tx(&b_full[sb], 2 * C::B_TILE_BYTES);
-                            tma2_load_2d(s_b + sb * C::B_TILE_BYTES, &map_b_half, &b_full[sb], tap * args.Cin + kc * BLOCK_K, n_half0);
-                            if (++sb == C::B_STAGES) { sb = 0; pb ^= 1; }
-                        }
+                }
+            }
+        }
+    } else if (warp == 6) {
+        // ===================================================================== weight-tile producer (streaming mode)
+        // Its own warp, so the A ring (one halo per 64-channel chunk) and the B ring (one half tile per tap) run
+        // ahead independently instead of the halo of chunk c+1 queueing behind the nine weight tiles of chunk c.
+        if (RESIDENT_KC == 0 && lane == 0 && pair_id < total_pairs) {
+            const int n_half0 = (int)rank * (BLOCK_N / 2);
+            int sb = 0;
+            uint32_t pb = 0;
+            for (int p = pair_id; p < total_pairs; p += n_pairs) {
+                for (int kc = 0; kc < kchunks; ++kc) {
+                    for (int row = 0; row < 3; ++row) {
+                        mbar_wait(&b_empty[sb], pb ^ 1);
+                        if (leader) mbar_expect_tx(&b_full[sb], 2 * C::B_STAGE_BYTES);
+                        for (int j = 0; j < 3; ++j)
+                            tma2_load_2d(s_b + sb * C::B_STAGE_BYTES + j * C::B_TILE_BYTES, &map_b_half, &b_full[sb],
+                                         (row * 3 + j) * args.Cin + kc * BLOCK_K, n_half0);
+                        if (++sb == C::B_STAGES) { sb = 0; pb ^= 1; }
                     }
                 }
             }
         }
     } else if (warp == 1) {
-        // ===================================================================== MMA issuer (leader CTA only)
-        if (leader && lane == 0 && pair_id < total_pairs) {
+        // ===================================================================== MMA issuer (leader CTA only; the whole
+        // warp walks the pipeline, one elected lane issues, taps are straight-line code with immediate offsets)
+        if (leader && pair_id < total_pairs) {
             constexpr uint32_t idesc = make_idesc_m256(BLOCK_N);
             int sa = 0, sb = 0, acc = 0;
             uint32_t pa = 0, pb = 0, acc_phase = 0;
@@ -870,32 +898,52 @@ conv_halo2_kernel(const __grid_constant__ CUtensorMap map_a_halo, const __grid_c
                 for (int kc = 0; kc < kchunks; ++kc) {
                     mbar_wait(&a_full[sa], pa);
                     tc_fence_after();
-                    const uint32_t a_base = smem_u32(s_a + sa * HALO_STAGE_BYTES);
-#pragma unroll 1
-                    for (int tap = 0; tap < 9; ++tap) {
-                        uint32_t b_addr;
-                        if (RESIDENT_KC > 0) {
-                            b_addr = smem_u32(s_res + (tap * RESIDENT_KC + kc) * C::B_TILE_BYTES);
-                        } else {
+                    const uint64_t a0 = make_smem_desc_sbo(smem_u32(s_a + sa * HALO_STAGE_BYTES), HALO_PITCH * 128);
+                    constexpr int kAUnit = 128 / 16;
+                    if (RESIDENT_KC > 0) {
+                        if (elect_one()) {
+                            const uint64_t b0 = make_smem_desc(smem_u32(s_res + kc * C::B_TILE_BYTES));
+#pragma unroll
+                            for (int tap = 0; tap < 9; ++tap) {
+                                const uint64_t adesc = a0 + (uint64_t)(((tap / 3) * HALO_PITCH + (tap % 3)) * kAUnit);
+                                const uint64_t bdesc = b0 + (uint64_t)(tap * RESIDENT_KC * (C::B_TILE_BYTES / 16));
+#pragma unroll
+                                for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
+                                    umma2_f16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc,
+                                              (tap | k) != 0 ? 1u : (kc != 0 ? 1u : 0u));
+                            }
+                            umma2_commit_mc(&a_empty[sa]);
+                            if (kc == kchunks - 1) umma2_commit_mc(&tmem_full[acc]);
+                        }
+                        __syncwarp();
+                    } else {
+#pragma unroll
+                        for (int row = 0; row < 3; ++row) {                 // one B stage = the three taps of a filter row
                             mbar_wait(&b_full[sb], pb);
                             tc_fence_after();
-                            b_addr = smem_u32(s_b + sb * C::B_TILE_BYTES);
-                        }
-                        const uint32_t a_addr = a_base + (uint32_t)(((tap / 3) * HALO_PITCH + (tap % 3)) * 128);
-                        const uint64_t adesc = make_smem_desc_sbo(a_addr, HALO_PITCH * 128);
-                        const uint64_t bdesc = make_smem_desc(b_addr);
+                            if (elect_one()) {
+                                const uint64_t b0 = make_smem_desc(smem_u32(s_b + sb * C::B_STAGE_BYTES));
 #pragma unroll
-                        for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
-                            umma2_f16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kc | tap | k) != 0 ? 1u : 0u);
-                        if (RESIDENT_KC == 0) {
-                            umma2_commit_mc(&b_empty[sb]);
+                                for (int j = 0; j < 3; ++j) {
+                                    const uint64_t adesc = a0 + (uint64_t)((row * HALO_PITCH + j) * kAUnit);
+                                    const uint64_t bdesc = b0 + (uint64_t)(j * (C::B_TILE_BYTES / 16));
+#pragma unroll
+                                    for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
+                                        umma2_f16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc,
+                                                  (row | j | k) != 0 ? 1u : (kc != 0 ? 1u : 0u));
+                                }
+                                umma2_commit_mc(&b_empty[sb]);
+                                if (row == 2) {
+                                    umma2_commit_mc(&a_empty[sa]);
+                                    if (kc == kchunks - 1) umma2_commit_mc(&tmem_full[acc]);
+                                }
+                            }
+                            __syncwarp();
                             if (++sb == C::B_STAGES) { sb = 0; pb ^= 1; }
                         }
                     }
-                    umma2_commit_mc(&a_empty[sa]);
                     if (++sa == C::A_STAGES) { sa = 0; pa ^= 1; }
                 }
-                umma2_commit_mc(&tmem_full[acc]);
                 if (++acc == 2) { acc = 0; acc_phase ^= 1; }
             }
         }
