@@ -20,8 +20,9 @@ CONFIGS = {
     "halo2": {"MEDSEG_HALO": "1", "MEDSEG_CTA2": "2"},
     "auto": {},
     "nostream2": {"MEDSEG_STREAM2": "0"},
+    "nodeep2": {"MEDSEG_DEEP2": "0"},
 }
-ENV_KEYS = ("MEDSEG_NAIVE_CONV", "MEDSEG_HALO", "MEDSEG_DESC_MODE", "MEDSEG_HALO_PITCH", "MEDSEG_CTA2", "MEDSEG_STREAM2")
+ENV_KEYS = ("MEDSEG_NAIVE_CONV", "MEDSEG_HALO", "MEDSEG_DESC_MODE", "MEDSEG_HALO_PITCH", "MEDSEG_CTA2", "MEDSEG_STREAM2", "MEDSEG_DEEP2")
 
 
 def sm_clock():

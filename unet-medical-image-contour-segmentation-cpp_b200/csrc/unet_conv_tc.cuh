@@ -274,8 +274,15 @@ __device__ __forceinline__ void epilogue_tile(const ConvArgs& args, const float*
         int best_c = 0;
         for (int c = 0; c < args.n_classes; ++c) {
             float s = s_head[args.n_classes * 64 + c];
+            const float4* w4 = reinterpret_cast<const float4*>(s_head + c * 64);   // broadcast 16-byte loads
 #pragma unroll
-            for (int j = 0; j < 64; ++j) s = fmaf(f[j], s_head[c * 64 + j], s);
+            for (int j = 0; j < 16; ++j) {
+                const float4 w = w4[j];
+                s = fmaf(f[4 * j + 0], w.x, s);
+                s = fmaf(f[4 * j + 1], w.y, s);
+                s = fmaf(f[4 * j + 2], w.z, s);
+                s = fmaf(f[4 * j + 3], w.w, s);
+            }
             if (args.logits) args.logits[((size_t)e.b * args.n_classes + c) * plane + (size_t)e.y * args.W + e.x] = s;
             if (s > best) { best = s; best_c = c; }   // strict >: first max wins, NaN never wins
         }
@@ -771,7 +778,7 @@ struct Halo2Cfg {
     // streaming mode: one B stage = the three weight tiles of one filter row (3 taps), so a stage is worth
     // 12 MMAs (~900 cycles) and five stages cover the TMA latency comfortably
     static constexpr int B_STAGE_BYTES = 3 * B_TILE_BYTES;
-    static constexpr int B_STAGES = RESIDENT_KC > 0 ? 0 : 5;
+    static constexpr int B_STAGES = RESIDENT_KC > 0 ? 0 : (BLOCK_N == 256 ? 3 : 5);
     static constexpr int STG_BYTES = 4 * 4096;
     static constexpr int BUDGET = 227 * 1024 - 4096 - 1024 - STG_BYTES;
     static constexpr int A_STAGES_RAW = (BUDGET - RES_BYTES - B_STAGES * B_STAGE_BYTES) / HALO_STAGE_BYTES;
@@ -811,7 +818,8 @@ conv_halo2_kernel(const __grid_constant__ CUtensorMap map_a_halo, const __grid_c
     const bool leader = rank == 0;
     const int pair_id = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
     const int tiles_x = args.W / HALO_TW, tiles_y = args.H / HALO_TH;
-    const int total_pairs = (args.batch * tiles_y * tiles_x) >> 1;     // host guarantees an even tile count
+    const int n_tiles = args.n_total / BLOCK_N;                        // > 1 only in streaming mode (Cout = 512 / 1024)
+    const int total_pairs = ((args.batch * tiles_y * tiles_x) >> 1) * n_tiles;   // work items: (tile pair, n tile); even tile count
     const int kchunks = args.Cin / BLOCK_K;
 
     if (threadIdx.x == 0) {
@@ -850,7 +858,7 @@ conv_halo2_kernel(const __grid_constant__ CUtensorMap map_a_halo, const __grid_c
             int sa = 0;
             uint32_t pa = 0;
             for (int p = pair_id; p < total_pairs; p += n_pairs) {
-                const TileCoord tc = decode_tile(2 * p + (int)rank, 1, tiles_x, tiles_y, BLOCK_N, HALO_TW, HALO_TH);
+                const TileCoord tc = decode_tile(2 * (p / n_tiles) + (int)rank, 1, tiles_x, tiles_y, BLOCK_N, HALO_TW, HALO_TH);
                 for (int kc = 0; kc < kchunks; ++kc) {
                     mbar_wait(&a_empty[sa], pa ^ 1);
                     if (leader) mbar_expect_tx(&a_full[sa], 2 * HALO_BOX_BYTES);
@@ -868,13 +876,14 @@ conv_halo2_kernel(const __grid_constant__ CUtensorMap map_a_halo, const __grid_c
             int sb = 0;
             uint32_t pb = 0;
             for (int p = pair_id; p < total_pairs; p += n_pairs) {
+                const int n_row0 = (p % n_tiles) * BLOCK_N + n_half0;
                 for (int kc = 0; kc < kchunks; ++kc) {
                     for (int row = 0; row < 3; ++row) {
                         mbar_wait(&b_empty[sb], pb ^ 1);
                         if (leader) mbar_expect_tx(&b_full[sb], 2 * C::B_STAGE_BYTES);
                         for (int j = 0; j < 3; ++j)
                             tma2_load_2d(s_b + sb * C::B_STAGE_BYTES + j * C::B_TILE_BYTES, &map_b_half, &b_full[sb],
-                                         (row * 3 + j) * args.Cin + kc * BLOCK_K, n_half0);
+                                         (row * 3 + j) * args.Cin + kc * BLOCK_K, n_row0);
                         if (++sb == C::B_STAGES) { sb = 0; pb ^= 1; }
                     }
                 }
@@ -962,8 +971,9 @@ conv_halo2_kernel(const __grid_constant__ CUtensorMap map_a_halo, const __grid_c
         int acc = 0;
         uint32_t acc_phase = 0;
         for (int p = pair_id; p < total_pairs; p += n_pairs) {
-            const TileCoord tcd = decode_tile(2 * p + (int)rank, 1, tiles_x, tiles_y, BLOCK_N, HALO_TW, HALO_TH);
+            const TileCoord tcd = decode_tile(2 * (p / n_tiles) + (int)rank, 1, tiles_x, tiles_y, BLOCK_N, HALO_TW, HALO_TH);
             e.b = tcd.b; e.y0 = tcd.y0; e.x0 = tcd.x0; e.y = tcd.y0 + ly; e.x = tcd.x0 + lx;
+            e.n0 = (p % n_tiles) * BLOCK_N;
             mbar_wait(&tmem_full[acc], acc_phase);
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BLOCK_N);
