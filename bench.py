@@ -272,7 +272,7 @@ def run_ours(args, rank, world, local):
             tc_ms += ms_l
     achieved = tc_flops / (tc_ms / 1e3) / 1e12
     peak = peaks["bf16_sustained"]
-    roofline = {"bound": "tensor", "kernel": "ms::tc::conv_gemm_kernel (21 launches per step)", "achieved": achieved, "peak": peak,
+    roofline = {"bound": "tensor", "kernel": "ms::tc::conv_halo2_kernel / conv_halo_kernel / conv_gemm_kernel (21 tcgen05 launches per step)", "achieved": achieved, "peak": peak,
                 "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None, "peak_source": peaks["source"] + " (sustained cuBLAS bf16)",
                 "unet_ms_per_step": all_ms, "unet_share_of_step": all_ms / ms_per_step}
     if args.layer_table and rank == 0:
@@ -285,7 +285,7 @@ def run_ours(args, rank, world, local):
         run, cores = oracle_runner(n_classes, args.head, S)
         vol = host[0].numpy()
         run(vol[:1])
-        sample = args.cpu_sample or 8
+        sample = args.cpu_sample or min(32, len(vol))
         t0 = time.perf_counter()
         run(vol[:sample])
         dtc = time.perf_counter() - t0
