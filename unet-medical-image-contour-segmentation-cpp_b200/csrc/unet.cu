@@ -28,7 +28,7 @@ namespace {
 
 // ------------------------------------------------------------------ first conv (Cin = 1): direct
 // K = 9 is pure bandwidth (SURVEY.md hard part H5), so this layer stays on the CUDA cores.  One block =
-// one image row.  The three input rows are staged once in shared memory as x = float(u8) / 255.0f
+// eight image rows.  The three input rows are staged once in shared memory as x = float(u8) / 255.0f
 // (exactly src/process.cpp:38); every thread keeps the 9 x 8 weights of its 8 output channels in
 // registers and walks the row 4 pixels at a time, so the inner loop is FMAs and 16-byte NHWC stores
 // (a warp writes four fully used 128-byte lines per store instruction).
@@ -47,18 +47,21 @@ __device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
     return d;
 }
 
+constexpr int kFirstRows = 8;   // image rows per block: the weights-to-registers prologue and the halo rows are amortised
+
 __global__ void __launch_bounds__(256) first_conv_kernel(const uint8_t* __restrict__ in, int H, int W,
                                                           const float* __restrict__ w /*[64][9]*/, const float* __restrict__ bias,
                                                           __nv_bfloat16* __restrict__ out /*NHWC 64*/) {
-    extern __shared__ float srow[];           // [3][W + 2], column 0 <-> x = -1
+    extern __shared__ float srow[];           // [kFirstRows + 2][W + 2], column 0 <-> x = -1
     __shared__ float sw[64 * 9 + 64];
-    const int y = blockIdx.x % H;
-    const size_t img = (size_t)(blockIdx.x / H) * H * W;
+    const int blocks_per_img = H / kFirstRows;
+    const int y0 = (blockIdx.x % blocks_per_img) * kFirstRows;
+    const size_t img = (size_t)(blockIdx.x / blocks_per_img) * H * W;
     const int pitch = W + 2;
     for (int i = threadIdx.x; i < 64 * 9 + 64; i += 256) sw[i] = i < 576 ? w[i] : bias[i - 576];
-    for (int i = threadIdx.x; i < 3 * pitch; i += 256) {
+    for (int i = threadIdx.x; i < (kFirstRows + 2) * pitch; i += 256) {
         const int r = i / pitch, c = i % pitch;
-        const int yy = y + r - 1, xx = c - 1;
+        const int yy = y0 + r - 1, xx = c - 1;
         srow[i] = (yy >= 0 && yy < H && xx >= 0 && xx < W) ? __fdiv_rn((float)in[img + (size_t)yy * W + xx], 255.0f) : 0.0f;
     }
     __syncthreads();
@@ -70,27 +73,30 @@ __global__ void __launch_bounds__(256) first_conv_kernel(const uint8_t* __restri
 #pragma unroll
         for (int t = 0; t < 9; ++t) wr[j][t] = sw[(cg + j) * 9 + t];
     }
-    for (int x0 = g * 4; x0 < W; x0 += 128) {
-        float v[3][6];
+    for (int ry = 0; ry < kFirstRows; ++ry) {
+        const float* rows = srow + ry * pitch;
+        for (int x0 = g * 4; x0 < W; x0 += 128) {
+            float v[3][6];
 #pragma unroll
-        for (int r = 0; r < 3; ++r)
+            for (int r = 0; r < 3; ++r)
 #pragma unroll
-            for (int c = 0; c < 6; ++c) v[r][c] = srow[r * pitch + x0 + c];
+                for (int c = 0; c < 6; ++c) v[r][c] = rows[r * pitch + x0 + c];
 #pragma unroll
-        for (int p = 0; p < 4; ++p) {
-            uint32_t pk[4];
+            for (int p = 0; p < 4; ++p) {
+                uint32_t pk[4];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                // two output channels per packed FMA (sm_100 fma.rn.f32x2): same rounding as two scalar fmaf
-                float2 acc = make_float2(br[2 * j], br[2 * j + 1]);
+                for (int j = 0; j < 4; ++j) {
+                    // two output channels per packed FMA (sm_100 fma.rn.f32x2): same rounding as two scalar fmaf
+                    float2 acc = make_float2(br[2 * j], br[2 * j + 1]);
 #pragma unroll
-                for (int t = 0; t < 9; ++t) {
-                    const float x = v[t / 3][p + t % 3];
-                    acc = ffma2(make_float2(x, x), make_float2(wr[2 * j][t], wr[2 * j + 1][t]), acc);
+                    for (int t = 0; t < 9; ++t) {
+                        const float x = v[t / 3][p + t % 3];
+                        acc = ffma2(make_float2(x, x), make_float2(wr[2 * j][t], wr[2 * j + 1][t]), acc);
+                    }
+                    pk[j] = tc::pack_bf16(fmaxf(acc.x, 0.0f), fmaxf(acc.y, 0.0f));
                 }
-                pk[j] = tc::pack_bf16(fmaxf(acc.x, 0.0f), fmaxf(acc.y, 0.0f));
+                *reinterpret_cast<uint4*>(out + (img + (size_t)(y0 + ry) * W + x0 + p) * 64 + cg) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
             }
-            *reinterpret_cast<uint4*>(out + (img + (size_t)y * W + x0 + p) * 64 + cg) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
         }
     }
 }
@@ -524,7 +530,7 @@ void UNet::run_layer(int li, const uint8_t* d_in_u8, int batch, uint8_t* d_mask,
     const UNetLayer& L = layers_[li];
     const int h = H_ >> L.level, w = W_ >> L.level;
     if (L.kind == 0) {
-        first_conv_kernel<<<(unsigned)(batch * h), 256, 3 * (w + 2) * sizeof(float), st>>>(d_in_u8, h, w, L.w_f32, L.bias, bufs_[L.dst].p);
+        first_conv_kernel<<<(unsigned)(batch * h / kFirstRows), 256, (kFirstRows + 2) * (w + 2) * sizeof(float), st>>>(d_in_u8, h, w, L.w_f32, L.bias, bufs_[L.dst].p);
         MS_LAUNCH_CHECK();
         return;
     }
