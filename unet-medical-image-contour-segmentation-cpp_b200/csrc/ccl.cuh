@@ -1,29 +1,36 @@
-// ccl.cuh -- warp-level union-find connected-component labelling (header-only templates).
+// ccl.cuh -- run-based union-find connected-component labelling on bit-packed rows (header-only).
 //
-// One labeller, parametrised by pixel predicate and connectivity, used four times on the hot path
-// (SURVEY.md hard part H3):
+// One labeller, parametrised by connectivity, used four times on the hot path (SURVEY.md hard part H3):
 //   postprocess  : 8-connected components of the *inverse* foreground   (src/postprocess.cpp:26)
 //                  8-connected components of the opened foreground       (src/postprocess.cpp:64)
 //   mask2polygon : 8-connected foreground components  (what cv::findContours traces)
 //                  4-connected background components  (the RETR_EXTERNAL test)
-// It replaces cv::connectedComponentsWithStats; label numbering differs (the reference's results do
-// not depend on numbering): here a component's label is the slice-local linear index of its
-// raster-first pixel, which is exactly the start pixel cv::findContours uses.
+// It replaces cv::connectedComponentsWithStats; label numbering differs (the reference's results do not depend on
+// numbering): a component's label is the slice-local linear index of its raster-first pixel, which is exactly the
+// start pixel cv::findContours uses.
 //
-// Three passes over int32 labels (4 B/px scratch, not algorithmic traffic):
-//   init    : each warp owns a 32-pixel row segment; one ballot gives every pixel the index of the
-//             first pixel of its horizontal run inside the segment (runs are pre-merged for free).
-//   merge   : unions across segment boundaries and with the row above, pruned so that only the
-//             leftmost pixel of every "both rows set" stretch issues a union (lock-free atomicMin).
-//   resolve : path-compress to the root, then per-component area (warp-aggregated atomics) and a
-//             "touches the image border" flag.
+// Representation: the predicate image is one bit per pixel, 32 pixels per word (`wpitch` words per row).  A *run* is a
+// maximal sequence of set bits inside one word; its *head* is its first pixel.  Only heads own an entry of the int32
+// label plane, so the label traffic scales with the number of runs, not pixels (CT-like masks: ~2 runs per row), and
+// everything else -- neighbourhood tests, hole filling, 3x3 morphology -- is word-wide bit arithmetic.  One thread owns
+// one word:
+//   heads   : L[head] = head (area / flag cleared)                       -- fused into the kernels that produce bits
+//   merge   : seam with the previous word, then for the row above only the leftmost pixel of every "both rows set"
+//             stretch (plus the two diagonal cases for 8-connectivity) issues a lock-free atomicMin union
+//   resolve : every head is compressed to its root; per-root area (run lengths) and "touches the border" flag
+// After resolve the root of any pixel is L[head of its run], two dependent loads.
 #pragma once
 #include "common.cuh"
 
 namespace ms {
 namespace ccl {
 
-constexpr int kThreads = 256;  // 8 warps = 8 consecutive 32-pixel segments of one row
+constexpr int kThreads = 256;
+
+struct BitImage {           // one slice
+    const uint32_t* bits;   // H rows x wpitch words
+    int H, W, wpitch;
+};
 
 __device__ __forceinline__ int ld_label(const int* L, int i) { return __ldcg(L + i); }
 
@@ -54,89 +61,141 @@ __device__ __forceinline__ void unite(int* L, int a, int b) {
     } while (!done);
 }
 
-// grid = (ceil(W / 256), H, batch)
-template <class Pred>
-__global__ void __launch_bounds__(kThreads) init_kernel(const uint8_t* __restrict__ mask, int H, int W, Pred pred,
-                                                         int* __restrict__ labels, int* __restrict__ area,
-                                                         uint8_t* __restrict__ flag) {
-    const int x = blockIdx.x * kThreads + threadIdx.x, y = blockIdx.y;
-    const size_t slice = (size_t)blockIdx.z * H * W;
-    const int lane = threadIdx.x & 31;
-    const bool in = x < W;
-    const int p = y * W + x;
-    const bool fg = in && pred(mask[slice + p]);
-    const unsigned bits = __ballot_sync(0xFFFFFFFFu, fg);
-    if (!in) return;
-    int lab = -1;
-    if (fg) {
-        const unsigned zeros_below = ~bits & ((1u << lane) - 1u);
-        const int start = zeros_below ? 32 - __clz(zeros_below) : 0;
-        lab = p - lane + start;
-    }
-    labels[slice + p] = lab;
-    if (area) area[slice + p] = 0;
-    if (flag) flag[slice + p] = 0;
+__device__ __forceinline__ uint32_t valid_mask(int W, int wx) {   // bits of word wx that lie inside the image
+    const int rem = W - wx * 32;
+    return rem >= 32 ? 0xFFFFFFFFu : (rem <= 0 ? 0u : ((1u << rem) - 1u));
+}
+__device__ __forceinline__ uint32_t load_word(const uint32_t* bits, int H, int wpitch, int y, int wx) {
+    return (y >= 0 && y < H && wx >= 0 && wx < wpitch) ? __ldg(bits + (size_t)y * wpitch + wx) : 0u;
+}
+// first bit of the run (inside the word) that contains set bit x
+__device__ __forceinline__ int run_head_bit(uint32_t bits, int x) {
+    const uint32_t zeros_below = ~bits & ((1u << x) - 1u);
+    return zeros_below ? 32 - __clz(zeros_below) : 0;
+}
+__device__ __forceinline__ uint32_t head_mask(uint32_t bits) { return bits & ~(bits << 1); }
+// mask of the run starting at head bit x
+__device__ __forceinline__ uint32_t run_mask(uint32_t bits, int x) {
+    const uint32_t above = ~(bits >> x);                 // first zero at or above x
+    const int len = above ? __ffs((int)above) - 1 : 32 - x;
+    return (len >= 32 ? 0xFFFFFFFFu : ((1u << len) - 1u)) << x;
+}
+// head pixel (linear index) of the run containing pixel (X, y); the bit must be set
+__device__ __forceinline__ int head_pixel(const uint32_t* bits, int wpitch, int W, int y, int X) {
+    const int wx = X >> 5;
+    const uint32_t b = __ldg(bits + (size_t)y * wpitch + wx);
+    return y * W + (wx << 5) + run_head_bit(b, X & 31);
+}
+// root of the component containing pixel (X, y) -- valid after resolve_kernel
+__device__ __forceinline__ int root_of(const uint32_t* bits, const int* L, int wpitch, int W, int y, int X) {
+    return L[head_pixel(bits, wpitch, W, y, X)];
 }
 
-// grid = (ceil(W / 256), H, batch).  CONN = 4 or 8.
-template <int CONN>
-__global__ void __launch_bounds__(kThreads) merge_kernel(int* __restrict__ labels_all, int H, int W) {
-    const int x = blockIdx.x * kThreads + threadIdx.x, y = blockIdx.y;
-    int* L = labels_all + (size_t)blockIdx.z * H * W;
-    const int lane = threadIdx.x & 31;
-    const int seg0 = x - lane;  // first column of this warp's segment
-    const bool in = x < W;
-    const int p = y * W + x;
-    const bool fg = in && (ld_label(L, p) >= 0);
-    const bool up = in && y > 0 && (ld_label(L, p - W) >= 0);
-    const unsigned cur = __ballot_sync(0xFFFFFFFFu, fg);
-    const unsigned upb = __ballot_sync(0xFFFFFFFFu, up);
-    if (cur == 0) return;  // warp-uniform
-    // columns just outside the segment (loaded by every lane from the same address: one broadcast)
-    const bool w_out = seg0 > 0 && (ld_label(L, y * W + seg0 - 1) >= 0);
-    const bool e_out = seg0 + 32 < W && (ld_label(L, y * W + seg0 + 32) >= 0);
-    const bool nw_out = y > 0 && seg0 > 0 && (ld_label(L, (y - 1) * W + seg0 - 1) >= 0);
-    const bool ne_out = y > 0 && seg0 + 32 < W && (ld_label(L, (y - 1) * W + seg0 + 32) >= 0);
-    if (!fg) return;
-    const bool Wn = lane > 0 ? ((cur >> (lane - 1)) & 1u) : w_out;
-    const bool En = lane < 31 ? ((cur >> (lane + 1)) & 1u) : e_out;
-    const bool NWn = lane > 0 ? ((upb >> (lane - 1)) & 1u) : nw_out;
-    const bool NEn = lane < 31 ? ((upb >> (lane + 1)) & 1u) : ne_out;
-    const bool Nn = up;
-    // horizontal: runs inside a segment were merged by init; only the segment seam remains
-    if (lane == 0 && Wn) unite(L, p, p - 1);
-    if (Nn) {
-        // the leftmost pixel of a stretch where both rows are set links the two runs
-        if (!(Wn && NWn)) unite(L, p, p - W);
-    } else if (CONN == 8) {
-        if (NWn && !Wn) unite(L, p, p - W - 1);  // if W is set, W links to NW (its N) itself
-        if (NEn && !En) unite(L, p, p - W + 1);  // if E is set, E links to NE (its N) itself
+// word-parallel kernels: thread t of slice blockIdx.y owns word t of the slice (row t / wpitch, word t % wpitch);
+// grid = (ceil(H * wpitch / 256), batch)
+#define MS_CCL_WORD_COORDS()                                            \
+    const int widx = blockIdx.x * ::ms::ccl::kThreads + threadIdx.x;      \
+    if (widx >= H * wpitch) return;                                      \
+    const int y = widx / wpitch, wx = widx - y * wpitch;                 \
+    const int sl = blockIdx.y
+
+// ---- heads: L[head] = head, statistics cleared.  One thread per word.  INVERT labels the complement of `bits`.
+template <bool INVERT>
+__global__ void __launch_bounds__(kThreads) heads_kernel(const uint32_t* __restrict__ bits_all, int H, int W, int wpitch,
+                                                          int* __restrict__ L_all, int* __restrict__ area_all, uint8_t* __restrict__ flag_all) {
+    MS_CCL_WORD_COORDS();
+    const size_t slice = (size_t)sl * H * W;
+    uint32_t b = bits_all[((size_t)sl * H + y) * wpitch + wx];
+    if (INVERT) b = ~b & valid_mask(W, wx);
+    uint32_t h = head_mask(b);
+    while (h) {
+        const int x = __ffs((int)h) - 1;
+        h &= h - 1;
+        const size_t p = slice + (size_t)y * W + wx * 32 + x;
+        L_all[p] = y * W + wx * 32 + x;
+        if (area_all) area_all[p] = 0;
+        if (flag_all) flag_all[p] = 0;
     }
 }
 
-// grid = (ceil(W / 256), H, batch).  After this pass labels[p] is the component root (raster-first
-// pixel), area[root] the pixel count and flag[root] != 0 iff the component touches the image border.
-static __global__ void __launch_bounds__(kThreads) resolve_kernel(int* __restrict__ labels_all, int H, int W,
-                                                            int* __restrict__ area_all, uint8_t* __restrict__ flag_all) {
-    const int x = blockIdx.x * kThreads + threadIdx.x, y = blockIdx.y;
-    const size_t slice = (size_t)blockIdx.z * H * W;
-    int* L = labels_all + slice;
-    const bool in = x < W;
-    const int p = y * W + x;
-    int r = -1;
-    if (in && ld_label(L, p) >= 0) {
-        r = find_root(L, p);
+// ---- merge.  One thread per word.  CONN = 4 or 8.
+template <int CONN, bool INVERT>
+__global__ void __launch_bounds__(kThreads) merge_kernel(const uint32_t* __restrict__ bits_all, int H, int W, int wpitch,
+                                                          int* __restrict__ L_all) {
+    MS_CCL_WORD_COORDS();
+    const uint32_t* B = bits_all + (size_t)sl * H * wpitch;
+    int* L = L_all + (size_t)sl * H * W;
+    auto word = [&](int yy, int ww) -> uint32_t {
+        if (yy < 0 || ww < 0 || ww >= wpitch) return 0u;
+        uint32_t v = __ldg(B + (size_t)yy * wpitch + ww);
+        return INVERT ? (~v & valid_mask(W, ww)) : v;
+    };
+    const uint32_t cur = word(y, wx);
+    if (cur == 0) return;
+    const uint32_t cl = word(y, wx - 1), cr = word(y, wx + 1);
+    const uint32_t up = word(y - 1, wx), ul = word(y - 1, wx - 1), ur = word(y - 1, wx + 1);
+    const int row0 = y * W + wx * 32;
+    auto head_cur = [&](int x) { return row0 + run_head_bit(cur, x); };
+    auto head_up = [&](int X) {   // X in -1 .. 32 relative to this word
+        if (X < 0) return row0 - W - 32 + run_head_bit(ul, 31);
+        if (X > 31) return row0 - W + 32;                       // bit 0 of the right word is its own run head
+        return row0 - W + run_head_bit(up, X);
+    };
+    // horizontal: runs inside a word are one run by construction; only the seam with the previous word remains
+    if ((cur & 1u) && (cl >> 31)) unite(L, row0, row0 - 32 + run_head_bit(cl, 31));
+    if (y == 0) return;
+    const uint32_t curW = (cur << 1) | (cl >> 31), curE = (cur >> 1) | (cr << 31);
+    const uint32_t upNW = (up << 1) | (ul >> 31), upNE = (up >> 1) | (ur << 31);
+    // the leftmost pixel of a stretch where both rows are set links the two runs
+    uint32_t m = cur & up & ~(curW & upNW);
+    while (m) {
+        const int x = __ffs((int)m) - 1;
+        m &= m - 1;
+        unite(L, head_cur(x), head_up(x));
+    }
+    if (CONN == 8) {
+        m = cur & ~up & upNW & ~curW;      // if W is set, W links to NW (its N) itself
+        while (m) {
+            const int x = __ffs((int)m) - 1;
+            m &= m - 1;
+            unite(L, head_cur(x), head_up(x - 1));
+        }
+        m = cur & ~up & upNE & ~curE;      // if E is set, E links to NE (its N) itself
+        while (m) {
+            const int x = __ffs((int)m) - 1;
+            m &= m - 1;
+            unite(L, head_cur(x), head_up(x + 1));
+        }
+    }
+}
+
+// ---- resolve.  One thread per word: heads -> roots, per-root area and border flag.
+template <bool INVERT>
+__global__ void __launch_bounds__(kThreads) resolve_kernel(const uint32_t* __restrict__ bits_all, int H, int W, int wpitch,
+                                                            int* __restrict__ L_all, int* __restrict__ area_all,
+                                                            uint8_t* __restrict__ flag_all) {
+    MS_CCL_WORD_COORDS();
+    const size_t slice = (size_t)sl * H * W;
+    int* L = L_all + slice;
+    uint32_t b = bits_all[((size_t)sl * H + y) * wpitch + wx];
+    if (INVERT) b = ~b & valid_mask(W, wx);
+    uint32_t h = head_mask(b);
+    while (h) {
+        const int x = __ffs((int)h) - 1;
+        h &= h - 1;
+        const int p = y * W + wx * 32 + x;
+        const int r = find_root(L, p);
         L[p] = r;
+        const uint32_t rm = run_mask(b, x);
+        if (area_all) atomicAdd(&area_all[slice + r], __popc(rm));
+        if (flag_all) {
+            const int x_first = wx * 32 + x, x_last = wx * 32 + 31 - __clz(rm);
+            if (y == 0 || y == H - 1 || x_first == 0 || x_last == W - 1) flag_all[slice + r] = 1;
+        }
     }
-    if (area_all) {
-        // one atomic per distinct root per warp
-        const unsigned peers = __match_any_sync(0xFFFFFFFFu, r);
-        if (r >= 0 && (int)(__ffs(peers) - 1) == (int)(threadIdx.x & 31)) atomicAdd(&area_all[slice + r], __popc(peers));
-    }
-    if (flag_all && r >= 0 && (x == 0 || y == 0 || x == W - 1 || y == H - 1)) flag_all[slice + r] = 1;
 }
 
-inline dim3 grid_for(int H, int W, int batch) { return dim3(cdiv(W, kThreads), H, batch); }
+inline dim3 grid_for(int H, int wpitch, int batch) { return dim3(cdiv(H * wpitch, kThreads), batch); }
 
 }  // namespace ccl
 }  // namespace ms

@@ -133,8 +133,8 @@ struct PolyDev {              // device-resident polygon set + counters
 };
 struct M2pWs {
     CclWs fg, bg;
-    DevBuf nb;                // u8 per pixel: 8-neighbour foreground code
     DevBuf fgbits;            // u32 per 32 pixels: bit-packed foreground
+    DevBuf nb;                // large slices only: u8 per pixel, 8-neighbour foreground code
     PolyDev poly;
     PinBuf h_header;          // pinned int64[4]
 };

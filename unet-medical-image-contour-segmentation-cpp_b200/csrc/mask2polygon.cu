@@ -9,10 +9,12 @@
 //       component that reaches the image frame                       -> second ccl + border flag
 //   (3) contours ordered by descending start index                   -> count / scan / scatter
 //   (4)-(6) border following + CHAIN_APPROX_SIMPLE                   -> contour_trace.cuh, one
-//       thread per contour, two passes (count, then emit at scanned offsets)
+//       thread per contour on the bit-packed foreground (a whole slice of it in shared memory when it
+//       fits), two passes (count, then emit at scanned offsets)
 //   (7) coordinate mapping (int)(x * (double)orig_w / w)             -> fused into the emit pass
 // No host round trip happens between these launches: all sizes live in `header` on the device, so
 // the whole stage is CUDA-graph capturable and only the caller decides when to synchronise.
+// The u8 mask is read once (-> one bit per pixel); labelling is the run-based union-find of ccl.cuh.
 // Algorithmic bytes: H*W (mask read) + 8 B per vertex + 4 B per contour offset.
 #include "ccl.cuh"
 #include "contour_trace.cuh"
@@ -21,69 +23,65 @@ namespace ms {
 
 namespace {
 
-constexpr int TW = 32, TH = 8;
 constexpr size_t kTraceSmemMax = 200 * 1024;   // slices up to ~1264 x 1264 trace out of shared memory
 
-// Fused: threshold -> 8-neighbour code, foreground label init, background label init + flag clear.
-// grid = (ceil(W/32), ceil(H/8), batch), block = 256.
-__global__ void __launch_bounds__(256) m2p_init_kernel(const uint8_t* __restrict__ mask, int H, int W, int thr,
-                                                        int* __restrict__ Lfg, int* __restrict__ Lbg,
-                                                        uint8_t* __restrict__ bg_flag, uint8_t* __restrict__ nb,
-                                                        uint32_t* __restrict__ fgbits, int wpitch) {
-    __shared__ uint8_t S[TH + 2][TW + 2];
-    const size_t slice = (size_t)blockIdx.z * H * W;
-    const int x0 = blockIdx.x * TW, y0 = blockIdx.y * TH;
-    for (int i = threadIdx.x; i < (TH + 2) * (TW + 2); i += 256) {
-        const int ly = i / (TW + 2), lx = i % (TW + 2);
-        const int x = x0 + lx - 1, y = y0 + ly - 1;
-        S[ly][lx] = (x >= 0 && x < W && y >= 0 && y < H) ? (uint8_t)(mask[slice + (size_t)y * W + x] > thr) : (uint8_t)0;
+// mask -> bits of (mask > thr), one word per warp.  grid = (ceil(W / 256), H, batch), block = 256 (8 words)
+__global__ void __launch_bounds__(256) thr_bits_kernel(const uint8_t* __restrict__ mask, int H, int W, int wpitch, int thr,
+                                                        uint32_t* __restrict__ bits) {
+    const int x = blockIdx.x * 256 + threadIdx.x, y = blockIdx.y;
+    const bool fg = x < W && mask[((size_t)blockIdx.z * H + y) * W + x] > thr;   // src/mask2polygon.cpp:31 threshold(127)
+    const unsigned b = __ballot_sync(0xFFFFFFFFu, fg);
+    if ((threadIdx.x & 31) == 0 && (x >> 5) < wpitch) bits[((size_t)blockIdx.z * H + y) * wpitch + (x >> 5)] = b;
+}
+
+// number of external contour starts among the run heads of word `wx` of row `y`, and (optionally) their pixel indices.
+// A component's root is its raster-first pixel, always a run head.  External <=> the pixel left of it belongs to a
+// background component that reaches the image frame (x == 0: the frame itself).  SURVEY.md section 8(c) clause (2).
+__device__ __forceinline__ int external_starts(const uint32_t* __restrict__ B, const int* __restrict__ Lfg, const int* __restrict__ Lbg,
+                                               const uint8_t* __restrict__ bg_flag, int W, int wpitch, int y, int wx, int* out /*<= 16*/) {
+    const uint32_t fgw = __ldg(B + (size_t)y * wpitch + wx);
+    uint32_t h = ccl::head_mask(fgw);
+    int n = 0;
+    while (h) {
+        const int x = __ffs((int)h) - 1;
+        h &= h - 1;
+        const int X = wx * 32 + x, p = y * W + X;
+        if (Lfg[p] != p) continue;                       // not a component root
+        bool ext = X == 0;
+        if (!ext) {
+            // left neighbour is background (p is raster-first): root of its background run
+            const int wl = (X - 1) >> 5;
+            const uint32_t bgw = ~__ldg(B + (size_t)y * wpitch + wl) & ccl::valid_mask(W, wl);
+            const int hp = y * W + (wl << 5) + ccl::run_head_bit(bgw, (X - 1) & 31);
+            ext = bg_flag[Lbg[hp]] != 0;
+        }
+        if (ext) {
+            if (out) out[n] = p;
+            ++n;
+        }
     }
+    return n;
+}
+
+// word-parallel: block b covers words [256 b, 256 b + 256) of its slice.  grid = (blocks_per_slice, batch)
+__global__ void __launch_bounds__(256) count_starts_kernel(const uint32_t* __restrict__ bits, const int* __restrict__ Lfg,
+                                                            const int* __restrict__ Lbg, const uint8_t* __restrict__ bg_flag, int H, int W,
+                                                            int wpitch, int* __restrict__ block_counts) {
+    __shared__ int wsum[8];
+    const int widx = blockIdx.x * 256 + threadIdx.x;
+    const size_t slice = (size_t)blockIdx.y * H * W;
+    int c = 0;
+    if (widx < H * wpitch)
+        c = external_starts(bits + (size_t)blockIdx.y * H * wpitch, Lfg + slice, Lbg + slice, bg_flag + slice, W, wpitch, widx / wpitch,
+                            widx % wpitch, nullptr);
+    c = __reduce_add_sync(0xFFFFFFFFu, c);
+    if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = c;
     __syncthreads();
-    const int lx = threadIdx.x & 31, ly = threadIdx.x >> 5;
-    const int x = x0 + lx, y = y0 + ly;
-    const bool in = x < W && y < H;
-    const bool fg = in && S[ly + 1][lx + 1];
-    const bool bg = in && !fg;
-    const unsigned fbits = __ballot_sync(0xFFFFFFFFu, fg);
-    const unsigned bbits = __ballot_sync(0xFFFFFFFFu, bg);
-    // bit-packed foreground, one word per 32-pixel segment (the trace kernels keep a whole slice of it in smem)
-    if (lx == 0 && y < H) fgbits[((size_t)blockIdx.z * H + y) * wpitch + blockIdx.x] = fbits;
-    if (!in) return;
-    const int p = y * W + x;
-    const unsigned below = (1u << lx) - 1u;
-    unsigned code = 0;
-    int lf = -1, lb = -1;
-    if (fg) {
-        const unsigned z = ~fbits & below;
-        lf = p - lx + (z ? 32 - __clz(z) : 0);
-        code = (unsigned)S[ly + 1][lx + 2] | ((unsigned)S[ly][lx + 2] << 1) | ((unsigned)S[ly][lx + 1] << 2) |
-               ((unsigned)S[ly][lx] << 3) | ((unsigned)S[ly + 1][lx] << 4) | ((unsigned)S[ly + 2][lx] << 5) |
-               ((unsigned)S[ly + 2][lx + 1] << 6) | ((unsigned)S[ly + 2][lx + 2] << 7);
-    } else {
-        const unsigned z = ~bbits & below;
-        lb = p - lx + (z ? 32 - __clz(z) : 0);
+    if (threadIdx.x == 0) {
+        int t = 0;
+        for (int i = 0; i < 8; ++i) t += wsum[i];
+        block_counts[(size_t)blockIdx.y * gridDim.x + blockIdx.x] = t;
     }
-    Lfg[slice + p] = lf;
-    Lbg[slice + p] = lb;
-    bg_flag[slice + p] = 0;
-    nb[slice + p] = (uint8_t)code;
-}
-
-__device__ __forceinline__ bool is_external_start(const int* Lfg, const int* Lbg, const uint8_t* bg_flag, int W, int p) {
-    if (Lfg[p] != p) return false;                 // not a component root
-    if (p % W == 0) return true;                    // left neighbour is the frame itself
-    return bg_flag[Lbg[p - 1]] != 0;                // left neighbour is background (p is raster-first)
-}
-
-// grid = (blocks_per_slice, batch), block = 256: block b covers pixels [256 b, 256 b + 256) of its slice
-__global__ void __launch_bounds__(256) count_starts_kernel(const int* __restrict__ Lfg, const int* __restrict__ Lbg,
-                                                            const uint8_t* __restrict__ bg_flag, int W, int n_per_slice,
-                                                            int* __restrict__ block_counts) {
-    const size_t slice = (size_t)blockIdx.y * n_per_slice;
-    const int p = blockIdx.x * 256 + threadIdx.x;
-    const bool s = p < n_per_slice && is_external_start(Lfg + slice, Lbg + slice, bg_flag + slice, W, p);
-    const int c = __syncthreads_count(s);
-    if (threadIdx.x == 0) block_counts[(size_t)blockIdx.y * gridDim.x + blockIdx.x] = c;
 }
 
 // Block-wide exclusive scan of `v` (blockDim.x == 1024); returns the exclusive prefix, *total gets the sum.
@@ -153,30 +151,39 @@ __global__ void __launch_bounds__(1024) scan_slices_kernel(const int* __restrict
     }
 }
 
-// Scatter start pixels in *descending* raster order per slice.
-__global__ void __launch_bounds__(256) write_starts_kernel(const int* __restrict__ Lfg, const int* __restrict__ Lbg,
-                                                            const uint8_t* __restrict__ bg_flag, int W, int n_per_slice,
-                                                            const int* __restrict__ block_offsets,
+// Scatter start pixels in *descending* raster order per slice (SURVEY.md section 8(c) clause (3)).
+__global__ void __launch_bounds__(256) write_starts_kernel(const uint32_t* __restrict__ bits, const int* __restrict__ Lfg,
+                                                            const int* __restrict__ Lbg, const uint8_t* __restrict__ bg_flag, int H, int W,
+                                                            int wpitch, const int* __restrict__ block_offsets,
                                                             const int* __restrict__ slice_start, int cap_contours,
                                                             int* __restrict__ starts, int* __restrict__ start_slice) {
-    __shared__ int wcount[8];
+    __shared__ int wsum[8];
     const int b = blockIdx.y;
-    const size_t slice = (size_t)b * n_per_slice;
-    const int p = blockIdx.x * 256 + threadIdx.x;
-    const bool s = p < n_per_slice && is_external_start(Lfg + slice, Lbg + slice, bg_flag + slice, W, p);
-    const unsigned bits = __ballot_sync(0xFFFFFFFFu, s);
+    const int widx = blockIdx.x * 256 + threadIdx.x;
+    const size_t slice = (size_t)b * H * W;
+    int found[16];
+    int c = 0;
+    if (widx < H * wpitch)
+        c = external_starts(bits + (size_t)b * H * wpitch, Lfg + slice, Lbg + slice, bg_flag + slice, W, wpitch, widx / wpitch, widx % wpitch, found);
+    // exclusive prefix of c over the block (raster order = thread order)
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    if (lane == 0) wcount[warp] = __popc(bits);
+    int inc = c;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xFFFFFFFFu, inc, o);
+        if (lane >= o) inc += t;
+    }
+    if (lane == 31) wsum[warp] = inc;
     __syncthreads();
-    if (!s) return;
-    int rank = __popc(bits & ((1u << lane) - 1u));
-    for (int i = 0; i < warp; ++i) rank += wcount[i];
-    rank += block_offsets[(size_t)b * gridDim.x + blockIdx.x];
+    int rank = inc - c + block_offsets[(size_t)b * gridDim.x + blockIdx.x];
+    for (int i = 0; i < warp; ++i) rank += wsum[i];
     const int first = slice_start[b], total = slice_start[b + 1] - first;
-    const int pos = first + (total - 1 - rank);
-    if (pos < cap_contours) {
-        starts[pos] = p;
-        start_slice[pos] = b;
+    for (int i = 0; i < c; ++i) {
+        const int pos = first + (total - 1 - (rank + i));
+        if (pos < cap_contours) {
+            starts[pos] = found[i];
+            start_slice[pos] = b;
+        }
     }
 }
 
@@ -193,38 +200,72 @@ struct WriteEmit {
     }
 };
 
-// One thread per contour.  npts[c] <- number of kept vertices.
-__global__ void __launch_bounds__(128) trace_count_kernel(const uint8_t* __restrict__ nb, int W, int n_per_slice,
-                                                           const int* __restrict__ starts, const int* __restrict__ start_slice,
-                                                           long long* __restrict__ header, int cap_contours,
-                                                           int* __restrict__ npts) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    const long long n = header[0] < cap_contours ? header[0] : cap_contours;
-    if (c >= n) return;
-    const int cnt = trace_contour(nb + (size_t)start_slice[c] * n_per_slice, W, starts[c], 8 * n_per_slice + 8, CountEmit{});
-    if (cnt < 0) atomicAdd((unsigned long long*)&header[3], 1ull);
-    npts[c] = cnt < 0 ? 0 : cnt;
+// 8-neighbour foreground code of a pixel from bit-packed rows.  PADDED: `bits` has a zero word / zero row on every
+// side (shared-memory copy); otherwise bounds are checked (global memory, large slices).
+// Codes: 0=E 1=NE 2=N 3=NW 4=W 5=SW 6=S 7=SE ; bit0 of a 3-bit row window = x-1, bit1 = x, bit2 = x+1
+__device__ __forceinline__ unsigned code_from_rows(unsigned up, unsigned cu, unsigned dn) {
+    return ((cu >> 2) & 1u) | (((up >> 2) & 1u) << 1) | (((up >> 1) & 1u) << 2) | ((up & 1u) << 3) | ((cu & 1u) << 4) |
+           ((dn & 1u) << 5) | (((dn >> 1) & 1u) << 6) | (((dn >> 2) & 1u) << 7);
 }
-
-// ---- shared-memory variant: one CTA per slice keeps the slice's bit-packed foreground (H*W/8 bytes, padded by a
-// zero word / zero row on every side) in shared memory, so a border-following step costs six LDS instead of a
-// dependent global load.  Thread t traces contours slice_start[b] + t, + blockDim, ...
-struct BitsCode {
+struct PaddedBitsCode {
     const uint32_t* bits;   // (H + 2) rows x pitch words, row 0 / word 0 are the zero frame
     int pitch;
     __device__ __forceinline__ unsigned operator()(int, int x, int y) const {
-        // bits x-1 .. x+1 of rows y-1, y, y+1; pixel x lives at bit position x + 32 of the padded row
-        const int X = x + 31, w = X >> 5, sh = X & 31;
-        const uint32_t* r = bits + (size_t)y * pitch + w;          // padded row y   <-> image row y-1
-        const unsigned up = __funnelshift_r(r[0], r[1], sh) & 7u;
-        const unsigned cu = __funnelshift_r(r[pitch], r[pitch + 1], sh) & 7u;
-        const unsigned dn = __funnelshift_r(r[2 * pitch], r[2 * pitch + 1], sh) & 7u;
-        // 0=E 1=NE 2=N 3=NW 4=W 5=SW 6=S 7=SE ; bit0 = x-1, bit1 = x, bit2 = x+1
-        return ((cu >> 2) & 1u) | (((up >> 2) & 1u) << 1) | (((up >> 1) & 1u) << 2) | ((up & 1u) << 3) | ((cu & 1u) << 4) |
-               ((dn & 1u) << 5) | (((dn >> 1) & 1u) << 6) | (((dn >> 2) & 1u) << 7);
+        const int X = x + 31, w = X >> 5, sh = X & 31;              // pixel x lives at bit x + 32 of the padded row
+        const uint32_t* r = bits + (size_t)y * pitch + w;            // padded row y <-> image row y - 1
+        return code_from_rows(__funnelshift_r(r[0], r[1], sh) & 7u, __funnelshift_r(r[pitch], r[pitch + 1], sh) & 7u,
+                              __funnelshift_r(r[2 * pitch], r[2 * pitch + 1], sh) & 7u);
     }
 };
+// Large slices (the bit image does not fit in shared memory): expand the bits once into one 8-neighbour code byte
+// per foreground pixel, so a border-following step is a single dependent byte load.  One thread per word.
+__global__ void __launch_bounds__(ccl::kThreads) nb_codes_kernel(const uint32_t* __restrict__ bits_all, int H, int W, int wpitch,
+                                                                  uint8_t* __restrict__ nb_all) {
+    MS_CCL_WORD_COORDS();
+    const uint32_t* B = bits_all + (size_t)sl * H * wpitch;
+    auto win = [&](int yy) -> unsigned long long {     // bit k <-> x = 32 wx + k - 1
+        if (yy < 0 || yy >= H) return 0ull;
+        const uint32_t c = __ldg(B + (size_t)yy * wpitch + wx);
+        const uint32_t l = wx > 0 ? __ldg(B + (size_t)yy * wpitch + wx - 1) : 0u;
+        const uint32_t r = wx + 1 < wpitch ? __ldg(B + (size_t)yy * wpitch + wx + 1) : 0u;
+        return ((unsigned long long)c << 1) | (l >> 31) | ((unsigned long long)(r & 1u) << 33);
+    };
+    const unsigned long long up = win(y - 1), cu = win(y), dn = win(y + 1);
+    uint8_t* dst = nb_all + (size_t)sl * H * W + (size_t)y * W + wx * 32;
+    uint32_t fg = (uint32_t)(cu >> 1);
+    while (fg) {
+        const int x = __ffs((int)fg) - 1;
+        fg &= fg - 1;
+        dst[x] = (uint8_t)code_from_rows((unsigned)(up >> x) & 7u, (unsigned)(cu >> x) & 7u, (unsigned)(dn >> x) & 7u);
+    }
+}
 
+// Large slices: one thread per contour, rows read through L1/L2.  npts[c] <- number of kept vertices.
+template <bool EMIT>
+__global__ void __launch_bounds__(128) trace_global_kernel(const uint8_t* __restrict__ nb, int H, int W,
+                                                            const int* __restrict__ starts, const int* __restrict__ start_slice,
+                                                            long long* __restrict__ header, int cap_contours, int* __restrict__ npts,
+                                                            long long cap_points, double sx, double sy, int2* __restrict__ xy) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    const long long n = header[0] < cap_contours ? header[0] : cap_contours;
+    if (c >= n) return;
+    if (EMIT && header[1] > cap_points) {   // caller's buffer too small: write nothing, flag it
+        if (c == 0) header[2] |= 2;
+        return;
+    }
+    const NbImageCode code{nb + (size_t)start_slice[c] * H * W};
+    if (EMIT) {
+        trace_contour_fn(code, W, starts[c], 8 * H * W + 8, WriteEmit{xy + npts[c], sx, sy, 0});
+    } else {
+        const int cnt = trace_contour_fn(code, W, starts[c], 8 * H * W + 8, CountEmit{});
+        if (cnt < 0) atomicAdd((unsigned long long*)&header[3], 1ull);
+        npts[c] = cnt < 0 ? 0 : cnt;
+    }
+}
+
+// Shared-memory variant: one CTA per slice keeps the slice's bit-packed foreground (H*W/8 bytes, padded by a zero word /
+// zero row on every side) in shared memory, so a border-following step costs six LDS instead of dependent global
+// loads.  Thread t traces contours slice_start[b] + t, + blockDim, ...
 template <bool EMIT>
 __global__ void __launch_bounds__(128) trace_smem_kernel(const uint32_t* __restrict__ fgbits, int H, int W, int wpitch,
                                                           const int* __restrict__ starts, const int* __restrict__ slice_start,
@@ -244,7 +285,7 @@ __global__ void __launch_bounds__(128) trace_smem_kernel(const uint32_t* __restr
         sbits[i] = (r >= 1 && r <= H && c >= 1 && c <= wpitch) ? fgbits[((size_t)b * H + (r - 1)) * wpitch + (c - 1)] : 0u;
     }
     __syncthreads();
-    const BitsCode code{sbits, pitch};
+    const PaddedBitsCode code{sbits, pitch};
     for (int c = c_lo + threadIdx.x; c < c_hi; c += blockDim.x) {
         if (EMIT) {
             trace_contour_fn(code, W, starts[c], 8 * H * W + 8, WriteEmit{xy + npts[c], sx, sy, 0});
@@ -277,20 +318,32 @@ __global__ void __launch_bounds__(1024) scan_points_kernel(int* __restrict__ npt
     }
 }
 
-__global__ void __launch_bounds__(128) trace_emit_kernel(const uint8_t* __restrict__ nb, int W, int n_per_slice,
-                                                          const int* __restrict__ starts, const int* __restrict__ start_slice,
-                                                          const int* __restrict__ offsets, long long* __restrict__ header,
-                                                          int cap_contours, long long cap_points, double sx, double sy,
-                                                          int2* __restrict__ xy) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    const long long n = header[0] < cap_contours ? header[0] : cap_contours;
-    if (c >= n) return;
-    if (header[1] > cap_points) {  // caller's buffer too small: write nothing, flag it
-        if (c == 0) header[2] |= 2;
-        return;
+template <bool EMIT>
+void launch_trace(M2pWs& ws, PolyDev& P, int h, int w, int batch, double sx, double sy, cudaStream_t st) {
+    const int wpitch = cdiv(w, 32);
+    const size_t trace_smem = (size_t)(h + 2) * (wpitch + 2) * 4;
+    long long* header = P.header.as<long long>();
+    if (trace_smem <= kTraceSmemMax) {
+        static bool attr = false;
+        if (!attr) {
+            MS_CUDA(cudaFuncSetAttribute(trace_smem_kernel<EMIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTraceSmemMax));
+            attr = true;
+        }
+        trace_smem_kernel<EMIT><<<batch, 128, trace_smem, st>>>(ws.fgbits.as<uint32_t>(), h, w, wpitch, P.starts.as<int>(),
+                                                               P.slice_start.as<int>(), header, (int)P.cap_contours, P.npts.as<int>(),
+                                                               (long long)P.cap_points, sx, sy, P.xy.as<int2>());
+    } else {
+        if (!EMIT) {   // count pass first: build the code image
+            ws.nb.reserve((size_t)batch * h * w);
+            nb_codes_kernel<<<ccl::grid_for(h, wpitch, batch), ccl::kThreads, 0, st>>>(ws.fgbits.as<uint32_t>(), h, w, wpitch, ws.nb.as<uint8_t>());
+            MS_LAUNCH_CHECK();
+        }
+        trace_global_kernel<EMIT><<<cdiv((int)P.cap_contours, 128), 128, 0, st>>>(ws.nb.as<uint8_t>(), h, w, P.starts.as<int>(),
+                                                                                 P.start_slice.as<int>(), header, (int)P.cap_contours,
+                                                                                 P.npts.as<int>(), (long long)P.cap_points, sx, sy,
+                                                                                 P.xy.as<int2>());
     }
-    trace_contour(nb + (size_t)start_slice[c] * n_per_slice, W, starts[c], 8 * n_per_slice + 8,
-                  WriteEmit{xy + offsets[c], sx, sy, 0});
+    MS_LAUNCH_CHECK();
 }
 
 }  // namespace
@@ -302,13 +355,12 @@ void m2p_phase_a(M2pWs& ws, PolyDev& P, const uint8_t* d_mask, int h, int w, int
     const size_t nb = (size_t)n * batch;
     if (P.cap_contours == 0) P.cap_contours = std::max<int64_t>(1024, 64 * (int64_t)batch);
     if (P.cap_points == 0) P.cap_points = std::max<int64_t>(65536, 4096 * (int64_t)batch);
+    const int wpitch = cdiv(w, 32);
     ws.fg.labels.reserve(nb * 4);
     ws.bg.labels.reserve(nb * 4);
     ws.bg.flag.reserve(nb);
-    ws.nb.reserve(nb);
-    const int wpitch = cdiv(w, 32);
     ws.fgbits.reserve((size_t)batch * h * wpitch * 4);
-    const int bps = cdiv(n, 256);
+    const int bps = cdiv(h * wpitch, 256);
     P.block_counts.reserve(((size_t)bps * batch + batch + 1) * 4);
     P.slice_start.reserve(((size_t)batch + 1) * 4);
     P.starts.reserve((size_t)P.cap_contours * 4);
@@ -319,70 +371,45 @@ void m2p_phase_a(M2pWs& ws, PolyDev& P, const uint8_t* d_mask, int h, int w, int
     int* Lfg = ws.fg.labels.as<int>();
     int* Lbg = ws.bg.labels.as<int>();
     uint8_t* flag = ws.bg.flag.as<uint8_t>();
-    uint8_t* nbc = ws.nb.as<uint8_t>();
+    uint32_t* B = ws.fgbits.as<uint32_t>();
     int* bc = P.block_counts.as<int>();
     int* slice_total = bc + (size_t)bps * batch;
     long long* header = P.header.as<long long>();
+    const dim3 gw = ccl::grid_for(h, wpitch, batch);
 
-    m2p_init_kernel<<<dim3(cdiv(w, TW), cdiv(h, TH), batch), 256, 0, st>>>(d_mask, h, w, threshold, Lfg, Lbg, flag, nbc,
-                                                                          ws.fgbits.as<uint32_t>(), wpitch);
+    thr_bits_kernel<<<dim3(cdiv(w, 256), h, batch), 256, 0, st>>>(d_mask, h, w, wpitch, threshold, B);
     MS_LAUNCH_CHECK();
-    const dim3 g = ccl::grid_for(h, w, batch);
-    ccl::merge_kernel<8><<<g, ccl::kThreads, 0, st>>>(Lfg, h, w);
+    ccl::heads_kernel<false><<<gw, ccl::kThreads, 0, st>>>(B, h, w, wpitch, Lfg, nullptr, nullptr);      // 8-connected foreground
     MS_LAUNCH_CHECK();
-    ccl::merge_kernel<4><<<g, ccl::kThreads, 0, st>>>(Lbg, h, w);
+    ccl::heads_kernel<true><<<gw, ccl::kThreads, 0, st>>>(B, h, w, wpitch, Lbg, nullptr, flag);          // 4-connected background
     MS_LAUNCH_CHECK();
-    ccl::resolve_kernel<<<g, ccl::kThreads, 0, st>>>(Lfg, h, w, nullptr, nullptr);
+    ccl::merge_kernel<8, false><<<gw, ccl::kThreads, 0, st>>>(B, h, w, wpitch, Lfg);
     MS_LAUNCH_CHECK();
-    ccl::resolve_kernel<<<g, ccl::kThreads, 0, st>>>(Lbg, h, w, nullptr, flag);
+    ccl::merge_kernel<4, true><<<gw, ccl::kThreads, 0, st>>>(B, h, w, wpitch, Lbg);
     MS_LAUNCH_CHECK();
-    count_starts_kernel<<<dim3(bps, batch), 256, 0, st>>>(Lfg, Lbg, flag, w, n, bc);
+    ccl::resolve_kernel<false><<<gw, ccl::kThreads, 0, st>>>(B, h, w, wpitch, Lfg, nullptr, nullptr);
+    MS_LAUNCH_CHECK();
+    ccl::resolve_kernel<true><<<gw, ccl::kThreads, 0, st>>>(B, h, w, wpitch, Lbg, nullptr, flag);
+    MS_LAUNCH_CHECK();
+    count_starts_kernel<<<dim3(bps, batch), 256, 0, st>>>(B, Lfg, Lbg, flag, h, w, wpitch, bc);
     MS_LAUNCH_CHECK();
     scan_blocks_kernel<<<batch, 1024, 0, st>>>(bc, bps, slice_total);
     MS_LAUNCH_CHECK();
     scan_slices_kernel<<<1, 1024, 0, st>>>(slice_total, batch, P.slice_start.as<int>(), header);
     MS_LAUNCH_CHECK();
-    write_starts_kernel<<<dim3(bps, batch), 256, 0, st>>>(Lfg, Lbg, flag, w, n, bc, P.slice_start.as<int>(), (int)P.cap_contours,
+    write_starts_kernel<<<dim3(bps, batch), 256, 0, st>>>(B, Lfg, Lbg, flag, h, w, wpitch, bc, P.slice_start.as<int>(), (int)P.cap_contours,
                                                           P.starts.as<int>(), P.start_slice.as<int>());
     MS_LAUNCH_CHECK();
-    const size_t trace_smem = (size_t)(h + 2) * (wpitch + 2) * 4;
-    if (trace_smem <= kTraceSmemMax) {
-        static bool attr = false;
-        if (!attr) {
-            MS_CUDA(cudaFuncSetAttribute(trace_smem_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTraceSmemMax));
-            MS_CUDA(cudaFuncSetAttribute(trace_smem_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTraceSmemMax));
-            attr = true;
-        }
-        trace_smem_kernel<false><<<batch, 128, trace_smem, st>>>(ws.fgbits.as<uint32_t>(), h, w, wpitch, P.starts.as<int>(),
-                                                                P.slice_start.as<int>(), header, (int)P.cap_contours, P.npts.as<int>(),
-                                                                0, 1.0, 1.0, nullptr);
-    } else {
-        trace_count_kernel<<<cdiv((int)P.cap_contours, 128), 128, 0, st>>>(nbc, w, n, P.starts.as<int>(), P.start_slice.as<int>(), header,
-                                                                         (int)P.cap_contours, P.npts.as<int>());
-    }
-    MS_LAUNCH_CHECK();
+    launch_trace<false>(ws, P, h, w, batch, 1.0, 1.0, st);
     scan_points_kernel<<<1, 1024, 0, st>>>(P.npts.as<int>(), (int)P.cap_contours, header);
     MS_LAUNCH_CHECK();
 }
 
 void m2p_phase_b(M2pWs& ws, PolyDev& P, int h, int w, int batch, int orig_w, int orig_h, cudaStream_t st) {
-    const int n = h * w;
     // src/mask2polygon.cpp:199-200
     const double sx = static_cast<double>(orig_w) / w;
     const double sy = static_cast<double>(orig_h) / h;
-    const int wpitch = cdiv(w, 32);
-    const size_t trace_smem = (size_t)(h + 2) * (wpitch + 2) * 4;
-    if (trace_smem <= kTraceSmemMax) {
-        trace_smem_kernel<true><<<batch, 128, trace_smem, st>>>(ws.fgbits.as<uint32_t>(), h, w, wpitch, P.starts.as<int>(),
-                                                               P.slice_start.as<int>(), P.header.as<long long>(), (int)P.cap_contours,
-                                                               P.npts.as<int>(), (long long)P.cap_points, sx, sy, P.xy.as<int2>());
-    } else {
-        trace_emit_kernel<<<cdiv((int)P.cap_contours, 128), 128, 0, st>>>(ws.nb.as<uint8_t>(), w, n, P.starts.as<int>(),
-                                                                        P.start_slice.as<int>(), P.npts.as<int>(),
-                                                                        P.header.as<long long>(), (int)P.cap_contours,
-                                                                        (long long)P.cap_points, sx, sy, P.xy.as<int2>());
-    }
-    MS_LAUNCH_CHECK();
+    launch_trace<true>(ws, P, h, w, batch, sx, sy, st);
 }
 
 }  // namespace ms
