@@ -241,8 +241,8 @@ def run_ours(args, rank, world, local):
     torch.cuda.synchronize()
     dt = max_over_ranks(time.perf_counter() - t0)
     e2e_value = world * B * args.steps / dt
-    h2d = B * S * S * 2
-    d2h = int(polys.n_points * 8 + (polys.n_contours + 1) * 4 + (B + 1) * 4 + 32)
+    h2d = world * B * S * S * 2                        # whole job, like `value`
+    d2h = world * int(polys.n_points * 8 + (polys.n_contours + 1) * 4 + (B + 1) * 4 + 32)
     # the same through the synchronous single call, for reference
     t0 = time.perf_counter()
     for i in range(args.steps):
