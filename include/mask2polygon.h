@@ -37,4 +37,10 @@ void generate_json(const std::vector<std::vector<Point>>& contours, const std::s
 // replaces create_overlay_image  (src/mask2polygon.cpp:114-129); `gray` is the normalised 8-bit image
 void create_overlay_image(const std::vector<std::vector<Point>>& contours, const MaskView& gray, const std::string& overlay_path);
 
+// replaces process_single_mask  (src/mask2polygon.cpp:134-222): sidecar lookup, mask PNG read + size check, contours,
+// overlay on `original_png` (if not empty), coordinate mapping, <output_dir>/<base_name>.json.  Like the reference it
+// reports failures on std::cerr and returns nothing (src/mask2polygon.cpp:219-221).
+void process_single_mask(const std::string& mask_path, const std::string& output_dir, const std::string& json_path,
+                         const std::string& original_png, const std::string& base_name);
+
 }  // namespace Mask2Polygon

@@ -185,3 +185,38 @@ def test_async_pipeline_matches_sync(unet_engine, ms):
     with pytest.raises(ms.MedsegError) as ei:
         unet_engine.wait_batch(0)                  # nothing submitted
     assert ei.value.code == ms.MS_ERR_STATE
+
+
+def test_cpp_facade_stage_api(ms, blob3, tmp_path):
+    """The reference-shaped C++ API (include/*.h): whole-slice call, then the stages chained through files as
+    src/process.cpp:211-242 does (preprocess_raw -> mask PNG -> process_single_mask), plus the in-memory stage calls."""
+    import subprocess
+    import cv2
+    from medseg_b200 import synth
+    exe = str(tmp_path / "facade_driver")
+    r = subprocess.run(["g++", "-std=c++17", "-O1", "-I", os.path.join(ROOT, "include"), os.path.join(ROOT, "tests", "facade", "facade_driver.cpp"),
+                        "-o", exe, ms.LIB_PATH, "-Wl,-rpath," + os.path.dirname(ms.LIB_PATH)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-2000:]
+    src = synth.ct_slice(77, w=600, h=400)
+    raw = tmp_path / "slice.raw"
+    src.tofile(raw)
+    out = tmp_path / "out"
+    os.makedirs(out / "b")
+    r = subprocess.run([exe, blob3, str(raw), "600", "400", str(out)], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, (r.stdout[-1500:], r.stderr[-1500:])
+    assert "inmem: hole=2 contours=1 pts=4 first=(8,8)" in r.stdout
+    # whole-slice artefacts == stage-by-stage artefacts == oracle
+    ja, jb = open(out / "a" / "slice.json").read(), open(out / "b" / "slice.json").read()
+    assert ja == jb
+    na = cv2.imread(str(out / "a" / "slice_normalized.png"), cv2.IMREAD_UNCHANGED)
+    nb = cv2.imread(str(out / "b" / "slice_normalized.png"), cv2.IMREAD_UNCHANGED)
+    assert (na == nb).all() and (na == op.preprocess_raw(src)).all()
+    assert open(out / "b" / "slice_original_sizes.json").read() == op.sidecar_json_text("slice.raw", 600, 400)
+    vis = cv2.imread(str(out / "a" / "slice_mask.png"), cv2.IMREAD_UNCHANGED)
+    contours = op.extract_contours(vis)
+    assert ja == op.generate_json(op.map_contour_points(contours, 600 / 512, 400 / 512), "slice", 600, 400)
+    oa = cv2.imread(str(out / "a" / "slice_contour_overlay.png"))
+    ob = cv2.imread(str(out / "b" / "slice_contour_overlay.png"))
+    assert (oa == ob).all() and (oa == op.create_overlay_image(contours, na)).all()
+    log = open(out / "log" / "segmentation_log.txt").read()
+    assert "driver: engine ready" in log and "Total processing time:" in log and "All resources cleaned up successfully" in log

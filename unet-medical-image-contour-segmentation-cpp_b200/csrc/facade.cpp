@@ -231,4 +231,44 @@ void create_overlay_image(const std::vector<std::vector<Point>>& contours, const
         throw std::runtime_error("Fail to Save Overlay PNG: " + overlay_path);             // src/mask2polygon.cpp:126-128
 }
 
+void process_single_mask(const std::string& mask_path, const std::string& output_dir, const std::string& json_path,
+                         const std::string& original_png, const std::string& base_name) {
+    try {
+        std::cout << "Processing Mask: " << base_name + ".png" << std::endl;                       // :141
+        const SizeInfo sz = load_size_json(json_path, base_name);                                   // :144-160
+        std::cout << "Original Size: " << sz.original_width << "x" << sz.original_height << std::endl;
+        std::cout << "Scaled Size: " << sz.scaled_width << "x" << sz.scaled_height << std::endl;
+        ms::png::Image mimg;
+        if (!ms::png::read_file(mask_path, mimg)) throw std::runtime_error("Fail to Read Mask File: " + mask_path);   // :166-169
+        if (mimg.w != sz.scaled_width || mimg.h != sz.scaled_height)                                 // :172-179
+            throw std::runtime_error("Mask size mismatch: " + std::to_string(mimg.w) + "x" + std::to_string(mimg.h) + " (actual) vs " +
+                                     std::to_string(sz.scaled_width) + "x" + std::to_string(sz.scaled_height) + " (JSON)");
+        const std::vector<uint8_t> grey = ms::png::to_grey(mimg);
+        const auto contours = extract_contours(MaskView{grey.data(), mimg.h, mimg.w});              // :182
+        if (contours.empty()) {
+            std::cout << "Warning: No Contours Detected" << std::endl;                              // :184-185
+            return;
+        }
+        std::cout << "Extracted " << contours.size() << " Contours" << std::endl;
+        if (!original_png.empty()) {                                                                // :189-196
+            ms::png::Image oimg;
+            if (!ms::png::read_file(original_png, oimg)) throw std::runtime_error("Fail to Read Original Image: " + original_png);
+            const std::vector<uint8_t> og = ms::png::to_grey(oimg);
+            const std::string overlay_path = output_dir + "/" + base_name + "_contour_overlay.png";
+            create_overlay_image(contours, MaskView{og.data(), oimg.h, oimg.w}, overlay_path);
+            std::cout << "Overlay Image Saved to: " << overlay_path << std::endl;
+        } else {
+            std::cout << "Warning: Original PNG not provided, skipping overlay generation" << std::endl;
+        }
+        const double scale_x = static_cast<double>(sz.original_width) / sz.scaled_width;            // :199-200
+        const double scale_y = static_cast<double>(sz.original_height) / sz.scaled_height;
+        const auto mapped = map_contour_points(contours, scale_x, scale_y);
+        const std::string out_json = output_dir + "/" + base_name + ".json";                        // :206
+        generate_json(mapped, out_json, base_name, sz.original_width, sz.original_height);
+        std::cout << "JSON Saved to: " << out_json << std::endl;
+    } catch (const std::exception& e) {
+        std::cerr << "Processing Failure: " << e.what() << std::endl;                               // :219-221
+    }
+}
+
 }  // namespace Mask2Polygon
