@@ -201,7 +201,6 @@ def test_cpp_facade_stage_api(ms, blob3, tmp_path):
     raw = tmp_path / "slice.raw"
     src.tofile(raw)
     out = tmp_path / "out"
-    os.makedirs(out / "b")
     r = subprocess.run([exe, blob3, str(raw), "600", "400", str(out)], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, (r.stdout[-1500:], r.stderr[-1500:])
     assert "inmem: hole=2 contours=1 pts=4 first=(8,8)" in r.stdout

@@ -21,8 +21,9 @@ CONFIGS = {
     "auto": {},
     "nostream2": {"MEDSEG_STREAM2": "0"},
     "nodeep2": {"MEDSEG_DEEP2": "0"},
+    "stream128": {"MEDSEG_RES_BIG": "0"},
 }
-ENV_KEYS = ("MEDSEG_NAIVE_CONV", "MEDSEG_HALO", "MEDSEG_DESC_MODE", "MEDSEG_HALO_PITCH", "MEDSEG_CTA2", "MEDSEG_STREAM2", "MEDSEG_DEEP2")
+ENV_KEYS = ("MEDSEG_NAIVE_CONV", "MEDSEG_HALO", "MEDSEG_DESC_MODE", "MEDSEG_HALO_PITCH", "MEDSEG_CTA2", "MEDSEG_STREAM2", "MEDSEG_DEEP2", "MEDSEG_RES_BIG")
 
 
 def sm_clock():

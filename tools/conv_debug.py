@@ -24,11 +24,12 @@ CONFIGS = {
     "auto": {},
     "nostream2": {"MEDSEG_STREAM2": "0"},
     "nodeep2": {"MEDSEG_DEEP2": "0"},
+    "stream128": {"MEDSEG_RES_BIG": "0"},
 }
 
 
 def make_engine(blob, nb, env):
-    for k in ("MEDSEG_NAIVE_CONV", "MEDSEG_HALO", "MEDSEG_DESC_MODE", "MEDSEG_HALO_PITCH", "MEDSEG_CTA2", "MEDSEG_STREAM2", "MEDSEG_DEEP2"):
+    for k in ("MEDSEG_NAIVE_CONV", "MEDSEG_HALO", "MEDSEG_DESC_MODE", "MEDSEG_HALO_PITCH", "MEDSEG_CTA2", "MEDSEG_STREAM2", "MEDSEG_DEEP2", "MEDSEG_RES_BIG"):
         os.environ.pop(k, None)
     os.environ.update(env)
     return ms.Engine({"weights": blob, "max_batch": nb})

@@ -15,6 +15,7 @@
 #include "overlay.hpp"
 
 #include <cstdio>
+#include <filesystem>
 #include <fstream>
 #include <iostream>
 #include <sstream>
@@ -145,6 +146,10 @@ bool preprocess_raw(const std::string& raw_path, const std::string& png_path, co
     if (got != src.size() || ms_preprocess_host(hd, src.data(), w, h, 1, dst.data()) != MS_OK) {
         std::cerr << "preprocess_raw error: " << (got != src.size() ? "short read" : ms_last_error(hd)) << '\n';
         return false;
+    }
+    {
+        std::error_code ec;
+        std::filesystem::create_directories(std::filesystem::path(png_path).parent_path(), ec);   // :121
     }
     if (!ms::png::write_file(png_path, dst.data(), info.net_w, info.net_h, 1)) {       // :122
         std::cerr << "preprocess_raw error: imwrite failed" << '\n';

@@ -343,6 +343,8 @@ void UNet::load(const std::string& blob_path, int net_h, int net_w, int n_classe
     cta2_force_ = cv && cv[0] == '2';
     const char* d2 = std::getenv("MEDSEG_DEEP2");
     deep2_enabled_ = !(d2 && d2[0] == '0');
+    const char* rb = std::getenv("MEDSEG_RES_BIG");
+    res_big_ = !(rb && rb[0] == '0');
     const char* sv = std::getenv("MEDSEG_STREAM2");
     stream2_enabled_ = !(sv && sv[0] == '0');   // MEDSEG_CTA2=2: prefer the pair kernel wherever it applies (A/B measurements)
     const char* pv = std::getenv("MEDSEG_HALO_PITCH");
@@ -425,8 +427,14 @@ void UNet::load(const std::string& blob_path, int net_h, int net_w, int n_classe
         // per-tap streaming kernel is faster.
         if (halo_enabled_ && cout == L.block_n && L.block_n <= 128 && h % tc::HALO_TH == 0 && w % tc::HALO_TW == 0) {
             const int kc = cin / tc::BLOCK_K;
-            const bool fits1 = 9 * kc * L.block_n * 128 <= 144 * 1024;
-            const bool fits2 = 9 * kc * (L.block_n / 2) * 128 <= 144 * 1024 && ((h / tc::HALO_TH) * (w / tc::HALO_TW)) % 2 == 0;
+            // single CTA: all weights resident.  With two chunks a 144 KiB weight set leaves only two halo stages and the
+            // pair kernel (half the weights per CTA, four stages) is faster; with one chunk per tile the pair kernel's
+            // cross-CTA hand-offs are not amortised and it loses (profiles/r1_ab_pair_vs_single.log).
+            const int bytes1 = 9 * kc * L.block_n * 128;
+            const bool fits1 = bytes1 <= 144 * 1024 && (kc == 1 || bytes1 <= 96 * 1024);
+            const bool pair_ok = ((h / tc::HALO_TH) * (w / tc::HALO_TW)) % 2 == 0;
+            // a resident half-weight set that leaves room for only two halo stages loses to streaming (measured)
+            const bool fits2 = 9 * kc * (L.block_n / 2) * 128 <= (res_big_ ? 144 : 96) * 1024 && pair_ok;
             if (fits1 && !(cta2_force_ && fits2)) {
                 L.halo = 1;
                 L.resident_kc = kc;

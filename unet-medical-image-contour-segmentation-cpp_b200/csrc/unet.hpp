@@ -62,6 +62,7 @@ class UNet {
     bool cta2_enabled_ = true;  // MEDSEG_CTA2=0: single-CTA halo kernel only
     bool cta2_force_ = false;
     bool deep2_enabled_ = true;    // MEDSEG_DEEP2=0: per-tap kernel for the N = 256 layers
+    bool res_big_ = true;          // MEDSEG_RES_BIG=0: 144 KiB half-weight sets stream instead of staying resident
     bool stream2_enabled_ = true;  // MEDSEG_STREAM2=0: per-tap kernel instead of the streaming pair kernel (dec2a)
     int halo_pitch_ = 16;       // MEDSEG_HALO_PITCH
     int desc_mode_ = 0;         // MEDSEG_DESC_MODE: UMMA descriptor base-offset convention of the halo kernel
