@@ -134,7 +134,6 @@ struct PolyDev {              // device-resident polygon set + counters
 struct M2pWs {
     CclWs fg, bg;
     DevBuf fgbits;            // u32 per 32 pixels: bit-packed foreground
-    DevBuf nb;                // large slices only: u8 per pixel, 8-neighbour foreground code
     PolyDev poly;
     PinBuf h_header;          // pinned int64[4]
 };

@@ -48,42 +48,76 @@ MS_HD uint8_t trace_load(const uint8_t* nb, int i) {
 #endif
 }
 
-// Walks one outer border.  `code(p, x, y)` returns the 8-neighbour foreground code of pixel p = y * W + x;
-// `emit(x, y)` is called for every kept vertex, in order.
-// Returns the number of kept vertices, or -1 if `max_steps` was exhausted (corrupt input).
-template <class Code, class Emit>
-MS_HD int trace_contour_fn(Code code, int W, int start, int max_steps, Emit emit) {
-    int x = start % W, y = start / W;
-    const unsigned c0 = code(start, x, y);
-    if (c0 == 0) {  // isolated pixel
-        emit(x, y);
-        return 1;
-    }
-    // probe 3,2,1,0,7,6,5,4: reverse the byte so that bit k <-> direction (3 - k) & 7
-    unsigned rev = 0;
+// Resumable walk.  `code(p, x, y)` returns the 8-neighbour foreground code of pixel p = y * W + x; `emit(x, y)` is called
+// for every kept vertex, in order; `inside(x, y)` says whether `code` can currently be evaluated at that pixel (always
+// true for a whole-image code source; a shared-memory window returns false when the walk leaves it, the caller then
+// re-centres the window and calls trace_run again with the same state).
+struct TraceState {
+    int start, last, p, x, y, d_prev, prev_out, n;
+    int phase;   // 0 = not started, 1 = walking, 2 = finished
+};
+MS_HD void trace_begin(TraceState& s, int W, int start) {
+    s.start = start; s.p = start; s.x = start % W; s.y = start / W; s.n = 0; s.phase = 0;
+    s.last = 0; s.d_prev = 0; s.prev_out = 0;
+}
+// returns 1 = finished (s.n kept vertices), 0 = paused because the current pixel is not `inside`, -1 = `max_steps` exhausted
+template <class Code, class Emit, class Inside>
+MS_HD int trace_run(Code code, int W, TraceState& s, int max_steps, Emit& emit, Inside inside) {
+    if (s.phase == 2) return 1;
+    if (s.phase == 0) {
+        if (!inside(s.x, s.y)) return 0;
+        const unsigned c0 = code(s.p, s.x, s.y);
+        if (c0 == 0) {  // isolated pixel
+            emit(s.x, s.y);
+            s.n = 1;
+            s.phase = 2;
+            return 1;
+        }
+        // probe 3,2,1,0,7,6,5,4: reverse the byte so that bit k <-> direction (3 - k) & 7
+        unsigned rev = 0;
 #pragma unroll
-    for (int k = 0; k < 8; ++k) rev |= ((c0 >> ((3 - k) & 7)) & 1u) << k;
-    const int dL = (3 - trace_first_set(rev)) & 7;
-    const int last = start + trace_dy(dL) * W + trace_dx(dL);
-    int p = start, d_prev = dL, prev_out = (dL + 4) & 7, n = 0;
+        for (int k = 0; k < 8; ++k) rev |= ((c0 >> ((3 - k) & 7)) & 1u) << k;
+        const int dL = (3 - trace_first_set(rev)) & 7;
+        s.last = s.start + trace_dy(dL) * W + trace_dx(dL);
+        s.d_prev = dL;
+        s.prev_out = (dL + 4) & 7;
+        s.phase = 1;
+    }
     for (int step = 0; step < max_steps; ++step) {
-        const unsigned cc = code(p, x, y);
-        const unsigned rot = ((cc | (cc << 8)) >> ((d_prev + 1) & 7)) & 0xFFu;  // bit k <-> direction d_prev+1+k
-        const int d = (d_prev + 1 + trace_first_set(rot)) & 7;                  // rot != 0: the way back is always set
-        if (d != prev_out) {
-            emit(x, y);
-            ++n;
-            prev_out = d;
+        if (!inside(s.x, s.y)) return 0;
+        const unsigned cc = code(s.p, s.x, s.y);
+        const unsigned rot = ((cc | (cc << 8)) >> ((s.d_prev + 1) & 7)) & 0xFFu;  // bit k <-> direction d_prev+1+k
+        const int d = (s.d_prev + 1 + trace_first_set(rot)) & 7;                  // rot != 0: the way back is always set
+        if (d != s.prev_out) {
+            emit(s.x, s.y);
+            ++s.n;
+            s.prev_out = d;
         }
         const int ddx = trace_dx(d), ddy = trace_dy(d);
-        const int q = p + ddy * W + ddx;
-        if (q == start && p == last) return n;
-        p = q;
-        x += ddx;
-        y += ddy;
-        d_prev = (d + 4) & 7;
+        const int q = s.p + ddy * W + ddx;
+        if (q == s.start && s.p == s.last) {
+            s.phase = 2;
+            return 1;
+        }
+        s.p = q;
+        s.x += ddx;
+        s.y += ddy;
+        s.d_prev = (d + 4) & 7;
     }
     return -1;
+}
+
+struct TraceAlwaysInside {
+    MS_HD bool operator()(int, int) const { return true; }
+};
+
+// Walks one outer border in one go.  Returns the number of kept vertices, or -1 if `max_steps` was exhausted.
+template <class Code, class Emit>
+MS_HD int trace_contour_fn(Code code, int W, int start, int max_steps, Emit emit) {
+    TraceState s;
+    trace_begin(s, W, start);
+    const int r = trace_run(code, W, s, max_steps, emit, TraceAlwaysInside{});
+    return r == 1 ? s.n : -1;
 }
 
 struct NbImageCode {   // neighbour codes precomputed per pixel in global memory

@@ -342,7 +342,7 @@ void ms_destroy(ms_handle* h) {
     h->log("All resources cleaned up successfully");    // :52
     for (DevBuf* b : {&h->d_src, &h->d_norm, &h->d_mask_raw, &h->d_mask, &h->d_logits, &h->d_scratch_in, &h->d_scratch_out,
                       &h->pre.minmax, &h->post.ccl.labels, &h->post.ccl.area, &h->post.ccl.flag, &h->post.bin_a, &h->post.bin_b,
-                      &h->m2p.fg.labels, &h->m2p.fg.area, &h->m2p.fg.flag, &h->m2p.bg.labels, &h->m2p.bg.area, &h->m2p.bg.flag, &h->m2p.fgbits, &h->m2p.nb,
+                      &h->m2p.fg.labels, &h->m2p.fg.area, &h->m2p.fg.flag, &h->m2p.bg.labels, &h->m2p.bg.area, &h->m2p.bg.flag, &h->m2p.fgbits,
                       &h->m2p.poly.starts, &h->m2p.poly.start_slice, &h->m2p.poly.npts, &h->m2p.poly.slice_start,
                       &h->m2p.poly.block_counts, &h->m2p.poly.xy, &h->m2p.poly.header})
         b->release();

@@ -217,49 +217,72 @@ struct PaddedBitsCode {
                               __funnelshift_r(r[2 * pitch], r[2 * pitch + 1], sh) & 7u);
     }
 };
-// Large slices (the bit image does not fit in shared memory): expand the bits once into one 8-neighbour code byte
-// per foreground pixel, so a border-following step is a single dependent byte load.  One thread per word.
-__global__ void __launch_bounds__(ccl::kThreads) nb_codes_kernel(const uint32_t* __restrict__ bits_all, int H, int W, int wpitch,
-                                                                  uint8_t* __restrict__ nb_all) {
-    MS_CCL_WORD_COORDS();
-    const uint32_t* B = bits_all + (size_t)sl * H * wpitch;
-    auto win = [&](int yy) -> unsigned long long {     // bit k <-> x = 32 wx + k - 1
-        if (yy < 0 || yy >= H) return 0ull;
-        const uint32_t c = __ldg(B + (size_t)yy * wpitch + wx);
-        const uint32_t l = wx > 0 ? __ldg(B + (size_t)yy * wpitch + wx - 1) : 0u;
-        const uint32_t r = wx + 1 < wpitch ? __ldg(B + (size_t)yy * wpitch + wx + 1) : 0u;
-        return ((unsigned long long)c << 1) | (l >> 31) | ((unsigned long long)(r & 1u) << 33);
-    };
-    const unsigned long long up = win(y - 1), cu = win(y), dn = win(y + 1);
-    uint8_t* dst = nb_all + (size_t)sl * H * W + (size_t)y * W + wx * 32;
-    uint32_t fg = (uint32_t)(cu >> 1);
-    while (fg) {
-        const int x = __ffs((int)fg) - 1;
-        fg &= fg - 1;
-        dst[x] = (uint8_t)code_from_rows((unsigned)(up >> x) & 7u, (unsigned)(cu >> x) & 7u, (unsigned)(dn >> x) & 7u);
+// Large slices (the bit image does not fit in shared memory): one CTA per contour keeps a 256 x 256-pixel WINDOW of the
+// bit image in shared memory, centred on the walk; thread 0 follows the border (six LDS per step) until it leaves the
+// window's interior, then the CTA re-centres the window and the walk resumes (contour_trace.cuh: trace_run).  A long
+// contour (the stress masks have ~10^5-step borders) therefore walks at shared-memory latency, not at one dependent
+// L2 access per step, and all contours of all slices walk concurrently.
+constexpr int kWinW = 256, kWinH = 256, kWinPitch = kWinW / 32 + 1;   // +1 word: funnel shifts read one word ahead
+struct WindowCode {
+    const uint32_t* win;   // kWinH rows x kWinPitch words
+    int x0, y0;            // image coordinates of the window's first pixel (x0 a multiple of 32, may be negative)
+    __device__ __forceinline__ unsigned operator()(int, int x, int y) const {
+        const int cx = x - x0 - 1, w = cx >> 5, sh = cx & 31;          // bits cx .. cx+2 = x-1 .. x+1
+        const uint32_t* r = win + (y - y0 - 1) * kWinPitch + w;
+        return code_from_rows(__funnelshift_r(r[0], r[1], sh) & 7u, __funnelshift_r(r[kWinPitch], r[kWinPitch + 1], sh) & 7u,
+                              __funnelshift_r(r[2 * kWinPitch], r[2 * kWinPitch + 1], sh) & 7u);
     }
-}
+};
+struct WindowInside {
+    int x0, y0;
+    __device__ __forceinline__ bool operator()(int x, int y) const {
+        return x - 1 >= x0 && x + 1 < x0 + kWinW && y - 1 >= y0 && y + 1 < y0 + kWinH;
+    }
+};
 
-// Large slices: one thread per contour, rows read through L1/L2.  npts[c] <- number of kept vertices.
 template <bool EMIT>
-__global__ void __launch_bounds__(128) trace_global_kernel(const uint8_t* __restrict__ nb, int H, int W,
-                                                            const int* __restrict__ starts, const int* __restrict__ start_slice,
-                                                            long long* __restrict__ header, int cap_contours, int* __restrict__ npts,
-                                                            long long cap_points, double sx, double sy, int2* __restrict__ xy) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(64) trace_window_kernel(const uint32_t* __restrict__ fgbits, int H, int W, int wpitch,
+                                                           const int* __restrict__ starts, const int* __restrict__ start_slice,
+                                                           long long* __restrict__ header, int cap_contours, int* __restrict__ npts,
+                                                           long long cap_points, double sx, double sy, int2* __restrict__ xy) {
+    __shared__ uint32_t win[kWinH * kWinPitch];
+    __shared__ int s_org[2], s_status;
+    const int c = blockIdx.x;
     const long long n = header[0] < cap_contours ? header[0] : cap_contours;
     if (c >= n) return;
     if (EMIT && header[1] > cap_points) {   // caller's buffer too small: write nothing, flag it
-        if (c == 0) header[2] |= 2;
+        if (c == 0 && threadIdx.x == 0) header[2] |= 2;
         return;
     }
-    const NbImageCode code{nb + (size_t)start_slice[c] * H * W};
-    if (EMIT) {
-        trace_contour_fn(code, W, starts[c], 8 * H * W + 8, WriteEmit{xy + npts[c], sx, sy, 0});
-    } else {
-        const int cnt = trace_contour_fn(code, W, starts[c], 8 * H * W + 8, CountEmit{});
-        if (cnt < 0) atomicAdd((unsigned long long*)&header[3], 1ull);
-        npts[c] = cnt < 0 ? 0 : cnt;
+    const uint32_t* B = fgbits + (size_t)start_slice[c] * H * wpitch;
+    TraceState st;
+    trace_begin(st, W, starts[c]);
+    CountEmit count_emit;
+    WriteEmit write_emit{xy + (EMIT ? npts[c] : 0), sx, sy, 0};
+    for (int round = 0; round < (1 << 20); ++round) {
+        if (threadIdx.x == 0) {
+            s_org[0] = ((st.x - kWinW / 2) >> 5) << 5;
+            s_org[1] = st.y - kWinH / 2;
+        }
+        __syncthreads();
+        const int x0 = s_org[0], y0 = s_org[1];
+        for (int i = threadIdx.x; i < kWinH * kWinPitch; i += 64) {
+            const int ry = i / kWinPitch, wq = i - ry * kWinPitch;
+            const int gy = y0 + ry, gw = (x0 >> 5) + wq;
+            win[i] = (gy >= 0 && gy < H && gw >= 0 && gw < wpitch) ? __ldg(B + (size_t)gy * wpitch + gw) : 0u;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const WindowCode code{win, x0, y0};
+            const WindowInside inside{x0, y0};
+            s_status = EMIT ? trace_run(code, W, st, 8 * H * W + 8, write_emit, inside) : trace_run(code, W, st, 8 * H * W + 8, count_emit, inside);
+        }
+        __syncthreads();
+        if (s_status != 0) break;
+    }
+    if (threadIdx.x == 0 && !EMIT) {
+        if (s_status != 1) atomicAdd((unsigned long long*)&header[3], 1ull);
+        npts[c] = s_status == 1 ? st.n : 0;
     }
 }
 
@@ -333,15 +356,9 @@ void launch_trace(M2pWs& ws, PolyDev& P, int h, int w, int batch, double sx, dou
                                                                P.slice_start.as<int>(), header, (int)P.cap_contours, P.npts.as<int>(),
                                                                (long long)P.cap_points, sx, sy, P.xy.as<int2>());
     } else {
-        if (!EMIT) {   // count pass first: build the code image
-            ws.nb.reserve((size_t)batch * h * w);
-            nb_codes_kernel<<<ccl::grid_for(h, wpitch, batch), ccl::kThreads, 0, st>>>(ws.fgbits.as<uint32_t>(), h, w, wpitch, ws.nb.as<uint8_t>());
-            MS_LAUNCH_CHECK();
-        }
-        trace_global_kernel<EMIT><<<cdiv((int)P.cap_contours, 128), 128, 0, st>>>(ws.nb.as<uint8_t>(), h, w, P.starts.as<int>(),
-                                                                                 P.start_slice.as<int>(), header, (int)P.cap_contours,
-                                                                                 P.npts.as<int>(), (long long)P.cap_points, sx, sy,
-                                                                                 P.xy.as<int2>());
+        trace_window_kernel<EMIT><<<(unsigned)P.cap_contours, 64, 0, st>>>(ws.fgbits.as<uint32_t>(), h, w, wpitch, P.starts.as<int>(),
+                                                                          P.start_slice.as<int>(), header, (int)P.cap_contours,
+                                                                          P.npts.as<int>(), (long long)P.cap_points, sx, sy, P.xy.as<int2>());
     }
     MS_LAUNCH_CHECK();
 }
