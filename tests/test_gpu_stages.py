@@ -146,6 +146,27 @@ def test_mask2polygon_stress_2048(stage_engine, ms, kind):
     assert contours_equal(got, want)
 
 
+@pytest.mark.parametrize("variant", ["smem", "window", "crack"])
+def test_mask2polygon_trace_variants(stage_engine, ms, monkeypatch, variant):
+    """The three contour-ordering kernels (whole slice in shared memory, 256 x 256 window walk, crack list ranking)
+    are interchangeable: same golden / random / ragged cases, bit-exact, whichever one MEDSEG_TRACE forces."""
+    from medseg_b200 import synth
+    monkeypatch.setenv("MEDSEG_TRACE", variant)
+    for m, want in golden_contours():
+        assert contours_equal(stage_engine.mask2polygon(m).slice(0), want)
+    for m in _random_masks(150, 77):
+        assert contours_equal(stage_engine.mask2polygon(m).slice(0), op.extract_contours(m))
+    rng = np.random.default_rng(9)
+    batch = np.stack([(rng.random((70, 131)) < p).astype(np.uint8) * 255 for p in (0.0, 0.3, 1.0, 0.6, 0.05)])
+    polys = stage_engine.mask2polygon(batch, orig_w=262, orig_h=35)
+    for i in range(len(batch)):
+        want = op.map_contour_points(op.extract_contours(batch[i]), 262 / 131, 35 / 70)
+        assert contours_equal(polys.slice(i), want), i
+    for kind in ("blobs", "rings", "checker", "diag", "noise"):
+        m = synth.stress_mask(kind, 512, 512, seed=4)
+        assert contours_equal(stage_engine.mask2polygon(m).slice(0), op.extract_contours(m)), kind
+
+
 def test_mask2polygon_rotation_property(stage_engine, ms):
     """Size-independent property at full size: the multiset of traced border pixels is invariant
     under a 180-degree rotation of the mask (coordinates mirrored)."""

@@ -136,6 +136,15 @@ struct M2pWs {
     DevBuf fgbits;            // u32 per 32 pixels: bit-packed foreground
     PolyDev poly;
     PinBuf h_header;          // pinned int64[4]
+    // parallel contour ordering (large slices, mask2polygon.cu "crack" kernels)
+    DevBuf crack_pair;        // u64 per directed crack (4 per pixel): {next crack | contour marker, rank}
+    DevBuf crack_pos;         // u32 per crack position of the external contours: pixel index | kept bit
+    DevBuf crack_blocks;      // int32 per 1024 positions: kept-vertex counts, then exclusive offsets
+    DevBuf crack_contour;     // int32 [2 * (cap_contours + 1)]: position base per contour, rotation
+    DevBuf crack_meta;        // int64 total positions, int32 round flags
+    void release_crack() {
+        for (DevBuf* b : {&crack_pair, &crack_pos, &crack_blocks, &crack_contour, &crack_meta}) b->release();
+    }
 };
 // Phase A: labels, external starts (descending raster order per slice), per-contour vertex counts, offsets.
 void m2p_phase_a(M2pWs& ws, PolyDev& poly, const uint8_t* d_mask, int h, int w, int batch, int threshold, cudaStream_t st);

@@ -346,6 +346,7 @@ void ms_destroy(ms_handle* h) {
                       &h->m2p.poly.starts, &h->m2p.poly.start_slice, &h->m2p.poly.npts, &h->m2p.poly.slice_start,
                       &h->m2p.poly.block_counts, &h->m2p.poly.xy, &h->m2p.poly.header})
         b->release();
+    h->m2p.release_crack();
     for (auto& S : h->slots) {
         if (S.ev_done) cudaEventSynchronize(S.ev_done);
         S.d_src.release();

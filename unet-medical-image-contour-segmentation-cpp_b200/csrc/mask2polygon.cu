@@ -18,6 +18,8 @@
 // Algorithmic bytes: H*W (mask read) + 8 B per vertex + 4 B per contour offset.
 #include "ccl.cuh"
 #include "contour_trace.cuh"
+#include <cstdlib>
+#include <cstring>
 
 namespace ms {
 
@@ -320,6 +322,259 @@ __global__ void __launch_bounds__(128) trace_smem_kernel(const uint32_t* __restr
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Parallel contour ordering (slices whose bit image does not fit in shared memory).
+//
+// A *crack* is a directed pixel edge with foreground on its left and background on its right: crack (p, s) is side s of
+// foreground pixel p (s: 0 = W side walked southwards, 1 = S eastwards, 2 = E northwards, 3 = N westwards).  At the end
+// of a crack the walk turns towards the diagonal pixel if that is foreground (8-connectivity), else runs straight on
+// along the next pixel, else turns around p itself.  succ() is a permutation of the cracks; its cycle through the W
+// side of a component's raster-first pixel is that component's outer border, and the owners of the cracks along the
+// cycle -- consecutive repeats removed -- are exactly the pixels cv::findContours visits, in its order (checked against
+// cv2 by the pure-Python model in tests/test_crack_model.py and, for these kernels, by the GPU stress tests).  Border following, inherently sequential, becomes
+// list ranking:
+//   init   every crack: {succ, 1}
+//   cut    the predecessor of each external start crack ends its list and carries the contour number
+//   jump   log2(longest border) rounds of pointer jumping, in place: {next, rank} is one 64-bit word, and every value a
+//          racing reader can observe is a true statement "next is rank cracks ahead", so no double buffering
+//   flags  every crack now knows its contour and position.  The first crack of each pixel visit applies the
+//          CHAIN_APPROX_SIMPLE rule (direction to the next visited pixel != direction from the previous one) from the
+//          3x3 neighbourhood alone and drops {pixel, kept} at its position
+//   scan   kept flags -> output offsets;  emit maps the coordinates.
+// Every kernel is word-parallel over the bit image or position-parallel; nothing walks a contour.
+namespace crack {
+
+typedef unsigned long long u64;
+constexpr uint32_t kKept = 0x80000000u;
+__device__ __forceinline__ u64 pack(int next, uint32_t rank) { return ((u64)rank << 32) | (uint32_t)next; }
+__device__ __forceinline__ int next_of(u64 v) { return (int)(uint32_t)v; }
+__device__ __forceinline__ uint32_t rank_of(u64 v) { return (uint32_t)(v >> 32); }
+
+// 34-bit row windows around word (y, wx): bit k <-> x = wx * 32 + k - 1; outside the image = background
+struct Nbhd {
+    u64 up, cu, dn;
+    uint32_t border;   // foreground pixels of the word with a background 4-neighbour (the pixels that own cracks)
+};
+__device__ __forceinline__ Nbhd load_nbhd(const uint32_t* __restrict__ B, int H, int wpitch, int y, int wx) {
+    auto window = [&](int yy) -> u64 {
+        if (yy < 0 || yy >= H) return 0ull;
+        const uint32_t* r = B + (size_t)yy * wpitch + wx;
+        const uint32_t c = __ldg(r), l = wx > 0 ? __ldg(r - 1) : 0u, rr = wx + 1 < wpitch ? __ldg(r + 1) : 0u;
+        return (u64)(l >> 31) | ((u64)c << 1) | ((u64)(rr & 1u) << 33);
+    };
+    Nbhd n;
+    n.cu = window(y);
+    const uint32_t fg = (uint32_t)(n.cu >> 1);
+    n.up = n.dn = 0;
+    n.border = 0;
+    if (fg == 0) return n;
+    n.up = window(y - 1);
+    n.dn = window(y + 1);
+    n.border = fg & ~((uint32_t)(n.up >> 1) & (uint32_t)(n.dn >> 1) & (uint32_t)n.cu & (uint32_t)(n.cu >> 2));
+    return n;
+}
+__device__ __forceinline__ unsigned code_at(const Nbhd& n, int j) {
+    return code_from_rows((unsigned)(n.up >> j) & 7u, (unsigned)(n.cu >> j) & 7u, (unsigned)(n.dn >> j) & 7u);
+}
+__device__ __forceinline__ bool has(unsigned code, int d) { return (code >> (d & 7)) & 1u; }
+__device__ __forceinline__ int step(int p, int d, int W) { return p + trace_dy(d & 7) * W + trace_dx(d & 7); }
+// side s exists as a crack iff the 4-neighbour across it (W, S, E, N = directions 4, 6, 0, 2) is background
+__device__ __forceinline__ bool side_open(unsigned code, int s) { return !has(code, 4 + 2 * s); }
+// successor: diagonal pixel (directions SW, SE, NE, NW for s = 0..3) -> its side s+3; straight pixel (S, E, N, W) -> its side
+// s; else the next side of p
+__device__ __forceinline__ int succ(unsigned code, int p, int s, int W) {
+    if (has(code, 5 + 2 * s)) return step(p, 5 + 2 * s, W) * 4 + ((s + 3) & 3);
+    if (has(code, 6 + 2 * s)) return step(p, 6 + 2 * s, W) * 4 + s;
+    return p * 4 + ((s + 1) & 3);
+}
+// predecessor (the inverse): diagonal pixel (NW, SW, SE, NE) -> its side s+1; straight pixel (N, W, S, E) -> its side s;
+// else the previous side of p
+__device__ __forceinline__ int pred_dir(unsigned code, int s) {   // direction of the predecessor's owner, -1 = p itself
+    if (has(code, 3 + 2 * s)) return (3 + 2 * s) & 7;
+    if (has(code, 2 + 2 * s)) return (2 + 2 * s) & 7;
+    return -1;
+}
+__device__ __forceinline__ int pred(unsigned code, int p, int s, int W) {
+    if (has(code, 3 + 2 * s)) return step(p, 3 + 2 * s, W) * 4 + ((s + 1) & 3);
+    if (has(code, 2 + 2 * s)) return step(p, 2 + 2 * s, W) * 4 + s;
+    return p * 4 + ((s + 3) & 3);
+}
+template <class F>
+__device__ __forceinline__ void for_each_crack(const Nbhd& n, int row0, F&& f) {   // row0 = pixel index of the word's bit 0
+    uint32_t m = n.border;
+    while (m) {
+        const int j = __ffs((int)m) - 1;
+        m &= m - 1;
+        const unsigned code = code_at(n, j);
+#pragma unroll
+        for (int s = 0; s < 4; ++s)
+            if (side_open(code, s)) f(row0 + j, s, code);
+    }
+}
+
+__global__ void __launch_bounds__(ccl::kThreads) init_kernel(const uint32_t* __restrict__ bits_all, int H, int W, int wpitch,
+                                                              u64* __restrict__ pair_all) {
+    MS_CCL_WORD_COORDS();
+    const Nbhd n = load_nbhd(bits_all + (size_t)sl * H * wpitch, H, wpitch, y, wx);
+    u64* pair = pair_all + (size_t)sl * H * W * 4;
+    for_each_crack(n, y * W + wx * 32, [&](int p, int s, unsigned code) { __stcg(&pair[p * 4 + s], pack(succ(code, p, s, W), 1u)); });
+}
+
+// one thread per contour: end the list at the predecessor of the start crack; rotation of the start pixel's visit
+__global__ void __launch_bounds__(256) cut_kernel(const uint32_t* __restrict__ bits_all, int H, int W, int wpitch,
+                                                   const int* __restrict__ starts, const int* __restrict__ start_slice,
+                                                   const long long* __restrict__ header, int cap_contours, u64* __restrict__ pair_all,
+                                                   int* __restrict__ rot, int* __restrict__ npts) {
+    const int c = blockIdx.x * 256 + threadIdx.x;
+    const long long n = header[0] < cap_contours ? header[0] : cap_contours;
+    if (c >= n) return;
+    const int sl = start_slice[c], p = starts[c], x = p % W, y = p / W;
+    const Nbhd nb = load_nbhd(bits_all + (size_t)sl * H * wpitch, H, wpitch, y, x >> 5);
+    const unsigned code = code_at(nb, x & 31);
+    // the start pixel's visit may begin up to three cracks before its W side (N, E, S sides walked just before)
+    int back = 0, s = 0;
+    while (back < 3 && pred_dir(code, s) < 0) {
+        s = (s + 3) & 3;
+        ++back;
+    }
+    rot[c] = back;
+    npts[c] = 0;
+    __stcg(&pair_all[(size_t)sl * H * W * 4 + pred(code, p, 0, W)], pack(-(c + 2), 1u));
+}
+
+__global__ void __launch_bounds__(ccl::kThreads) jump_kernel(const uint32_t* __restrict__ bits_all, int H, int W, int wpitch,
+                                                              u64* __restrict__ pair_all, const int* __restrict__ busy, int round) {
+    if (round > 0 && busy[round - 1] == 0) return;   // every external border already ranked
+    MS_CCL_WORD_COORDS();
+    const Nbhd n = load_nbhd(bits_all + (size_t)sl * H * wpitch, H, wpitch, y, wx);
+    u64* pair = pair_all + (size_t)sl * H * W * 4;
+    for_each_crack(n, y * W + wx * 32, [&](int p, int s, unsigned) {
+        u64* me = &pair[p * 4 + s];
+        const u64 v = __ldcg(me);
+        const int nx = next_of(v);
+        if (nx < 0) return;
+        const u64 t = __ldcg(&pair[nx]);
+        __stcg(me, pack(next_of(t), rank_of(v) + rank_of(t)));
+    });
+}
+
+// busy[round] = some external border is not completely ranked after rounds 0 .. round.  After k rounds every crack is
+// either ranked or points at least 2^k cracks ahead (the in-place update can only jump further than the synchronous one),
+// so a border of length L is completely ranked once its start crack is ranked and 2^k >= L; the start crack alone being
+// ranked is not enough, it may have got there through already-updated successors while a crack behind it has not.
+__global__ void __launch_bounds__(256) check_kernel(int H, int W, const int* __restrict__ starts, const int* __restrict__ start_slice,
+                                                     const long long* __restrict__ header, int cap_contours,
+                                                     const u64* __restrict__ pair_all, int* __restrict__ busy, int round) {
+    if (round > 0 && busy[round - 1] == 0) return;
+    const int c = blockIdx.x * 256 + threadIdx.x;
+    const long long n = header[0] < cap_contours ? header[0] : cap_contours;
+    if (c >= n) return;
+    const u64 t = __ldcg(&pair_all[(size_t)start_slice[c] * H * W * 4 + (size_t)starts[c] * 4]);
+    if (next_of(t) >= 0 || (u64)rank_of(t) > (1ull << (round + 1))) busy[round] = 1;
+}
+
+// 1 block of 1024: border length of every contour -> exclusive position bases; meta[0] = total positions
+__global__ void __launch_bounds__(1024) length_kernel(int H, int W, const int* __restrict__ starts, const int* __restrict__ start_slice,
+                                                       long long* __restrict__ header, int cap_contours, const u64* __restrict__ pair_all,
+                                                       int* __restrict__ cbase, long long* __restrict__ meta) {
+    const long long n64 = header[0];
+    const int n = (int)(n64 < cap_contours ? n64 : cap_contours);
+    long long carry = 0;
+    for (int base = 0; base < n; base += 1024) {
+        const int i = base + threadIdx.x;
+        int v = 0;
+        if (i < n) {
+            const u64 t = __ldcg(&pair_all[(size_t)start_slice[i] * H * W * 4 + (size_t)starts[i] * 4]);
+            if (next_of(t) == -(i + 2)) v = (int)rank_of(t);
+            else atomicAdd((unsigned long long*)&header[3], 1ull);   // unranked border: cannot happen
+        }
+        int tot;
+        const int ex = block_exscan_1024(v, &tot);
+        if (i < n) cbase[i] = (int)(carry + ex);
+        carry += tot;
+    }
+    if (threadIdx.x == 0) {
+        cbase[n] = (int)carry;
+        meta[0] = carry;
+    }
+}
+
+__global__ void __launch_bounds__(ccl::kThreads) flags_kernel(const uint32_t* __restrict__ bits_all, int H, int W, int wpitch,
+                                                               const u64* __restrict__ pair_all, const int* __restrict__ cbase,
+                                                               const int* __restrict__ rot, uint32_t* __restrict__ pos_px,
+                                                               int* __restrict__ npts) {
+    MS_CCL_WORD_COORDS();
+    const Nbhd n = load_nbhd(bits_all + (size_t)sl * H * wpitch, H, wpitch, y, wx);
+    const u64* pair = pair_all + (size_t)sl * H * W * 4;
+    for_each_crack(n, y * W + wx * 32, [&](int p, int s, unsigned code) {
+        const u64 v = __ldcg(&pair[p * 4 + s]);
+        const int nx = next_of(v);
+        if (nx >= 0) return;                               // hole border or border of a non-external component
+        const int c = -nx - 2;
+        const int base = cbase[c], len = cbase[c + 1] - base;
+        int pos = len - (int)rank_of(v) + rot[c];          // position along the border, the start pixel's visit first
+        if (pos >= len) pos -= len;
+        bool kept = false;
+        const int pd = pred_dir(code, s);
+        if (pd >= 0) {                                     // first crack of a visit of p
+            const int d_prev = (pd + 4) & 7;               // direction previous pixel -> p
+            int d_out = -1;                                // direction p -> next visited pixel
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+                const int ss = (s + t) & 3;
+                if (d_out < 0 && has(code, 5 + 2 * ss)) d_out = (5 + 2 * ss) & 7;
+                if (d_out < 0 && has(code, 6 + 2 * ss)) d_out = (6 + 2 * ss) & 7;
+            }
+            kept = d_out != d_prev;
+        } else if (code == 0 && s == 0) {
+            kept = true;                                   // isolated pixel: a single vertex
+        }
+        pos_px[(size_t)base + pos] = (uint32_t)p | (kept ? kKept : 0u);
+        if (kept) atomicAdd(&npts[c], 1);
+    });
+}
+
+// position-parallel: kept vertices per 1024 positions
+__global__ void __launch_bounds__(1024) pos_count_kernel(const uint32_t* __restrict__ pos_px, const long long* __restrict__ meta,
+                                                          int* __restrict__ blocks) {
+    const long long T = meta[0], i = (long long)blockIdx.x * 1024 + threadIdx.x;
+    if ((long long)blockIdx.x * 1024 >= T) return;
+    const int cnt = __syncthreads_count(i < T && (pos_px[i] & kKept));
+    if (threadIdx.x == 0) blocks[blockIdx.x] = cnt;
+}
+__global__ void __launch_bounds__(1024) pos_scan_kernel(int* __restrict__ blocks, const long long* __restrict__ meta) {
+    const int nb = (int)((meta[0] + 1023) / 1024);
+    int carry = 0;
+    for (int base = 0; base < nb; base += 1024) {
+        const int i = base + threadIdx.x;
+        const int v = i < nb ? blocks[i] : 0;
+        int tot;
+        const int ex = block_exscan_1024(v, &tot);
+        if (i < nb) blocks[i] = carry + ex;
+        carry += tot;
+    }
+}
+__global__ void __launch_bounds__(1024) pos_emit_kernel(const uint32_t* __restrict__ pos_px, const long long* __restrict__ meta,
+                                                         const int* __restrict__ blocks, long long* __restrict__ header,
+                                                         long long cap_points, int W, double sx, double sy, int2* __restrict__ xy) {
+    const long long T = meta[0], i = (long long)blockIdx.x * 1024 + threadIdx.x;
+    if ((long long)blockIdx.x * 1024 >= T) return;
+    if (header[1] > cap_points) {
+        if (blockIdx.x == 0 && threadIdx.x == 0) header[2] |= 2;
+        return;
+    }
+    const uint32_t v = i < T ? pos_px[i] : 0u;
+    const bool kept = v & kKept;
+    int tot;
+    const int ex = block_exscan_1024(kept ? 1 : 0, &tot);
+    if (kept) {
+        const int p = (int)(v & ~kKept), x = p % W, y = p / W;
+        WriteEmit{xy + blocks[blockIdx.x] + ex, sx, sy, 0}(x, y);
+    }
+}
+
+}  // namespace crack
+
 // 1 block of 1024: in-place exclusive scan of npts[0..n) ; npts[n] = header[1] = total
 __global__ void __launch_bounds__(1024) scan_points_kernel(int* __restrict__ npts, int cap_contours, long long* __restrict__ header) {
     const long long n64 = header[0];
@@ -341,12 +596,29 @@ __global__ void __launch_bounds__(1024) scan_points_kernel(int* __restrict__ npt
     }
 }
 
+enum TraceMode { kTraceSmem = 0, kTraceWindow = 1, kTraceCrack = 2 };
+
+// MEDSEG_TRACE = smem | window | crack forces a variant (tests exercise all three on the same masks)
+TraceMode pick_trace_mode(int h, int w, int batch) {
+    const int wpitch = cdiv(w, 32);
+    const size_t trace_smem = (size_t)(h + 2) * (wpitch + 2) * 4;
+    const bool smem_ok = trace_smem <= kTraceSmemMax;
+    const bool crack_ok = (int64_t)h * w * batch * 4 < ((int64_t)1 << 31);   // positions are int32
+    if (const char* e = std::getenv("MEDSEG_TRACE")) {
+        if (!std::strcmp(e, "window")) return kTraceWindow;
+        if (!std::strcmp(e, "crack") && crack_ok) return kTraceCrack;
+        if (!std::strcmp(e, "smem") && smem_ok) return kTraceSmem;
+    }
+    if (smem_ok) return kTraceSmem;
+    return crack_ok ? kTraceCrack : kTraceWindow;
+}
+
 template <bool EMIT>
-void launch_trace(M2pWs& ws, PolyDev& P, int h, int w, int batch, double sx, double sy, cudaStream_t st) {
+void launch_trace(M2pWs& ws, PolyDev& P, TraceMode mode, int h, int w, int batch, double sx, double sy, cudaStream_t st) {
     const int wpitch = cdiv(w, 32);
     const size_t trace_smem = (size_t)(h + 2) * (wpitch + 2) * 4;
     long long* header = P.header.as<long long>();
-    if (trace_smem <= kTraceSmemMax) {
+    if (mode == kTraceSmem) {
         static bool attr = false;
         if (!attr) {
             MS_CUDA(cudaFuncSetAttribute(trace_smem_kernel<EMIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTraceSmemMax));
@@ -360,6 +632,58 @@ void launch_trace(M2pWs& ws, PolyDev& P, int h, int w, int batch, double sx, dou
                                                                           P.start_slice.as<int>(), header, (int)P.cap_contours,
                                                                           P.npts.as<int>(), (long long)P.cap_points, sx, sy, P.xy.as<int2>());
     }
+    MS_LAUNCH_CHECK();
+}
+
+// list-ranking variant of the counting pass: leaves per-contour vertex counts in P.npts and {pixel, kept} per border
+// position in ws.crack_pos (consumed by crack_emit)
+void crack_count(M2pWs& ws, PolyDev& P, int h, int w, int batch, cudaStream_t st) {
+    const int wpitch = cdiv(w, 32);
+    const size_t ncracks = (size_t)h * w * batch * 4;
+    const int nblocks = (int)cdiv64((int64_t)ncracks, 1024);
+    ws.crack_pair.reserve(ncracks * 8);
+    ws.crack_pos.reserve(ncracks * 4);
+    ws.crack_blocks.reserve((size_t)nblocks * 4);
+    ws.crack_contour.reserve(((size_t)P.cap_contours + 1) * 8);
+    ws.crack_meta.reserve(8 + 32 * 4);
+    crack::u64* pair = ws.crack_pair.as<crack::u64>();
+    long long* meta = ws.crack_meta.as<long long>();
+    int* busy = reinterpret_cast<int*>(meta + 1);
+    int* cbase = ws.crack_contour.as<int>();
+    int* rot = cbase + P.cap_contours + 1;
+    const uint32_t* B = ws.fgbits.as<uint32_t>();
+    long long* header = P.header.as<long long>();
+    const dim3 gw = ccl::grid_for(h, wpitch, batch);
+    const int gc = (int)cdiv64(P.cap_contours, 256);
+    int rounds = 0;
+    while (((int64_t)1 << rounds) < (int64_t)h * w * 4) ++rounds;   // a border has at most 4 * h * w cracks
+
+    MS_CUDA(cudaMemsetAsync(meta, 0, 8 + 32 * 4, st));
+    crack::init_kernel<<<gw, ccl::kThreads, 0, st>>>(B, h, w, wpitch, pair);
+    MS_LAUNCH_CHECK();
+    crack::cut_kernel<<<gc, 256, 0, st>>>(B, h, w, wpitch, P.starts.as<int>(), P.start_slice.as<int>(), header, (int)P.cap_contours, pair,
+                                          rot, P.npts.as<int>());
+    MS_LAUNCH_CHECK();
+    for (int r = 0; r < rounds; ++r) {
+        crack::jump_kernel<<<gw, ccl::kThreads, 0, st>>>(B, h, w, wpitch, pair, busy, r);
+        MS_LAUNCH_CHECK();
+        crack::check_kernel<<<gc, 256, 0, st>>>(h, w, P.starts.as<int>(), P.start_slice.as<int>(), header, (int)P.cap_contours, pair, busy, r);
+        MS_LAUNCH_CHECK();
+    }
+    crack::length_kernel<<<1, 1024, 0, st>>>(h, w, P.starts.as<int>(), P.start_slice.as<int>(), header, (int)P.cap_contours, pair, cbase, meta);
+    MS_LAUNCH_CHECK();
+    crack::flags_kernel<<<gw, ccl::kThreads, 0, st>>>(B, h, w, wpitch, pair, cbase, rot, ws.crack_pos.as<uint32_t>(), P.npts.as<int>());
+    MS_LAUNCH_CHECK();
+    crack::pos_count_kernel<<<nblocks, 1024, 0, st>>>(ws.crack_pos.as<uint32_t>(), meta, ws.crack_blocks.as<int>());
+    MS_LAUNCH_CHECK();
+    crack::pos_scan_kernel<<<1, 1024, 0, st>>>(ws.crack_blocks.as<int>(), meta);
+    MS_LAUNCH_CHECK();
+}
+
+void crack_emit(M2pWs& ws, PolyDev& P, int h, int w, int batch, double sx, double sy, cudaStream_t st) {
+    const int nblocks = (int)cdiv64((int64_t)h * w * batch * 4, 1024);
+    crack::pos_emit_kernel<<<nblocks, 1024, 0, st>>>(ws.crack_pos.as<uint32_t>(), ws.crack_meta.as<long long>(), ws.crack_blocks.as<int>(),
+                                                     P.header.as<long long>(), (long long)P.cap_points, w, sx, sy, P.xy.as<int2>());
     MS_LAUNCH_CHECK();
 }
 
@@ -417,7 +741,9 @@ void m2p_phase_a(M2pWs& ws, PolyDev& P, const uint8_t* d_mask, int h, int w, int
     write_starts_kernel<<<dim3(bps, batch), 256, 0, st>>>(B, Lfg, Lbg, flag, h, w, wpitch, bc, P.slice_start.as<int>(), (int)P.cap_contours,
                                                           P.starts.as<int>(), P.start_slice.as<int>());
     MS_LAUNCH_CHECK();
-    launch_trace<false>(ws, P, h, w, batch, 1.0, 1.0, st);
+    const TraceMode mode = pick_trace_mode(h, w, batch);
+    if (mode == kTraceCrack) crack_count(ws, P, h, w, batch, st);
+    else launch_trace<false>(ws, P, mode, h, w, batch, 1.0, 1.0, st);
     scan_points_kernel<<<1, 1024, 0, st>>>(P.npts.as<int>(), (int)P.cap_contours, header);
     MS_LAUNCH_CHECK();
 }
@@ -426,7 +752,9 @@ void m2p_phase_b(M2pWs& ws, PolyDev& P, int h, int w, int batch, int orig_w, int
     // src/mask2polygon.cpp:199-200
     const double sx = static_cast<double>(orig_w) / w;
     const double sy = static_cast<double>(orig_h) / h;
-    launch_trace<true>(ws, P, h, w, batch, sx, sy, st);
+    const TraceMode mode = pick_trace_mode(h, w, batch);
+    if (mode == kTraceCrack) crack_emit(ws, P, h, w, batch, sx, sy, st);
+    else launch_trace<true>(ws, P, mode, h, w, batch, sx, sy, st);
 }
 
 }  // namespace ms
