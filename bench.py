@@ -272,8 +272,17 @@ def run_ours(args, rank, world, local):
             tc_ms += ms_l
     achieved = tc_flops / (tc_ms / 1e3) / 1e12
     peak = peaks["bf16_sustained"]
+    # DRAM bytes of the same 21 launches from the committed `ncu --set full` capture (tools/forward_once.py, same batch)
+    traffic, traffic_src = None, None
+    prof = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r1_ncu_full_forward_b32.json")
+    if os.path.exists(prof):
+        with open(prof) as f:
+            pj = json.load(f)
+        if pj.get("batch") == B and S == 512:
+            traffic = pj["tcgen05_dram_bytes"]
+            traffic_src = "profiles/r1_ncu_full_forward_b32.json: dram__bytes_read.sum + dram__bytes_write.sum summed over the 21 tcgen05 launches of one step"
     roofline = {"bound": "tensor", "kernel": "ms::tc::conv_halo2_kernel / conv_halo_kernel / conv_gemm_kernel (21 tcgen05 launches per step)", "achieved": achieved, "peak": peak,
-                "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None, "peak_source": peaks["source"] + " (sustained cuBLAS bf16)",
+                "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peaks["source"] + " (sustained cuBLAS bf16)",
                 "unet_ms_per_step": all_ms, "unet_share_of_step": all_ms / ms_per_step}
     if args.layer_table and rank == 0:
         with open(args.layer_table, "w") as f:

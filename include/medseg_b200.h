@@ -172,6 +172,24 @@ MS_API int ms_wait_batch(ms_handle* h, int slot, ms_polygons* out);
  * <stem>_contour_overlay.png, <stem>.json (src/process.cpp:207-242, src/mask2polygon.cpp:134-222). */
 MS_API int ms_process_raw_file(ms_handle* h, const char* raw_path, int w, int hgt, const char* out_dir);
 
+/* Batched form of the per-file loop of src/main.cpp:148-164: n headerless u16 files of the same w x hgt, artefacts of
+ * file i (the same five as ms_process_raw_file, byte-identical to calling it per file) into out_dirs[i].  A prefetch
+ * thread reads batch k+1 into pinned memory and a pool of writer threads (MEDSEG_WRITERS, default min(cores, 16))
+ * encodes batch k-1 while the GPU works on batch k (max_batch files per launch sequence).  A file that cannot be read
+ * or written is counted in *n_failed (and ok[i] = 0) without stopping the others -- the reference's success_count /
+ * fail_count (src/main.cpp:160-164); the return value is MS_OK unless the call itself failed.  ok, n_ok, n_failed may
+ * be NULL. */
+MS_API int ms_process_raw_files(ms_handle* h, const char* const* raw_paths, const char* const* out_dirs, int64_t n, int w, int hgt,
+                                uint8_t* ok, int64_t* n_ok, int64_t* n_failed);
+
+/* Replaces find_16bit_images + the directory branch of src/main.cpp:28-48,134-168: regular files with extension .raw
+ * .dcm .tif .tiff (case-insensitive) in input_dir, optionally recursive with the sub-directory structure reproduced
+ * under out_dir (:151-156).  The list is sorted by path; shard (shard_index of shard_count)
+ * takes a contiguous block of it, so N processes -- one per GPU -- cover a directory without talking to each other.
+ * *n_found = files in the whole list, *n_ok / *n_failed = this shard's outcome. */
+MS_API int ms_process_directory(ms_handle* h, const char* input_dir, int w, int hgt, const char* out_dir, int recursive,
+                                int shard_index, int shard_count, int64_t* n_found, int64_t* n_ok, int64_t* n_failed);
+
 /* Byte-exact LabelMe-style document of Mask2Polygon::generate_json (src/mask2polygon.cpp:68-109,
  * nlohmann::json dump with std::setw(4)).  Writes at most `cap` bytes (no NUL) to `dst`, returns the
  * full length (call with cap = 0 to size) or a negative ms_status. */

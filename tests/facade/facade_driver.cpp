@@ -4,6 +4,8 @@
 // 2. the stages one by one, the way src/process.cpp:211-242 chains them through files:
 //    Preprocess::preprocess_raw -> (mask PNG written by step 1) -> Mask2Polygon::process_single_mask
 #include <cstdio>
+#include <cstdlib>
+#include <vector>
 #include <fstream>
 #include <iostream>
 #include <string>
@@ -36,6 +38,16 @@ int main(int argc, char** argv) {
     const auto cs = Mask2Polygon::extract_contours(Mask2Polygon::MaskView{vis.data(), 64, 64});
     std::printf("inmem: hole=%d contours=%zu pts=%zu first=(%d,%d)\n", (int)pp[30 * 64 + 30], cs.size(), cs.empty() ? 0 : cs[0].size(),
                 cs.empty() ? -1 : cs[0][0].x, cs.empty() ? -1 : cs[0][0].y);
+    // the batched extensions: a directory holding the same slice twice -> same JSON as the single call
+    {
+        const std::string in_dir = out + "/dir_in";
+        std::system(("mkdir -p '" + in_dir + "' && cp '" + raw + "' '" + in_dir + "/s0.raw' && cp '" + raw + "' '" + in_dir + "/s1.RAW'").c_str());
+        int good = -1, bad = -1;
+        const bool okd = MedicalSeg::process_directory(in_dir, w, h, out + "/dir_out", false, &good, &bad);
+        std::vector<bool> flags;
+        const int n = MedicalSeg::process_image_batch({in_dir + "/s0.raw", in_dir + "/missing.raw"}, w, h, {out + "/list0", out + "/list1"}, &flags);
+        std::printf("dir: ok=%d good=%d bad=%d list=%d flags=%d%d\n", (int)okd, good, bad, n, (int)flags[0], (int)flags[1]);
+    }
     std::printf("log: %s\n", MedicalSeg::get_log_path().c_str());
     MedicalSeg::cleanup_resources();
     return 0;

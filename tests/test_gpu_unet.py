@@ -123,6 +123,66 @@ def test_process_raw_file_artifacts(unet_engine, ms, tmp_path):
     assert (overlay == op.create_overlay_image(contours, norm)).all()
 
 
+def _tree_bytes(root):
+    out = {}
+    for d, _, files in os.walk(root):
+        for f in files:
+            p = os.path.join(d, f)
+            out[os.path.relpath(p, root)] = open(p, "rb").read()
+    return out
+
+
+def test_process_directory_matches_per_file(unet_engine, ms, tmp_path):
+    """N3: the batched directory walk (src/main.cpp:28-48,134-168) writes, for every file, exactly the bytes the
+    per-file call writes; extensions are filtered case-insensitively; unreadable files are counted, not fatal;
+    -r reproduces the sub-directory structure; shards split the sorted list into contiguous blocks."""
+    from medseg_b200 import synth
+    src_dir = tmp_path / "in"
+    (src_dir / "sub" / "deeper").mkdir(parents=True)
+    names = ["a_000.raw", "a_001.RAW", "a_002.tif", "a_003.dcm", "a_004.tiff", "a_005.raw", "a_006.raw", "a_007.raw", "a_008.raw",
+             "sub/b_000.raw", "sub/deeper/c_000.raw"]                       # max_batch = 4 -> three batches at top level
+    for i, n in enumerate(names):
+        synth.ct_slice(100 + i, w=576, h=448).tofile(src_dir / n)
+    (src_dir / "notes.txt").write_text("ignored")
+    (src_dir / "a_short.raw").write_bytes(b"\0" * 1000)                      # shorter than w*h*2 bytes -> failed
+    top = sorted(n for n in names if "/" not in n)
+
+    # per-file reference run
+    want_dir = tmp_path / "want"
+    for n in names:
+        sub = os.path.dirname(n)
+        unet_engine.process_raw_file(str(src_dir / n), 576, 448, str(want_dir / sub))
+    want = _tree_bytes(want_dir)
+    assert len(want) >= 3 * len(names)
+
+    # flat directory
+    found, good, bad = unet_engine.process_directory(str(src_dir), 576, 448, str(tmp_path / "flat"))
+    assert (found, good, bad) == (len(top) + 1, len(top), 1)
+    flat = _tree_bytes(tmp_path / "flat")
+    assert flat == {k: v for k, v in want.items() if "/" not in k}
+
+    # recursive keeps the tree
+    found, good, bad = unet_engine.process_directory(str(src_dir), 576, 448, str(tmp_path / "rec"), recursive=True)
+    assert (found, good, bad) == (len(names) + 1, len(names), 1)
+    assert _tree_bytes(tmp_path / "rec") == want
+
+    # two shards cover the list exactly once
+    res = [unet_engine.process_directory(str(src_dir), 576, 448, str(tmp_path / f"shard{r}"), recursive=True, shard_index=r, shard_count=2)
+           for r in range(2)]
+    assert res[0][0] == res[1][0] == len(names) + 1 and res[0][1] + res[1][1] == len(names) and res[0][2] + res[1][2] == 1
+    s0, s1 = _tree_bytes(tmp_path / "shard0"), _tree_bytes(tmp_path / "shard1")
+    assert not (set(s0) & set(s1)) and {**s0, **s1} == want
+
+    # explicit list, per-file output directories, a missing file in the middle
+    paths = [str(src_dir / top[0]), str(tmp_path / "nope.raw"), str(src_dir / top[1])]
+    ok = unet_engine.process_raw_files(paths, 576, 448, [str(tmp_path / "l0"), str(tmp_path / "l1"), str(tmp_path / "l2")])
+    assert ok.tolist() == [True, False, True]
+    stem0 = os.path.splitext(top[0])[0]
+    assert _tree_bytes(tmp_path / "l0") == {k: v for k, v in want.items() if k.startswith(stem0 + "_") or k == stem0 + ".json"}
+    assert not os.path.exists(tmp_path / "l1") or not os.listdir(tmp_path / "l1")
+    assert unet_engine.process_raw_files([], 576, 448, str(tmp_path)).tolist() == []
+
+
 def test_log_file(ms, blob3, tmp_path):
     from medseg_b200 import synth
     e = ms.Engine(blob3, str(tmp_path / "log"))
@@ -217,5 +277,10 @@ def test_cpp_facade_stage_api(ms, blob3, tmp_path):
     oa = cv2.imread(str(out / "a" / "slice_contour_overlay.png"))
     ob = cv2.imread(str(out / "b" / "slice_contour_overlay.png"))
     assert (oa == ob).all() and (oa == op.create_overlay_image(contours, na)).all()
+    assert "dir: ok=1 good=2 bad=0 list=1 flags=10" in r.stdout
+    assert "Directory processing completed:" in r.stdout and "  Success: 2 files" in r.stdout
+    for stem in ("s0", "s1"):
+        assert open(out / "dir_out" / f"{stem}.json").read() == ja.replace('"slice.raw"', f'"{stem}.raw"')
+    assert open(out / "list0" / "s0.json").read() == open(out / "dir_out" / "s0.json").read()
     log = open(out / "log" / "segmentation_log.txt").read()
     assert "driver: engine ready" in log and "Total processing time:" in log and "All resources cleaned up successfully" in log

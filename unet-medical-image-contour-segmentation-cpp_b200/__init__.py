@@ -73,6 +73,8 @@ ABI = {
     "ms_submit_batch_host": (_I, [_P, _I, _P, _I, _I, _I]),
     "ms_wait_batch": (_I, [_P, _I, C.POINTER(ms_polygons)]),
     "ms_process_raw_file": (_I, [_P, C.c_char_p, _I, _I, C.c_char_p]),
+    "ms_process_raw_files": (_I, [_P, C.POINTER(C.c_char_p), C.POINTER(C.c_char_p), _L, _I, _I, _P, C.POINTER(_L), C.POINTER(_L)]),
+    "ms_process_directory": (_I, [_P, C.c_char_p, _I, _I, C.c_char_p, _I, _I, _I, C.POINTER(_L), C.POINTER(_L), C.POINTER(_L)]),
     "ms_polygons_to_json": (_L, [_P, _P, _I, C.c_char_p, _I, _I, _P, _L]),
     "ms_launch_count": (_L, [_P]),
     "ms_time_layer": (_I, [_P, _I, _I, _I, C.POINTER(C.c_float), C.POINTER(C.c_double)]),
@@ -293,6 +295,34 @@ class Engine:
 
     def process_raw_file(self, raw_path: str, w: int, h: int, out_dir: str) -> None:
         self._check(self._l.ms_process_raw_file(self._h, raw_path.encode(), w, h, out_dir.encode()))
+
+    def process_raw_files(self, raw_paths, w: int, h: int, out_dirs) -> np.ndarray:
+        """Batched per-file loop (src/main.cpp:148-164).  `out_dirs` is one directory or one per file.
+        Returns a bool array: file i produced its artefacts."""
+        raw_paths = [os.fspath(p) for p in raw_paths]
+        if isinstance(out_dirs, (str, os.PathLike)):
+            out_dirs = [out_dirs] * len(raw_paths)
+        out_dirs = [os.fspath(p) for p in out_dirs]
+        if len(out_dirs) != len(raw_paths):
+            raise ValueError("one output directory per file")
+        n = len(raw_paths)
+        a = (C.c_char_p * max(n, 1))(*[p.encode() for p in raw_paths])
+        b = (C.c_char_p * max(n, 1))(*[p.encode() for p in out_dirs])
+        ok = np.zeros(max(n, 1), np.uint8)
+        n_ok, n_bad = _L(0), _L(0)
+        self._check(self._l.ms_process_raw_files(self._h, a, b, n, w, h, ok.ctypes.data, C.byref(n_ok), C.byref(n_bad)))
+        assert n_ok.value + n_bad.value == n
+        return ok[:n].astype(bool)
+
+    def process_directory(self, input_dir: str, w: int, h: int, out_dir: str, recursive: bool = False, shard_index: int = 0,
+                          shard_count: int = 1):
+        """Directory branch of src/main.cpp:134-168.  Returns (n_found, n_ok, n_failed); with shard_count > 1 the
+        sorted file list is split into contiguous blocks (sharding.shard_range) and only this shard's is processed."""
+        found, good, bad = _L(0), _L(0), _L(0)
+        self._check(self._l.ms_process_directory(self._h, os.fspath(input_dir).encode(), w, h, os.fspath(out_dir).encode(),
+                                                 1 if recursive else 0, shard_index, shard_count, C.byref(found), C.byref(good),
+                                                 C.byref(bad)))
+        return found.value, good.value, bad.value
 
     # ------------------------------------------------------------------ device-pointer entry points
     def preprocess_dev(self, d_src: int, w: int, h: int, batch: int, d_out_u8: int, d_out_bf16: int = 0, stream: int = 0):

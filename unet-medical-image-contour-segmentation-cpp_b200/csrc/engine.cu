@@ -13,8 +13,12 @@
 #include "png_min.hpp"
 #include "overlay.hpp"
 
+#include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <cstring>
+#include <filesystem>
+#include <thread>
 #include <fstream>
 #include <iostream>
 #include <sstream>
@@ -30,6 +34,17 @@ void fail(int code, const std::string& what) { throw Error{code, what}; }
 }  // namespace ms
 
 using namespace ms;
+
+// host copies of one batch's results on the file path (double-buffered: writers of batch k run under batch k + 1)
+struct BatchHost {
+    PinBuf in, norm, mask;
+    std::vector<int32_t> slice_start, cstart, xy, uxy;
+    void release() {
+        in.release();
+        norm.release();
+        mask.release();
+    }
+};
 
 struct ms_handle {
     int device = 0;
@@ -58,6 +73,7 @@ struct ms_handle {
         bool busy = false;
     } slots[2];
     cudaStream_t copy_stream = nullptr, d2h_stream = nullptr;
+    BatchHost file_host[2];   // ms_process_raw_file(s) / ms_process_directory
     // log: every line is appended with open/append/close, so the C++ facade's own std::ofstream
     // (opened with ios::app on the same file, see facade.cpp) interleaves correctly with it
     std::string log_path;
@@ -347,6 +363,7 @@ void ms_destroy(ms_handle* h) {
                       &h->m2p.poly.block_counts, &h->m2p.poly.xy, &h->m2p.poly.header})
         b->release();
     h->m2p.release_crack();
+    for (auto& B : h->file_host) B.release();
     for (auto& S : h->slots) {
         if (S.ev_done) cudaEventSynchronize(S.ev_done);
         S.d_src.release();
@@ -534,82 +551,286 @@ int64_t ms_polygons_to_json(const int32_t* xy, const int32_t* contour_start, int
     }
 }
 
+// ---------------------------------------------------------------- file path (P0 + N1 + N3)
+namespace {
+
+// Everything the artefact writer of one slice needs; no CUDA, no handle state, so slices are written concurrently.
+struct SliceJob {
+    std::string raw, dir, base;
+    int status = MS_OK;          // first failure (read or write) of this file
+    std::string error;
+    std::string console;         // the reference's std::cout lines for this file, printed in file order by the caller
+    int slot = -1;               // index inside its batch (-1: never reached the GPU)
+};
+// the five artefacts of src/process.cpp:207-242 / src/mask2polygon.cpp:134-222 for one slice
+void write_artefacts(SliceJob& J, const BatchHost& B, int w, int hgt, int net_w, int net_h, int fg_value) {
+    try {
+        const size_t npx = (size_t)net_w * net_h;
+        const uint8_t* norm = B.norm.as<uint8_t>() + (size_t)J.slot * npx;
+        const uint8_t* mask = B.mask.as<uint8_t>() + (size_t)J.slot * npx;
+        const int c0 = B.slice_start[J.slot], nc = B.slice_start[J.slot + 1] - c0;
+        const int32_t* cstart = B.cstart.data() + c0;
+        std::ostringstream out;
+        mkdirs(J.dir);
+        const std::string png_path = J.dir + "/" + J.base + "_normalized.png";                 // src/process.cpp:207
+        const std::string sizes_path = J.dir + "/" + J.base + "_original_sizes.json";          // :208
+        const std::string mask_path = J.dir + "/" + J.base + "_mask.png";                      // :209
+        // src/preprocess.cpp:121-134
+        MS_REQUIRE(png::write_file(png_path, norm, net_w, net_h, 1), MS_ERR_IO, "imwrite failed: " + png_path);
+        {
+            std::ofstream jf(sizes_path, std::ios::binary);
+            MS_REQUIRE(jf.good(), MS_ERR_IO, "cannot write " + sizes_path);
+            jf << json::sidecar_text(basename_of(J.raw), w, hgt, net_w, net_h);
+        }
+        std::vector<uint8_t> vis(npx);
+        for (size_t i = 0; i < npx; ++i) vis[i] = mask[i] == 1 ? 128 : (mask[i] == 2 ? 255 : (mask[i] == fg_value ? 255 : 0));  // :178-185
+        MS_REQUIRE(png::write_file(mask_path, vis.data(), net_w, net_h, 1), MS_ERR_IO, "Failed to save mask");   // :236-239
+        out << "Processing Mask: " << J.base + ".png" << "\n";                                // src/mask2polygon.cpp:141
+        out << "Original Size: " << w << "x" << hgt << "\n";                                  // :162
+        out << "Scaled Size: " << net_w << "x" << net_h << "\n";                              // :163
+        if (nc == 0) {
+            out << "Warning: No Contours Detected\n";                                         // :184 (no JSON is written)
+        } else {
+            out << "Extracted " << nc << " Contours\n";                                       // :187
+            // overlay with unmapped (network-space) contours, red, 1 px (src/mask2polygon.cpp:114-129, 189-193)
+            std::vector<uint8_t> rgb(npx * 3);
+            for (size_t i = 0; i < npx; ++i) rgb[3 * i] = rgb[3 * i + 1] = rgb[3 * i + 2] = norm[i];
+            draw_contours_red(rgb, net_w, net_h, B.uxy.data(), cstart, nc);
+            const std::string overlay_path = J.dir + "/" + J.base + "_contour_overlay.png";  // :190
+            MS_REQUIRE(png::write_file(overlay_path, rgb.data(), net_w, net_h, 3), MS_ERR_IO, "Fail to Save Overlay PNG: " + overlay_path);
+            out << "Overlay Image Saved to: " << overlay_path << "\n";                        // :193
+            const std::string out_json = J.dir + "/" + J.base + ".json";                      // :206
+            std::ofstream f(out_json, std::ios::binary);
+            MS_REQUIRE(f.good(), MS_ERR_IO, "Fail to Create JSON File: " + out_json);
+            f << json::labelme_text(B.xy.data(), cstart, nc, J.base, w, hgt);                  // :207
+            out << "JSON Saved to: " << out_json << "\n";                                     // :208
+        }
+        J.console = out.str();
+    } catch (const Error& e) {
+        J.status = e.code;
+        J.error = e.what;
+    } catch (const std::exception& e) {
+        J.status = MS_ERR_INTERNAL;
+        J.error = e.what();
+    }
+}
+
+int writer_threads() {
+    if (const char* e = std::getenv("MEDSEG_WRITERS")) return std::max(1, std::atoi(e));
+    const unsigned hc = std::thread::hardware_concurrency();
+    return (int)std::min<unsigned>(std::max(1u, hc), 16u);
+}
+
+// Reads batch `k` of the job list into B.in (good slices packed), assigning slots.  Runs on the prefetch thread.
+void read_batch(std::vector<SliceJob>& jobs, size_t first, size_t last, BatchHost& B, int w, int hgt) {
+    const size_t n_in = (size_t)w * hgt;
+    int slot = 0;
+    for (size_t i = first; i < last; ++i) {
+        SliceJob& J = jobs[i];
+        // the reference maps w*h*2 bytes of the headerless file from offset 0 (src/preprocess.cpp:28-61, :86)
+        FILE* f = std::fopen(J.raw.c_str(), "rb");
+        if (!f) {
+            J.status = MS_ERR_IO;
+            J.error = "open failed: " + J.raw;
+            continue;
+        }
+        const size_t got = std::fread(B.in.as<uint16_t>() + (size_t)slot * n_in, 2, n_in, f);
+        std::fclose(f);
+        if (got != n_in) {
+            J.status = MS_ERR_IO;
+            J.error = "file shorter than width*height*2 bytes: " + J.raw;
+            continue;
+        }
+        J.slot = slot++;
+    }
+}
+
+// The batched file pipeline: prefetch thread (disk -> pinned) | GPU (this thread) | writer threads (artefacts), each
+// working on a different batch.  Per-file failures are recorded in the jobs; only CUDA / argument errors throw.
+void process_jobs(ms_handle* h, std::vector<SliceJob>& jobs, int w, int hgt, bool report_errors = true) {
+    MS_REQUIRE(h->unet.loaded(), MS_ERR_STATE, "no weights loaded (handle was created without a weight blob)");
+    MS_REQUIRE(w > 0 && hgt > 0, MS_ERR_ARG, "bad slice size");
+    const size_t n = jobs.size(), mb = (size_t)h->max_batch;
+    const size_t n_batches = (n + mb - 1) / mb;
+    const size_t n_in = (size_t)w * hgt, npx = (size_t)h->net_w * h->net_h;
+    BatchHost* host = h->file_host;   // kept across calls: pinned allocations cost milliseconds
+    for (int b = 0; b < 2; ++b) {
+        BatchHost& B = host[b];
+        const size_t cap = std::min(n, mb);
+        B.in.reserve(cap * n_in * 2);
+        B.norm.reserve(cap * npx);
+        B.mask.reserve(cap * npx);
+    }
+    std::thread reader;
+    std::vector<std::thread> writers;
+    std::atomic<size_t> next_job{0};
+    auto range = [&](size_t k) { return std::make_pair(k * mb, std::min(n, (k + 1) * mb)); };
+    auto join_writers = [&] {
+        for (auto& t : writers) t.join();
+        writers.clear();
+    };
+    auto report = [&](size_t k, long long infer_ms) {     // console + log lines of batch k, in file order
+        const auto r = range(k);
+        for (size_t i = r.first; i < r.second; ++i) {
+            const SliceJob& J = jobs[i];
+            h->log("\n=== Processing Image: " + basename_of(J.raw) + " ===");                 // src/process.cpp:198
+            if (J.status != MS_OK) {
+                if (report_errors) {
+                    std::cerr << "Processing error: " << J.error << std::endl;                // :257
+                    h->log("error: " + J.error);                                              // :259
+                }
+                continue;
+            }
+            h->log("Inference time: " + std::to_string(infer_ms) + " ms");                    // :228 (the whole batch)
+            std::cout << J.console;
+            h->log("Processing completed for: " + J.base);                                    // :250
+        }
+    };
+    long long infer_ms[2] = {0, 0};
+    try {
+        read_batch(jobs, range(0).first, range(0).second, host[0], w, hgt);
+        for (size_t k = 0; k < n_batches; ++k) {
+            BatchHost& B = host[k & 1];
+            if (k + 1 < n_batches) {
+                const auto r = range(k + 1);
+                reader = std::thread(read_batch, std::ref(jobs), r.first, r.second, std::ref(host[(k + 1) & 1]), w, hgt);
+            }
+            const auto r = range(k);
+            int nb = 0;
+            for (size_t i = r.first; i < r.second; ++i) nb += jobs[i].slot >= 0;
+            if (nb > 0) {
+                const auto t0 = std::chrono::high_resolution_clock::now();
+                h->d_src.reserve((size_t)nb * n_in * 2);
+                MS_CUDA(cudaMemcpyAsync(h->d_src.p, B.in.p, (size_t)nb * n_in * 2, cudaMemcpyHostToDevice, h->stream));
+                pipeline_dev(h, h->d_src.as<uint16_t>(), w, hgt, nb, h->stream);
+                const long long* hh = h->h_header.as<long long>();
+                B.slice_start.resize((size_t)nb + 1);
+                B.cstart.resize((size_t)hh[0] + 1);
+                B.xy.resize((size_t)std::max<long long>(hh[1], 1) * 2);
+                B.uxy.resize(B.xy.size());
+                ms_polygons pg{B.xy.data(), (int64_t)B.xy.size() / 2, B.cstart.data(), hh[0], B.slice_start.data(), 0, 0};
+                MS_CUDA(cudaMemcpyAsync(B.norm.p, h->d_norm.p, (size_t)nb * npx, cudaMemcpyDeviceToHost, h->stream));
+                MS_CUDA(cudaMemcpyAsync(B.mask.p, h->d_mask.p, (size_t)nb * npx, cudaMemcpyDeviceToHost, h->stream));
+                copy_polygons_out(h, nb, &pg, h->stream);
+                if (hh[1] > 0) {   // the overlay is drawn in network space: emit once more with the identity mapping
+                    m2p_phase_b(h->m2p, h->m2p.poly, h->net_h, h->net_w, nb, h->net_w, h->net_h, h->stream);
+                    download_sync(h, B.uxy.data(), h->m2p.poly.xy.p, (size_t)hh[1] * 8, h->stream);
+                }
+                infer_ms[k & 1] = std::chrono::duration_cast<std::chrono::milliseconds>(std::chrono::high_resolution_clock::now() - t0).count();
+            }
+            join_writers();                                   // batch k - 1 is on disk
+            if (k > 0) report(k - 1, infer_ms[(k - 1) & 1]);
+            next_job = r.first;
+            const int nt = std::min<int>(writer_threads(), std::max(nb, 1));
+            for (int t = 0; t < nt; ++t)
+                writers.emplace_back([&, r, k] {
+                    for (size_t i = next_job.fetch_add(1); i < r.second; i = next_job.fetch_add(1))
+                        if (jobs[i].slot >= 0) write_artefacts(jobs[i], host[k & 1], w, hgt, h->net_w, h->net_h, h->fg_value);
+                });
+            if (reader.joinable()) reader.join();
+        }
+        join_writers();
+        if (n_batches > 0) report(n_batches - 1, infer_ms[(n_batches - 1) & 1]);
+    } catch (...) {
+        if (reader.joinable()) reader.join();
+        join_writers();
+        throw;
+    }
+}
+
+bool is_16bit_image(const std::string& path) {               // src/main.cpp:18-25
+    std::string ext = std::filesystem::path(path).extension().string();
+    for (auto& c : ext) c = (char)std::tolower((unsigned char)c);
+    return ext == ".raw" || ext == ".dcm" || ext == ".tif" || ext == ".tiff";
+}
+
+}  // namespace
+
 int ms_process_raw_file(ms_handle* h, const char* raw_path, int w, int hgt, const char* out_dir) {
     if (!h) return MS_ERR_ARG;
     return guarded(h, [&] {
         MS_REQUIRE(raw_path && out_dir && w > 0 && hgt > 0, MS_ERR_ARG, "process_raw_file: bad argument");
         const auto t0 = std::chrono::high_resolution_clock::now();
-        const std::string raw = raw_path, dir = out_dir;
-        const std::string base = stem_of(raw);                                             // src/process.cpp:201
-        h->log("\n=== Processing Image: " + basename_of(raw) + " ===");                     // :198
-        const std::string png_path = dir + "/" + base + "_normalized.png";                 // :207
-        const std::string sizes_path = dir + "/" + base + "_original_sizes.json";          // :208
-        const std::string mask_path = dir + "/" + base + "_mask.png";                      // :209
-        // read the headerless u16 slice (the reference mmaps w*h*2 bytes from offset 0, src/preprocess.cpp:86)
-        const size_t n_in = (size_t)w * hgt;
-        std::vector<uint16_t> src(n_in);
-        {
-            FILE* f = std::fopen(raw.c_str(), "rb");
-            MS_REQUIRE(f, MS_ERR_IO, "open failed: " + raw);
-            const size_t got = std::fread(src.data(), 2, n_in, f);
-            std::fclose(f);
-            MS_REQUIRE(got == n_in, MS_ERR_IO, "file shorter than width*height*2 bytes: " + raw);
-        }
-        mkdirs(dir);
-        const size_t npx = (size_t)h->net_w * h->net_h;
-        std::vector<uint8_t> norm(npx), mask(npx);
-        h->d_src.reserve(n_in * 2);
-        upload(h, h->d_src.p, src.data(), n_in * 2, h->stream);
-        const auto ti0 = std::chrono::high_resolution_clock::now();
-        pipeline_dev(h, h->d_src.as<uint16_t>(), w, hgt, 1, h->stream);
-        const auto ti1 = std::chrono::high_resolution_clock::now();
-        const long long* hh = h->h_header.as<long long>();
-        const int nc = (int)hh[0];
-        std::vector<int32_t> cstart((size_t)nc + 1), xy((size_t)std::max<long long>(hh[1], 1) * 2), sl(2);
-        ms_polygons pg{xy.data(), (int64_t)xy.size() / 2, cstart.data(), nc, sl.data(), 0, 0};
-        MS_CUDA(cudaMemcpyAsync(norm.data(), h->d_norm.p, npx, cudaMemcpyDeviceToHost, h->stream));
-        MS_CUDA(cudaMemcpyAsync(mask.data(), h->d_mask.p, npx, cudaMemcpyDeviceToHost, h->stream));
-        copy_polygons_out(h, 1, &pg, h->stream);
-        h->log("Inference time: " + std::to_string(std::chrono::duration_cast<std::chrono::milliseconds>(ti1 - ti0).count()) + " ms");  // :228
-
-        // artefacts (src/preprocess.cpp:121-134, src/process.cpp:234-239)
-        MS_REQUIRE(png::write_file(png_path, norm.data(), h->net_w, h->net_h, 1), MS_ERR_IO, "imwrite failed: " + png_path);
-        {
-            std::ofstream jf(sizes_path, std::ios::binary);
-            MS_REQUIRE(jf.good(), MS_ERR_IO, "cannot write " + sizes_path);
-            jf << json::sidecar_text(basename_of(raw), w, hgt, h->net_w, h->net_h);
-        }
-        std::vector<uint8_t> vis(npx);
-        for (size_t i = 0; i < npx; ++i) vis[i] = mask[i] == 1 ? 128 : (mask[i] == 2 ? 255 : (mask[i] == h->fg_value ? 255 : 0));  // :178-185
-        MS_REQUIRE(png::write_file(mask_path, vis.data(), h->net_w, h->net_h, 1), MS_ERR_IO, "Failed to save mask");
-
-        std::cout << "Processing Mask: " << base + ".png" << std::endl;                   // src/mask2polygon.cpp:141
-        std::cout << "Original Size: " << w << "x" << hgt << std::endl;                   // :162
-        std::cout << "Scaled Size: " << h->net_w << "x" << h->net_h << std::endl;          // :163
-        if (nc == 0) {
-            std::cout << "Warning: No Contours Detected" << std::endl;                    // :184 (no JSON is written)
-        } else {
-            std::cout << "Extracted " << nc << " Contours" << std::endl;                  // :187
-            // overlay with unmapped (network-space) contours, red, 1 px (src/mask2polygon.cpp:114-129, 189-193)
-            std::vector<int32_t> uxy((size_t)hh[1] * 2);
-            m2p_phase_b(h->m2p, h->m2p.poly, h->net_h, h->net_w, 1, h->net_w, h->net_h, h->stream);
-            download_sync(h, uxy.data(), h->m2p.poly.xy.p, (size_t)hh[1] * 8, h->stream);
-            std::vector<uint8_t> rgb(npx * 3);
-            for (size_t i = 0; i < npx; ++i) rgb[3 * i] = rgb[3 * i + 1] = rgb[3 * i + 2] = norm[i];
-            draw_contours_red(rgb, h->net_w, h->net_h, uxy.data(), cstart.data(), nc);
-            const std::string overlay_path = dir + "/" + base + "_contour_overlay.png";  // :190
-            MS_REQUIRE(png::write_file(overlay_path, rgb.data(), h->net_w, h->net_h, 3), MS_ERR_IO, "Fail to Save Overlay PNG: " + overlay_path);
-            std::cout << "Overlay Image Saved to: " << overlay_path << std::endl;         // :193
-            const std::string out_json = dir + "/" + base + ".json";                      // :206
-            std::ofstream f(out_json, std::ios::binary);
-            MS_REQUIRE(f.good(), MS_ERR_IO, "Fail to Create JSON File: " + out_json);
-            f << json::labelme_text(xy.data(), cstart.data(), nc, base, w, hgt);           // :207
-            std::cout << "JSON Saved to: " << out_json << std::endl;                      // :208
-        }
+        std::vector<SliceJob> jobs(1);
+        jobs[0].raw = raw_path;
+        jobs[0].dir = out_dir;
+        jobs[0].base = stem_of(jobs[0].raw);                                              // src/process.cpp:201
+        // process_jobs reports per-file failures on std::cerr itself; here the failure is also the call's status
+        process_jobs(h, jobs, w, hgt, false);
+        if (jobs[0].status != MS_OK) fail(jobs[0].status, jobs[0].error);
         const auto total_ms = std::chrono::duration_cast<std::chrono::milliseconds>(std::chrono::high_resolution_clock::now() - t0).count();
         h->log("Total processing time: " + std::to_string(total_ms) + " ms");            // src/process.cpp:249
-        h->log("Processing completed for: " + base);                                      // :250
         std::cout << "Total processing time: " << total_ms << " ms" << std::endl;         // :253
+    });
+}
+
+int ms_process_raw_files(ms_handle* h, const char* const* raw_paths, const char* const* out_dirs, int64_t n, int w, int hgt, uint8_t* ok,
+                         int64_t* n_ok, int64_t* n_failed) {
+    if (!h) return MS_ERR_ARG;
+    return guarded(h, [&] {
+        MS_REQUIRE(n >= 0 && (n == 0 || (raw_paths && out_dirs)) && w > 0 && hgt > 0, MS_ERR_ARG, "process_raw_files: bad argument");
+        std::vector<SliceJob> jobs((size_t)n);
+        for (int64_t i = 0; i < n; ++i) {
+            MS_REQUIRE(raw_paths[i] && out_dirs[i], MS_ERR_ARG, "process_raw_files: null path");
+            jobs[i].raw = raw_paths[i];
+            jobs[i].dir = out_dirs[i];
+            jobs[i].base = stem_of(jobs[i].raw);
+        }
+        const auto t0 = std::chrono::high_resolution_clock::now();
+        process_jobs(h, jobs, w, hgt);
+        int64_t good = 0;
+        for (int64_t i = 0; i < n; ++i) {
+            if (ok) ok[i] = jobs[i].status == MS_OK;
+            good += jobs[i].status == MS_OK;
+        }
+        if (n_ok) *n_ok = good;
+        if (n_failed) *n_failed = n - good;
+        const auto total_ms = std::chrono::duration_cast<std::chrono::milliseconds>(std::chrono::high_resolution_clock::now() - t0).count();
+        h->log("Total processing time: " + std::to_string(total_ms) + " ms (" + std::to_string(n) + " files)");
+    });
+}
+
+int ms_process_directory(ms_handle* h, const char* input_dir, int w, int hgt, const char* out_dir, int recursive, int shard_index,
+                         int shard_count, int64_t* n_found, int64_t* n_ok, int64_t* n_failed) {
+    if (!h) return MS_ERR_ARG;
+    return guarded(h, [&] {
+        namespace fs = std::filesystem;
+        MS_REQUIRE(input_dir && out_dir && w > 0 && hgt > 0 && shard_count >= 1 && shard_index >= 0 && shard_index < shard_count, MS_ERR_ARG,
+                   "process_directory: bad argument");
+        std::error_code ec;
+        MS_REQUIRE(fs::is_directory(input_dir, ec), MS_ERR_IO, std::string("not a directory: ") + input_dir);
+        // src/main.cpp:28-48; sorted so that every rank sees the same list
+        std::vector<std::string> files;
+        if (recursive) {
+            for (fs::recursive_directory_iterator it(input_dir, fs::directory_options::skip_permission_denied, ec), end; it != end && !ec; it.increment(ec))
+                if (it->is_regular_file(ec) && is_16bit_image(it->path().string())) files.push_back(it->path().string());
+        } else {
+            for (fs::directory_iterator it(input_dir, fs::directory_options::skip_permission_denied, ec), end; it != end && !ec; it.increment(ec))
+                if (it->is_regular_file(ec) && is_16bit_image(it->path().string())) files.push_back(it->path().string());
+        }
+        std::sort(files.begin(), files.end());
+        if (n_found) *n_found = (int64_t)files.size();
+        // contiguous block of the list per shard; earlier shards take the remainder
+        const size_t total = files.size();
+        const size_t base = total / (size_t)shard_count, rem = total % (size_t)shard_count;   // sharding.py: shard_range
+        const size_t lo = (size_t)shard_index * base + std::min<size_t>((size_t)shard_index, rem), hi = lo + base + ((size_t)shard_index < rem);
+        std::vector<SliceJob> jobs(hi - lo);
+        for (size_t i = lo; i < hi; ++i) {
+            SliceJob& J = jobs[i - lo];
+            J.raw = files[i];
+            J.base = stem_of(J.raw);
+            J.dir = out_dir;
+            if (recursive) {                                                               // src/main.cpp:151-156: keep the tree
+                const std::string rel = fs::relative(fs::path(J.raw), fs::path(input_dir), ec).parent_path().string();
+                if (!rel.empty()) J.dir = (fs::path(out_dir) / rel).string();
+            }
+        }
+        mkdirs(out_dir);                                                                   // src/main.cpp:130
+        process_jobs(h, jobs, w, hgt);
+        int64_t good = 0;
+        for (const auto& J : jobs) good += J.status == MS_OK;
+        if (n_ok) *n_ok = good;
+        if (n_failed) *n_failed = (int64_t)jobs.size() - good;
     });
 }
 

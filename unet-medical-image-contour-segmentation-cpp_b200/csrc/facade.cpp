@@ -97,6 +97,63 @@ bool process_single_image(const std::string& raw_path, int width, int height, co
     return true;
 }
 
+int process_image_batch(const std::vector<std::string>& raw_paths, int width, int height, const std::vector<std::string>& output_dirs,
+                        std::vector<bool>* ok) {
+    if (ok) ok->assign(raw_paths.size(), false);
+    if (!g_handle) {
+        std::cerr << "Processing error: Engine not initialized" << std::endl;
+        return 0;
+    }
+    if (output_dirs.size() != raw_paths.size()) {
+        std::cerr << "Processing error: one output directory per file is required" << std::endl;
+        return 0;
+    }
+    std::vector<const char*> a, b;
+    for (size_t i = 0; i < raw_paths.size(); ++i) {
+        a.push_back(raw_paths[i].c_str());
+        b.push_back(output_dirs[i].c_str());
+    }
+    std::vector<uint8_t> flags(raw_paths.size() + 1, 0);
+    int64_t good = 0, bad = 0;
+    const int rc = ms_process_raw_files(g_handle, a.data(), b.data(), (int64_t)raw_paths.size(), width, height, flags.data(), &good, &bad);
+    if (rc != MS_OK) {
+        std::cerr << "Processing error: " << ms_last_error(g_handle) << std::endl;
+        return 0;
+    }
+    if (ok)
+        for (size_t i = 0; i < raw_paths.size(); ++i) (*ok)[i] = flags[i] != 0;
+    return (int)good;
+}
+
+bool process_directory(const std::string& input_dir, int width, int height, const std::string& output_dir, bool recursive,
+                       int* success_count, int* fail_count) {
+    if (success_count) *success_count = 0;
+    if (fail_count) *fail_count = 0;
+    if (!g_handle) {
+        std::cerr << "Processing error: Engine not initialized" << std::endl;
+        return false;
+    }
+    std::cout << "Processing directory: " << input_dir << std::endl;                   // src/main.cpp:135
+    std::cout << "Recursive: " << (recursive ? "Yes" : "No") << std::endl;             // :136
+    int64_t found = 0, good = 0, bad = 0;
+    const int rc = ms_process_directory(g_handle, input_dir.c_str(), width, height, output_dir.c_str(), recursive ? 1 : 0, 0, 1, &found,
+                                        &good, &bad);
+    if (rc != MS_OK) {
+        std::cerr << "Directory error: " << ms_last_error(g_handle) << std::endl;      // :44
+        return false;
+    }
+    if (found == 0) {
+        std::cerr << "No 16-bit images found in directory" << std::endl;               // :140
+        return false;
+    }
+    std::cout << "\nDirectory processing completed:" << std::endl;                    // :166-168
+    std::cout << "  Success: " << good << " files" << std::endl;
+    std::cout << "  Failed: " << bad << " files" << std::endl;
+    if (success_count) *success_count = (int)good;
+    if (fail_count) *fail_count = (int)bad;
+    return true;
+}
+
 void cleanup_resources() {
     if (g_handle) {
         ms_destroy(g_handle);                                                          // src/cleanup.cpp:16-45
