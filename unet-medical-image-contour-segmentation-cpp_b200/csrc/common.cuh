@@ -125,10 +125,12 @@ struct PolyDev {              // device-resident polygon set + counters
     DevBuf slice_start;       // int32 [batch + 1]
     DevBuf block_counts;      // int32 scratch
     DevBuf xy;                // int32 [cap_points * 2]
-    DevBuf header;            // int64 [4]: n_contours, n_points, overflow, trace_error
+    DevBuf header;            // int64 [8]: n_contours, n_points, overflow, trace_error, n_chunks
+    DevBuf chunks;            // int2 [cap_chunks * 64]: kept vertices (unmapped) in walk order, 64 per chunk
+    DevBuf chunk_meta;        // int2 [cap_chunks]: {contour, sequence number} of each chunk
     int64_t cap_contours = 0, cap_points = 0;
     void release() {
-        for (DevBuf* b : {&starts, &start_slice, &npts, &slice_start, &block_counts, &xy, &header}) b->release();
+        for (DevBuf* b : {&starts, &start_slice, &npts, &slice_start, &block_counts, &xy, &header, &chunks, &chunk_meta}) b->release();
     }
 };
 struct M2pWs {

@@ -25,7 +25,7 @@ namespace ms {
 
 namespace {
 
-constexpr size_t kTraceSmemMax = 200 * 1024;   // slices up to ~1264 x 1264 trace out of shared memory
+constexpr size_t kTraceSmemMax = 200 * 1024;   // slices up to ~1264 x 1264 trace out of shared memory (+ the 8 KiB step table)
 
 // mask -> bits of (mask > thr), one word per warp.  grid = (ceil(W / 256), H, batch), block = 256 (8 words)
 __global__ void __launch_bounds__(256) thr_bits_kernel(const uint8_t* __restrict__ mask, int H, int W, int wpitch, int thr,
@@ -150,6 +150,7 @@ __global__ void __launch_bounds__(1024) scan_slices_kernel(const int* __restrict
         header[1] = 0;      // n_points (set by scan_points_kernel)
         header[2] = 0;      // overflow flags
         header[3] = 0;      // trace errors
+        header[4] = 0;      // vertex chunks handed out by the border followers
     }
 }
 
@@ -189,18 +190,63 @@ __global__ void __launch_bounds__(256) write_starts_kernel(const uint32_t* __res
     }
 }
 
-struct CountEmit {
-    __device__ void operator()(int, int) const {}
+// The border followers walk every contour ONCE.  Kept vertices go, unmapped, into 64-vertex chunks handed out by an atomic
+// counter (a chunk is owned by one contour and filled completely before the next one is taken); after the per-contour
+// counts are scanned, gather_kernel copies chunk (contour c, sequence s) to offset[c] + 64 s with the coordinate
+// mapping applied -- a parallel copy instead of a second walk, and re-runnable with another mapping (the overlay wants
+// network-space coordinates, the JSON original-space ones).
+constexpr int kChunk = 64;
+struct ChunkEmit {
+    int2* tmp;                       // [cap_chunks][kChunk]
+    int2* meta;                      // [cap_chunks] {contour, sequence}
+    unsigned long long* counter;     // header[4]
+    long long cap_chunks;
+    int contour;
+    int k;
+    int2* cur;
+    __device__ void operator()(int x, int y) {
+        const int i = k & (kChunk - 1);
+        if (i == 0) {
+            const unsigned long long j = atomicAdd(counter, 1ull);
+            cur = nullptr;
+            if ((long long)j < cap_chunks) {   // else: capacities too small, the caller grows them and re-runs (counts stay exact)
+                meta[j] = make_int2(contour, k / kChunk);
+                cur = tmp + j * kChunk;
+            }
+        }
+        if (cur) cur[i] = make_int2(x, y);
+        ++k;
+    }
 };
-struct WriteEmit {
+__device__ __forceinline__ int2 map_point(int2 p, double sx, double sy) {
+    // src/mask2polygon.cpp:54-55: static_cast<int>(pt.x * scale_x)
+    return make_int2((int)__dmul_rn((double)p.x, sx), (int)__dmul_rn((double)p.y, sy));
+}
+struct WriteEmit {   // direct mapped write at a known offset (crack path)
     int2* dst;
     double sx, sy;
     mutable int i;
-    __device__ void operator()(int x, int y) const {
-        // src/mask2polygon.cpp:54-55: static_cast<int>(pt.x * scale_x)
-        dst[i++] = make_int2((int)__dmul_rn((double)x, sx), (int)__dmul_rn((double)y, sy));
-    }
+    __device__ void operator()(int x, int y) const { dst[i++] = map_point(make_int2(x, y), sx, sy); }
 };
+inline long long chunk_capacity(const PolyDev& P) { return P.cap_points / kChunk + P.cap_contours + 1; }
+
+// one thread per chunk slot: copy + map.  grid covers cap_chunks * kChunk threads
+__global__ void __launch_bounds__(256) gather_kernel(const int2* __restrict__ tmp, const int2* __restrict__ meta, long long* __restrict__ header,
+                                                      long long cap_chunks, const int* __restrict__ offsets, int cap_contours,
+                                                      long long cap_points, double sx, double sy, int2* __restrict__ xy) {
+    const long long idx = (long long)blockIdx.x * 256 + threadIdx.x;
+    const long long j = idx / kChunk;
+    const long long n_chunks = header[4] < cap_chunks ? header[4] : cap_chunks;
+    if (j >= n_chunks) return;
+    if (header[1] > cap_points || header[0] > cap_contours) {   // caller's buffers too small: write nothing, flag it
+        if (idx == 0) header[2] |= 2;
+        return;
+    }
+    const int2 m = meta[j];
+    const int k = m.y * kChunk + (int)(idx % kChunk);
+    const int base = offsets[m.x];
+    if (k < offsets[m.x + 1] - base) xy[base + k] = map_point(tmp[idx], sx, sy);
+}
 
 // 8-neighbour foreground code of a pixel from bit-packed rows.  PADDED: `bits` has a zero word / zero row on every
 // side (shared-memory copy); otherwise bounds are checked (global memory, large slices).
@@ -209,30 +255,97 @@ __device__ __forceinline__ unsigned code_from_rows(unsigned up, unsigned cu, uns
     return ((cu >> 2) & 1u) | (((up >> 2) & 1u) << 1) | (((up >> 1) & 1u) << 2) | ((up & 1u) << 3) | ((cu & 1u) << 4) |
            ((dn & 1u) << 5) | (((dn >> 1) & 1u) << 6) | (((dn >> 2) & 1u) << 7);
 }
-struct PaddedBitsCode {
+// 3x3 window of a pixel as 9 raw bits: up3 | cu3 << 3 | dn3 << 6, bit 0 of each triple = x - 1
+struct PaddedBitsWindow {
     const uint32_t* bits;   // (H + 2) rows x pitch words, row 0 / word 0 are the zero frame
     int pitch;
-    __device__ __forceinline__ unsigned operator()(int, int x, int y) const {
+    __device__ __forceinline__ unsigned operator()(int x, int y) const {
         const int X = x + 31, w = X >> 5, sh = X & 31;              // pixel x lives at bit x + 32 of the padded row
-        const uint32_t* r = bits + (size_t)y * pitch + w;            // padded row y <-> image row y - 1
-        return code_from_rows(__funnelshift_r(r[0], r[1], sh) & 7u, __funnelshift_r(r[pitch], r[pitch + 1], sh) & 7u,
-                              __funnelshift_r(r[2 * pitch], r[2 * pitch + 1], sh) & 7u);
+        const uint32_t* r = bits + y * pitch + w;                    // padded row y <-> image row y - 1
+        return (__funnelshift_r(r[0], r[1], sh) & 7u) | ((__funnelshift_r(r[pitch], r[pitch + 1], sh) & 7u) << 3) |
+               ((__funnelshift_r(r[2 * pitch], r[2 * pitch + 1], sh) & 7u) << 6);
     }
 };
+__device__ __forceinline__ unsigned code_from_window(unsigned w9) { return code_from_rows(w9 & 7u, (w9 >> 3) & 7u, (w9 >> 6) & 7u); }
+
+// One border-following step is a dependent chain (position -> window -> next direction -> position), so its depth is
+// the walking speed.  The chain "assemble the direction-indexed code, rotate by d_prev, find first set, look up dx/dy"
+// is replaced by ONE shared-memory lookup indexed by {d_prev, raw 3x3 window}: 4096 entries of
+//   bits 0-2 d_out | bits 3-4 dx + 1 | bits 5-6 dy + 1 | bits 7-9 next d_prev = d_out + 4
+constexpr int kLutEntries = 8 * 512;
+__device__ void build_trace_lut(uint16_t* lut) {
+    for (int i = threadIdx.x; i < kLutEntries; i += blockDim.x) {
+        const unsigned cc = code_from_window(i & 511), dp = i >> 9;
+        unsigned e = 0;
+        if (cc) {
+            const unsigned rot = ((cc | (cc << 8)) >> ((dp + 1) & 7)) & 0xFFu;
+            const int d = (int)(dp + 1 + (__ffs((int)rot) - 1)) & 7;
+            e = (unsigned)d | ((unsigned)(trace_dx(d) + 1) << 3) | ((unsigned)(trace_dy(d) + 1) << 5) | ((unsigned)((d + 4) & 7) << 7);
+        }
+        lut[i] = (uint16_t)e;
+    }
+}
+// trace_run (contour_trace.cuh) with the step taken from the table; same state, same results
+template <class Window, class Inside>
+__device__ __forceinline__ int trace_run_lut(Window win9, const uint16_t* __restrict__ lut, int W, TraceState& s, int max_steps,
+                                             ChunkEmit& emit, Inside inside) {
+    if (s.phase == 2) return 1;
+    if (s.phase == 0) {
+        if (!inside(s.x, s.y)) return 0;
+        const unsigned c0 = code_from_window(win9(s.x, s.y));
+        if (c0 == 0) {  // isolated pixel
+            emit(s.x, s.y);
+            s.n = 1;
+            s.phase = 2;
+            return 1;
+        }
+        unsigned rev = 0;   // probe NW, N, NE, E, SE, S, SW, W: bit k <-> direction (3 - k) & 7
+#pragma unroll
+        for (int k = 0; k < 8; ++k) rev |= ((c0 >> ((3 - k) & 7)) & 1u) << k;
+        const int dL = (3 - (__ffs((int)rev) - 1)) & 7;
+        s.last = s.start + trace_dy(dL) * W + trace_dx(dL);
+        s.d_prev = dL;
+        s.prev_out = (dL + 4) & 7;
+        s.phase = 1;
+    }
+    int x = s.x, y = s.y, p = s.p, prev_out = s.prev_out, n = s.n;
+    unsigned dp9 = (unsigned)s.d_prev << 9;
+    int status = -1;
+    for (int step = 0; step < max_steps; ++step) {
+        if (!inside(x, y)) { status = 0; break; }
+        const unsigned e = lut[dp9 | win9(x, y)];
+        const int d = e & 7;
+        if (d != prev_out) {
+            emit(x, y);
+            ++n;
+            prev_out = d;
+        }
+        const int ddx = (int)((e >> 3) & 3u) - 1, ddy = (int)((e >> 5) & 3u) - 1;
+        const int q = p + ddy * W + ddx;
+        if (q == s.start && p == s.last) { status = 1; break; }
+        p = q;
+        x += ddx;
+        y += ddy;
+        dp9 = (e << 2) & (7u << 9);
+    }
+    s.x = x; s.y = y; s.p = p; s.prev_out = prev_out; s.n = n; s.d_prev = (int)(dp9 >> 9);
+    if (status == 1) s.phase = 2;
+    return status;
+}
 // Large slices (the bit image does not fit in shared memory): one CTA per contour keeps a 256 x 256-pixel WINDOW of the
 // bit image in shared memory, centred on the walk; thread 0 follows the border (six LDS per step) until it leaves the
 // window's interior, then the CTA re-centres the window and the walk resumes (contour_trace.cuh: trace_run).  A long
 // contour (the stress masks have ~10^5-step borders) therefore walks at shared-memory latency, not at one dependent
 // L2 access per step, and all contours of all slices walk concurrently.
 constexpr int kWinW = 256, kWinH = 256, kWinPitch = kWinW / 32 + 1;   // +1 word: funnel shifts read one word ahead
-struct WindowCode {
+struct WindowBits {
     const uint32_t* win;   // kWinH rows x kWinPitch words
     int x0, y0;            // image coordinates of the window's first pixel (x0 a multiple of 32, may be negative)
-    __device__ __forceinline__ unsigned operator()(int, int x, int y) const {
+    __device__ __forceinline__ unsigned operator()(int x, int y) const {
         const int cx = x - x0 - 1, w = cx >> 5, sh = cx & 31;          // bits cx .. cx+2 = x-1 .. x+1
         const uint32_t* r = win + (y - y0 - 1) * kWinPitch + w;
-        return code_from_rows(__funnelshift_r(r[0], r[1], sh) & 7u, __funnelshift_r(r[kWinPitch], r[kWinPitch + 1], sh) & 7u,
-                              __funnelshift_r(r[2 * kWinPitch], r[2 * kWinPitch + 1], sh) & 7u);
+        return (__funnelshift_r(r[0], r[1], sh) & 7u) | ((__funnelshift_r(r[kWinPitch], r[kWinPitch + 1], sh) & 7u) << 3) |
+               ((__funnelshift_r(r[2 * kWinPitch], r[2 * kWinPitch + 1], sh) & 7u) << 6);
     }
 };
 struct WindowInside {
@@ -242,25 +355,21 @@ struct WindowInside {
     }
 };
 
-template <bool EMIT>
 __global__ void __launch_bounds__(64) trace_window_kernel(const uint32_t* __restrict__ fgbits, int H, int W, int wpitch,
                                                            const int* __restrict__ starts, const int* __restrict__ start_slice,
                                                            long long* __restrict__ header, int cap_contours, int* __restrict__ npts,
-                                                           long long cap_points, double sx, double sy, int2* __restrict__ xy) {
+                                                           int2* __restrict__ chunk_tmp, int2* __restrict__ chunk_meta, long long cap_chunks) {
     __shared__ uint32_t win[kWinH * kWinPitch];
+    __shared__ uint16_t lut[kLutEntries];
+    build_trace_lut(lut);
     __shared__ int s_org[2], s_status;
     const int c = blockIdx.x;
     const long long n = header[0] < cap_contours ? header[0] : cap_contours;
     if (c >= n) return;
-    if (EMIT && header[1] > cap_points) {   // caller's buffer too small: write nothing, flag it
-        if (c == 0 && threadIdx.x == 0) header[2] |= 2;
-        return;
-    }
     const uint32_t* B = fgbits + (size_t)start_slice[c] * H * wpitch;
     TraceState st;
     trace_begin(st, W, starts[c]);
-    CountEmit count_emit;
-    WriteEmit write_emit{xy + (EMIT ? npts[c] : 0), sx, sy, 0};
+    ChunkEmit emit{chunk_tmp, chunk_meta, (unsigned long long*)&header[4], cap_chunks, c, 0, nullptr};
     for (int round = 0; round < (1 << 20); ++round) {
         if (threadIdx.x == 0) {
             s_org[0] = ((st.x - kWinW / 2) >> 5) << 5;
@@ -275,14 +384,14 @@ __global__ void __launch_bounds__(64) trace_window_kernel(const uint32_t* __rest
         }
         __syncthreads();
         if (threadIdx.x == 0) {
-            const WindowCode code{win, x0, y0};
+            const WindowBits bits{win, x0, y0};
             const WindowInside inside{x0, y0};
-            s_status = EMIT ? trace_run(code, W, st, 8 * H * W + 8, write_emit, inside) : trace_run(code, W, st, 8 * H * W + 8, count_emit, inside);
+            s_status = trace_run_lut(bits, lut, W, st, 8 * H * W + 8, emit, inside);
         }
         __syncthreads();
         if (s_status != 0) break;
     }
-    if (threadIdx.x == 0 && !EMIT) {
+    if (threadIdx.x == 0) {
         if (s_status != 1) atomicAdd((unsigned long long*)&header[3], 1ull);
         npts[c] = s_status == 1 ? st.n : 0;
     }
@@ -291,34 +400,30 @@ __global__ void __launch_bounds__(64) trace_window_kernel(const uint32_t* __rest
 // Shared-memory variant: one CTA per slice keeps the slice's bit-packed foreground (H*W/8 bytes, padded by a zero word /
 // zero row on every side) in shared memory, so a border-following step costs six LDS instead of dependent global
 // loads.  Thread t traces contours slice_start[b] + t, + blockDim, ...
-template <bool EMIT>
 __global__ void __launch_bounds__(128) trace_smem_kernel(const uint32_t* __restrict__ fgbits, int H, int W, int wpitch,
                                                           const int* __restrict__ starts, const int* __restrict__ slice_start,
                                                           long long* __restrict__ header, int cap_contours, int* __restrict__ npts,
-                                                          long long cap_points, double sx, double sy, int2* __restrict__ xy) {
+                                                          int2* __restrict__ chunk_tmp, int2* __restrict__ chunk_meta, long long cap_chunks) {
     extern __shared__ uint32_t sbits[];
+    __shared__ uint16_t lut[kLutEntries];
     const int b = blockIdx.x;
     const int pitch = wpitch + 2;
     const int c_lo = slice_start[b], c_hi = min(slice_start[b + 1], cap_contours);
     if (c_lo >= c_hi) return;
-    if (EMIT && header[1] > cap_points) {
-        if (threadIdx.x == 0) header[2] |= 2;
-        return;
-    }
     for (int i = threadIdx.x; i < (H + 2) * pitch; i += blockDim.x) {
         const int r = i / pitch, c = i % pitch;
         sbits[i] = (r >= 1 && r <= H && c >= 1 && c <= wpitch) ? fgbits[((size_t)b * H + (r - 1)) * wpitch + (c - 1)] : 0u;
     }
+    build_trace_lut(lut);
     __syncthreads();
-    const PaddedBitsCode code{sbits, pitch};
+    const PaddedBitsWindow bits{sbits, pitch};
     for (int c = c_lo + threadIdx.x; c < c_hi; c += blockDim.x) {
-        if (EMIT) {
-            trace_contour_fn(code, W, starts[c], 8 * H * W + 8, WriteEmit{xy + npts[c], sx, sy, 0});
-        } else {
-            const int cnt = trace_contour_fn(code, W, starts[c], 8 * H * W + 8, CountEmit{});
-            if (cnt < 0) atomicAdd((unsigned long long*)&header[3], 1ull);
-            npts[c] = cnt < 0 ? 0 : cnt;
-        }
+        TraceState ts;
+        trace_begin(ts, W, starts[c]);
+        ChunkEmit emit{chunk_tmp, chunk_meta, (unsigned long long*)&header[4], cap_chunks, c, 0, nullptr};
+        const int cnt = trace_run_lut(bits, lut, W, ts, 8 * H * W + 8, emit, TraceAlwaysInside{}) == 1 ? ts.n : -1;
+        if (cnt < 0) atomicAdd((unsigned long long*)&header[3], 1ull);
+        npts[c] = cnt < 0 ? 0 : cnt;
     }
 }
 
@@ -613,25 +718,33 @@ TraceMode pick_trace_mode(int h, int w, int batch) {
     return crack_ok ? kTraceCrack : kTraceWindow;
 }
 
-template <bool EMIT>
-void launch_trace(M2pWs& ws, PolyDev& P, TraceMode mode, int h, int w, int batch, double sx, double sy, cudaStream_t st) {
+// the single walk: per-contour counts into P.npts, kept vertices into P.chunks
+void launch_trace(M2pWs& ws, PolyDev& P, TraceMode mode, int h, int w, int batch, cudaStream_t st) {
     const int wpitch = cdiv(w, 32);
     const size_t trace_smem = (size_t)(h + 2) * (wpitch + 2) * 4;
     long long* header = P.header.as<long long>();
+    const long long cap_chunks = chunk_capacity(P);
     if (mode == kTraceSmem) {
         static bool attr = false;
         if (!attr) {
-            MS_CUDA(cudaFuncSetAttribute(trace_smem_kernel<EMIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTraceSmemMax));
+            MS_CUDA(cudaFuncSetAttribute(trace_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTraceSmemMax));
             attr = true;
         }
-        trace_smem_kernel<EMIT><<<batch, 128, trace_smem, st>>>(ws.fgbits.as<uint32_t>(), h, w, wpitch, P.starts.as<int>(),
-                                                               P.slice_start.as<int>(), header, (int)P.cap_contours, P.npts.as<int>(),
-                                                               (long long)P.cap_points, sx, sy, P.xy.as<int2>());
+        trace_smem_kernel<<<batch, 128, trace_smem, st>>>(ws.fgbits.as<uint32_t>(), h, w, wpitch, P.starts.as<int>(), P.slice_start.as<int>(),
+                                                         header, (int)P.cap_contours, P.npts.as<int>(), P.chunks.as<int2>(),
+                                                         P.chunk_meta.as<int2>(), cap_chunks);
     } else {
-        trace_window_kernel<EMIT><<<(unsigned)P.cap_contours, 64, 0, st>>>(ws.fgbits.as<uint32_t>(), h, w, wpitch, P.starts.as<int>(),
-                                                                          P.start_slice.as<int>(), header, (int)P.cap_contours,
-                                                                          P.npts.as<int>(), (long long)P.cap_points, sx, sy, P.xy.as<int2>());
+        trace_window_kernel<<<(unsigned)P.cap_contours, 64, 0, st>>>(ws.fgbits.as<uint32_t>(), h, w, wpitch, P.starts.as<int>(),
+                                                                    P.start_slice.as<int>(), header, (int)P.cap_contours, P.npts.as<int>(),
+                                                                    P.chunks.as<int2>(), P.chunk_meta.as<int2>(), cap_chunks);
     }
+    MS_LAUNCH_CHECK();
+}
+void launch_gather(PolyDev& P, double sx, double sy, cudaStream_t st) {
+    const long long cap_chunks = chunk_capacity(P);
+    gather_kernel<<<(unsigned)cdiv64(cap_chunks * kChunk, 256), 256, 0, st>>>(P.chunks.as<int2>(), P.chunk_meta.as<int2>(), P.header.as<long long>(),
+                                                                             cap_chunks, P.npts.as<int>(), (int)P.cap_contours,
+                                                                             (long long)P.cap_points, sx, sy, P.xy.as<int2>());
     MS_LAUNCH_CHECK();
 }
 
@@ -708,7 +821,9 @@ void m2p_phase_a(M2pWs& ws, PolyDev& P, const uint8_t* d_mask, int h, int w, int
     P.start_slice.reserve((size_t)P.cap_contours * 4);
     P.npts.reserve(((size_t)P.cap_contours + 1) * 4);
     P.xy.reserve((size_t)P.cap_points * 8);
-    P.header.reserve(4 * sizeof(long long));
+    P.header.reserve(8 * sizeof(long long));
+    P.chunks.reserve((size_t)chunk_capacity(P) * kChunk * sizeof(int2));
+    P.chunk_meta.reserve((size_t)chunk_capacity(P) * sizeof(int2));
     int* Lfg = ws.fg.labels.as<int>();
     int* Lbg = ws.bg.labels.as<int>();
     uint8_t* flag = ws.bg.flag.as<uint8_t>();
@@ -743,7 +858,7 @@ void m2p_phase_a(M2pWs& ws, PolyDev& P, const uint8_t* d_mask, int h, int w, int
     MS_LAUNCH_CHECK();
     const TraceMode mode = pick_trace_mode(h, w, batch);
     if (mode == kTraceCrack) crack_count(ws, P, h, w, batch, st);
-    else launch_trace<false>(ws, P, mode, h, w, batch, 1.0, 1.0, st);
+    else launch_trace(ws, P, mode, h, w, batch, st);
     scan_points_kernel<<<1, 1024, 0, st>>>(P.npts.as<int>(), (int)P.cap_contours, header);
     MS_LAUNCH_CHECK();
 }
@@ -754,7 +869,7 @@ void m2p_phase_b(M2pWs& ws, PolyDev& P, int h, int w, int batch, int orig_w, int
     const double sy = static_cast<double>(orig_h) / h;
     const TraceMode mode = pick_trace_mode(h, w, batch);
     if (mode == kTraceCrack) crack_emit(ws, P, h, w, batch, sx, sy, st);
-    else launch_trace<true>(ws, P, mode, h, w, batch, sx, sy, st);
+    else launch_gather(P, sx, sy, st);
 }
 
 }  // namespace ms
