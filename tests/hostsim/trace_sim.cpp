@@ -22,15 +22,18 @@ struct UF {
 extern "C" int sim_find_contours(const uint8_t* mask, int H, int W, int thr, int32_t* xy, int64_t cap_pts,
                                  int32_t* cstart, int cap_c, int64_t* n_pts) {
     const size_t n = (size_t)H * W;
-    std::vector<uint8_t> fg(n), nb(n, 0);
+    std::vector<uint8_t> fg(n);
     for (size_t i = 0; i < n; ++i) fg[i] = mask[i] > thr;
     auto F = [&](int x, int y) { return x >= 0 && y >= 0 && x < W && y < H && fg[(size_t)y * W + x]; };
-    for (int y = 0; y < H; ++y)
-        for (int x = 0; x < W; ++x) {
-            unsigned c = 0;
-            for (int d = 0; d < 8; ++d) c |= (unsigned)F(x + ms::trace_dx(d), y + ms::trace_dy(d)) << d;
-            nb[(size_t)y * W + x] = (uint8_t)c;
-        }
+    // the step table exactly as a CTA builds it, and a raw 3x3 window source over the byte image
+    std::vector<uint16_t> lut(ms::kTraceLutEntries);
+    for (int i = 0; i < ms::kTraceLutEntries; ++i) lut[i] = ms::trace_lut_entry(i);
+    auto win9 = [&](int x, int y) {
+        unsigned w = 0;
+        for (int r = 0; r < 3; ++r)
+            for (int c = 0; c < 3; ++c) w |= (unsigned)F(x - 1 + c, y - 1 + r) << (3 * r + c);
+        return w;
+    };
     UF f8(n), b4(n);
     std::vector<uint8_t> outer(n, 0);
     for (int y = 0; y < H; ++y)
@@ -58,11 +61,13 @@ extern "C" int sim_find_contours(const uint8_t* mask, int H, int W, int thr, int
         int x = (int)(p % W);
         if (!(x == 0 || outer[b4.find((int)p - 1)])) continue;
         if (nout < cap_c) cstart[nout] = (int32_t)np;
-        int cnt = ms::trace_contour(nb.data(), W, (int)p, (int)(8 * n + 8), [&](int px, int py) {
+        auto emit = [&](int px, int py) {
             if (np < cap_pts) { xy[2 * np] = px; xy[2 * np + 1] = py; }
             ++np;
-        });
-        if (cnt < 0) return -1;
+        };
+        ms::TraceState st;
+        ms::trace_begin(st, W, (int)p);
+        if (ms::trace_run(win9, lut.data(), W, st, (int)(8 * n + 8), emit, ms::TraceAlwaysInside{}) != 1) return -1;
         ++nout;
     }
     if (nout <= cap_c) cstart[nout] = (int32_t)np;

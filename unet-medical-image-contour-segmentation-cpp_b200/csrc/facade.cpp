@@ -38,10 +38,6 @@ std::string file_name(const std::string& p) {
     const size_t s = p.find_last_of("/\\");
     return s == std::string::npos ? p : p.substr(s + 1);
 }
-std::string parent_dir(const std::string& p) {
-    const size_t s = p.find_last_of("/\\");
-    return s == std::string::npos ? std::string() : p.substr(0, s);
-}
 struct Csr {
     std::vector<int32_t> xy, cstart;
 };

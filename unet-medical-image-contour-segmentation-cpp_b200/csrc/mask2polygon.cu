@@ -8,10 +8,12 @@
 //   (2) external test: the pixel left of the start must belong to the 4-connected background
 //       component that reaches the image frame                       -> second ccl + border flag
 //   (3) contours ordered by descending start index                   -> count / scan / scatter
-//   (4)-(6) border following + CHAIN_APPROX_SIMPLE                   -> contour_trace.cuh, one
-//       thread per contour on the bit-packed foreground (a whole slice of it in shared memory when it
-//       fits), two passes (count, then emit at scanned offsets)
-//   (7) coordinate mapping (int)(x * (double)orig_w / w)             -> fused into the emit pass
+//   (4)-(6) contour ordering + CHAIN_APPROX_SIMPLE, three interchangeable bit-exact variants (MEDSEG_TRACE):
+//       smem   : one thread per contour follows the border (contour_trace.cuh) on the slice's bit image in shared
+//                memory, ONE walk: kept vertices -> 64-vertex chunks, counts -> scan -> parallel gather
+//       crack  : slices too large for shared memory: list ranking on directed pixel edges, nothing walks (below)
+//       window : fallback, the walk runs inside a re-centred 256 x 256 shared-memory window
+//   (7) coordinate mapping (int)(x * (double)orig_w / w)             -> fused into the gather / emit pass
 // No host round trip happens between these launches: all sizes live in `header` on the device, so
 // the whole stage is CUDA-graph capturable and only the caller decides when to synchronise.
 // The u8 mask is read once (-> one bit per pixel); labelling is the run-based union-find of ccl.cuh.
@@ -248,13 +250,6 @@ __global__ void __launch_bounds__(256) gather_kernel(const int2* __restrict__ tm
     if (k < offsets[m.x + 1] - base) xy[base + k] = map_point(tmp[idx], sx, sy);
 }
 
-// 8-neighbour foreground code of a pixel from bit-packed rows.  PADDED: `bits` has a zero word / zero row on every
-// side (shared-memory copy); otherwise bounds are checked (global memory, large slices).
-// Codes: 0=E 1=NE 2=N 3=NW 4=W 5=SW 6=S 7=SE ; bit0 of a 3-bit row window = x-1, bit1 = x, bit2 = x+1
-__device__ __forceinline__ unsigned code_from_rows(unsigned up, unsigned cu, unsigned dn) {
-    return ((cu >> 2) & 1u) | (((up >> 2) & 1u) << 1) | (((up >> 1) & 1u) << 2) | ((up & 1u) << 3) | ((cu & 1u) << 4) |
-           ((dn & 1u) << 5) | (((dn >> 1) & 1u) << 6) | (((dn >> 2) & 1u) << 7);
-}
 // 3x3 window of a pixel as 9 raw bits: up3 | cu3 << 3 | dn3 << 6, bit 0 of each triple = x - 1
 struct PaddedBitsWindow {
     const uint32_t* bits;   // (H + 2) rows x pitch words, row 0 / word 0 are the zero frame
@@ -266,71 +261,8 @@ struct PaddedBitsWindow {
                ((__funnelshift_r(r[2 * pitch], r[2 * pitch + 1], sh) & 7u) << 6);
     }
 };
-__device__ __forceinline__ unsigned code_from_window(unsigned w9) { return code_from_rows(w9 & 7u, (w9 >> 3) & 7u, (w9 >> 6) & 7u); }
-
-// One border-following step is a dependent chain (position -> window -> next direction -> position), so its depth is
-// the walking speed.  The chain "assemble the direction-indexed code, rotate by d_prev, find first set, look up dx/dy"
-// is replaced by ONE shared-memory lookup indexed by {d_prev, raw 3x3 window}: 4096 entries of
-//   bits 0-2 d_out | bits 3-4 dx + 1 | bits 5-6 dy + 1 | bits 7-9 next d_prev = d_out + 4
-constexpr int kLutEntries = 8 * 512;
-__device__ void build_trace_lut(uint16_t* lut) {
-    for (int i = threadIdx.x; i < kLutEntries; i += blockDim.x) {
-        const unsigned cc = code_from_window(i & 511), dp = i >> 9;
-        unsigned e = 0;
-        if (cc) {
-            const unsigned rot = ((cc | (cc << 8)) >> ((dp + 1) & 7)) & 0xFFu;
-            const int d = (int)(dp + 1 + (__ffs((int)rot) - 1)) & 7;
-            e = (unsigned)d | ((unsigned)(trace_dx(d) + 1) << 3) | ((unsigned)(trace_dy(d) + 1) << 5) | ((unsigned)((d + 4) & 7) << 7);
-        }
-        lut[i] = (uint16_t)e;
-    }
-}
-// trace_run (contour_trace.cuh) with the step taken from the table; same state, same results
-template <class Window, class Inside>
-__device__ __forceinline__ int trace_run_lut(Window win9, const uint16_t* __restrict__ lut, int W, TraceState& s, int max_steps,
-                                             ChunkEmit& emit, Inside inside) {
-    if (s.phase == 2) return 1;
-    if (s.phase == 0) {
-        if (!inside(s.x, s.y)) return 0;
-        const unsigned c0 = code_from_window(win9(s.x, s.y));
-        if (c0 == 0) {  // isolated pixel
-            emit(s.x, s.y);
-            s.n = 1;
-            s.phase = 2;
-            return 1;
-        }
-        unsigned rev = 0;   // probe NW, N, NE, E, SE, S, SW, W: bit k <-> direction (3 - k) & 7
-#pragma unroll
-        for (int k = 0; k < 8; ++k) rev |= ((c0 >> ((3 - k) & 7)) & 1u) << k;
-        const int dL = (3 - (__ffs((int)rev) - 1)) & 7;
-        s.last = s.start + trace_dy(dL) * W + trace_dx(dL);
-        s.d_prev = dL;
-        s.prev_out = (dL + 4) & 7;
-        s.phase = 1;
-    }
-    int x = s.x, y = s.y, p = s.p, prev_out = s.prev_out, n = s.n;
-    unsigned dp9 = (unsigned)s.d_prev << 9;
-    int status = -1;
-    for (int step = 0; step < max_steps; ++step) {
-        if (!inside(x, y)) { status = 0; break; }
-        const unsigned e = lut[dp9 | win9(x, y)];
-        const int d = e & 7;
-        if (d != prev_out) {
-            emit(x, y);
-            ++n;
-            prev_out = d;
-        }
-        const int ddx = (int)((e >> 3) & 3u) - 1, ddy = (int)((e >> 5) & 3u) - 1;
-        const int q = p + ddy * W + ddx;
-        if (q == s.start && p == s.last) { status = 1; break; }
-        p = q;
-        x += ddx;
-        y += ddy;
-        dp9 = (e << 2) & (7u << 9);
-    }
-    s.x = x; s.y = y; s.p = p; s.prev_out = prev_out; s.n = n; s.d_prev = (int)(dp9 >> 9);
-    if (status == 1) s.phase = 2;
-    return status;
+__device__ void build_trace_lut(uint16_t* lut) {   // contour_trace.cuh: the step table, one copy per CTA
+    for (int i = threadIdx.x; i < kTraceLutEntries; i += blockDim.x) lut[i] = trace_lut_entry(i);
 }
 // Large slices (the bit image does not fit in shared memory): one CTA per contour keeps a 256 x 256-pixel WINDOW of the
 // bit image in shared memory, centred on the walk; thread 0 follows the border (six LDS per step) until it leaves the
@@ -360,7 +292,7 @@ __global__ void __launch_bounds__(64) trace_window_kernel(const uint32_t* __rest
                                                            long long* __restrict__ header, int cap_contours, int* __restrict__ npts,
                                                            int2* __restrict__ chunk_tmp, int2* __restrict__ chunk_meta, long long cap_chunks) {
     __shared__ uint32_t win[kWinH * kWinPitch];
-    __shared__ uint16_t lut[kLutEntries];
+    __shared__ uint16_t lut[kTraceLutEntries];
     build_trace_lut(lut);
     __shared__ int s_org[2], s_status;
     const int c = blockIdx.x;
@@ -386,7 +318,7 @@ __global__ void __launch_bounds__(64) trace_window_kernel(const uint32_t* __rest
         if (threadIdx.x == 0) {
             const WindowBits bits{win, x0, y0};
             const WindowInside inside{x0, y0};
-            s_status = trace_run_lut(bits, lut, W, st, 8 * H * W + 8, emit, inside);
+            s_status = trace_run(bits, lut, W, st, 8 * H * W + 8, emit, inside);
         }
         __syncthreads();
         if (s_status != 0) break;
@@ -405,7 +337,7 @@ __global__ void __launch_bounds__(128) trace_smem_kernel(const uint32_t* __restr
                                                           long long* __restrict__ header, int cap_contours, int* __restrict__ npts,
                                                           int2* __restrict__ chunk_tmp, int2* __restrict__ chunk_meta, long long cap_chunks) {
     extern __shared__ uint32_t sbits[];
-    __shared__ uint16_t lut[kLutEntries];
+    __shared__ uint16_t lut[kTraceLutEntries];
     const int b = blockIdx.x;
     const int pitch = wpitch + 2;
     const int c_lo = slice_start[b], c_hi = min(slice_start[b + 1], cap_contours);
@@ -421,7 +353,7 @@ __global__ void __launch_bounds__(128) trace_smem_kernel(const uint32_t* __restr
         TraceState ts;
         trace_begin(ts, W, starts[c]);
         ChunkEmit emit{chunk_tmp, chunk_meta, (unsigned long long*)&header[4], cap_chunks, c, 0, nullptr};
-        const int cnt = trace_run_lut(bits, lut, W, ts, 8 * H * W + 8, emit, TraceAlwaysInside{}) == 1 ? ts.n : -1;
+        const int cnt = trace_run(bits, lut, W, ts, 8 * H * W + 8, emit, TraceAlwaysInside{}) == 1 ? ts.n : -1;
         if (cnt < 0) atomicAdd((unsigned long long*)&header[3], 1ull);
         npts[c] = cnt < 0 ? 0 : cnt;
     }
