@@ -49,6 +49,7 @@ __device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
 
 constexpr int kFirstRows = 8;   // image rows per block: the weights-to-registers prologue and the halo rows are amortised
 
+template <bool VEC16>
 __global__ void __launch_bounds__(256) first_conv_kernel(const uint8_t* __restrict__ in, int H, int W,
                                                           const float* __restrict__ w /*[64][9]*/, const float* __restrict__ bias,
                                                           __nv_bfloat16* __restrict__ out /*NHWC 64*/) {
@@ -59,10 +60,27 @@ __global__ void __launch_bounds__(256) first_conv_kernel(const uint8_t* __restri
     const size_t img = (size_t)(blockIdx.x / blocks_per_img) * H * W;
     const int pitch = W + 2;
     for (int i = threadIdx.x; i < 64 * 9 + 64; i += 256) sw[i] = i < 576 ? w[i] : bias[i - 576];
-    for (int i = threadIdx.x; i < (kFirstRows + 2) * pitch; i += 256) {
-        const int r = i / pitch, c = i % pitch;
-        const int yy = y0 + r - 1, xx = c - 1;
-        srow[i] = (yy >= 0 && yy < H && xx >= 0 && xx < W) ? __fdiv_rn((float)in[img + (size_t)yy * W + xx], 255.0f) : 0.0f;
+    if (VEC16) {
+        // 16 pixels per load, all of a thread's loads in flight together (the scalar form below spends a fifth of the
+        // kernel waiting on dependent byte loads: profiles/r1_ncu_full_forward_b32.json, enc1a)
+        const int cpr = W / 16;
+        for (int i = threadIdx.x; i < (kFirstRows + 2) * cpr; i += 256) {
+            const int r = i / cpr, c = i - r * cpr;
+            const int yy = y0 + r - 1;
+            uint4 v = make_uint4(0u, 0u, 0u, 0u);
+            if (yy >= 0 && yy < H) v = __ldg(reinterpret_cast<const uint4*>(in + img + (size_t)yy * W) + c);
+            float* dst = srow + r * pitch + 1 + c * 16;
+            const uint32_t wds[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int j = 0; j < 16; ++j) dst[j] = __fdiv_rn((float)((wds[j >> 2] >> (8 * (j & 3))) & 0xFFu), 255.0f);   // src/process.cpp:33
+        }
+        for (int r = threadIdx.x; r < kFirstRows + 2; r += 256) srow[r * pitch] = srow[r * pitch + W + 1] = 0.0f;
+    } else {
+        for (int i = threadIdx.x; i < (kFirstRows + 2) * pitch; i += 256) {
+            const int r = i / pitch, c = i % pitch;
+            const int yy = y0 + r - 1, xx = c - 1;
+            srow[i] = (yy >= 0 && yy < H && xx >= 0 && xx < W) ? __fdiv_rn((float)in[img + (size_t)yy * W + xx], 255.0f) : 0.0f;
+        }
     }
     __syncthreads();
     const int cg = (threadIdx.x & 7) * 8, g = threadIdx.x >> 3;
@@ -538,7 +556,12 @@ void UNet::run_layer(int li, const uint8_t* d_in_u8, int batch, uint8_t* d_mask,
     const UNetLayer& L = layers_[li];
     const int h = H_ >> L.level, w = W_ >> L.level;
     if (L.kind == 0) {
-        first_conv_kernel<<<(unsigned)(batch * h / kFirstRows), 256, (kFirstRows + 2) * (w + 2) * sizeof(float), st>>>(d_in_u8, h, w, L.w_f32, L.bias, bufs_[L.dst].p);
+        const unsigned grid = (unsigned)(batch * h / kFirstRows);
+        const size_t smem = (kFirstRows + 2) * (w + 2) * sizeof(float);
+        if (w % 16 == 0 && (reinterpret_cast<uintptr_t>(d_in_u8) & 15) == 0)
+            first_conv_kernel<true><<<grid, 256, smem, st>>>(d_in_u8, h, w, L.w_f32, L.bias, bufs_[L.dst].p);
+        else
+            first_conv_kernel<false><<<grid, 256, smem, st>>>(d_in_u8, h, w, L.w_f32, L.bias, bufs_[L.dst].p);
         MS_LAUNCH_CHECK();
         return;
     }
