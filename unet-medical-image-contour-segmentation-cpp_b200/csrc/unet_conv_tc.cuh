@@ -159,6 +159,11 @@ __device__ __forceinline__ void tma_store_5d(const CUtensorMap* map, uint32_t sr
 __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ uint4 ld_shared_v4(uint32_t addr) {
+    uint4 v;
+    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+    return v;
+}
 __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
     asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
@@ -339,18 +344,27 @@ __device__ __forceinline__ void epilogue_tile(const ConvArgs& args, const float*
                 tma_store_commit();
             }
             if (EPI == EPI_STORE && args.pool) {
-                // 2x2 max-pool inside the warp: lanes l, l^1 (x pair), l^TW (y pair)
+                // 2x2 max-pool out of the staged slab (the TMA store only reads it): the slab holds 32 px x 64 ch, i.e.
+                // 8 pooled pixels x 8 sixteen-byte channel chunks = 64 work items, two per lane.  Item (q, j): max over
+                // the rows (= pixels) l0, l0+1, l0+TW, l0+TW+1 of chunk j, which the 128-byte swizzle put at chunk
+                // position j ^ (row & 7).  Lanes 4q .. 4q+3 write pooled pixel q's 128 bytes contiguously.
+                // (The earlier form exchanged the 32 packed registers with two shuffles each: 4 warps x 128 SHFL per tile
+                // made the epilogue, not the MMA, the bound of enc2b.)
+                const int q = e.lane >> 2;
+                const int l0 = (q % (TW / 2)) * 2 + (q / (TW / 2)) * 2 * TW;
+                const int px = e.x0 + (l0 % TW), py = e.y0 + e.slab_y + (l0 / TW);
+                uint4* dst = reinterpret_cast<uint4*>(args.pool + (((size_t)e.b * (args.H / 2) + (py >> 1)) * (args.W / 2) + (px >> 1)) * args.pool_cstride + col);
 #pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    uint32_t v = pk[j];
-                    v = max_bf16x2(v, __shfl_xor_sync(0xFFFFFFFFu, v, 1));
-                    v = max_bf16x2(v, __shfl_xor_sync(0xFFFFFFFFu, v, TW));
-                    pk[j] = v;
-                }
-                if ((e.lane & (TW | 1)) == 0) {
-                    uint4* p4 = reinterpret_cast<uint4*>(args.pool + (((size_t)e.b * (args.H / 2) + (e.y >> 1)) * (args.W / 2) + (e.x >> 1)) * args.pool_cstride + col);
+                for (int it = 0; it < 2; ++it) {
+                    const int j = (e.lane & 3) * 2 + it;
+                    uint4 m = make_uint4(0u, 0u, 0u, 0u);   // post-ReLU values are >= +0
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) p4[j] = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+                    for (int k = 0; k < 4; ++k) {
+                        const int row = l0 + (k & 1) + (k >> 1) * TW;
+                        const uint4 v = ld_shared_v4(e.slab + (uint32_t)row * 128u + (uint32_t)((j ^ (row & 7)) << 4));
+                        m.x = max_bf16x2(m.x, v.x); m.y = max_bf16x2(m.y, v.y); m.z = max_bf16x2(m.z, v.z); m.w = max_bf16x2(m.w, v.w);
+                    }
+                    dst[j] = m;
                 }
             }
         }
