@@ -146,7 +146,7 @@ def test_mask2polygon_stress_2048(stage_engine, ms, kind):
     assert contours_equal(got, want)
 
 
-@pytest.mark.parametrize("variant", ["smem", "window", "crack"])
+@pytest.mark.parametrize("variant", ["rank", "smem", "window", "crack"])
 def test_mask2polygon_trace_variants(stage_engine, ms, monkeypatch, variant):
     """The three contour-ordering kernels (whole slice in shared memory, 256 x 256 window walk, crack list ranking)
     are interchangeable: same golden / random / ragged cases, bit-exact, whichever one MEDSEG_TRACE forces."""

@@ -34,8 +34,8 @@ def main():
         for i in range(b):
             cv2.findContours(m[i], cv2.RETR_EXTERNAL, cv2.CHAIN_APPROX_SIMPLE)
         row = {"case": name, "shape": [b, h, w], "cv2_ms": (time.perf_counter() - t0) * 1e3}
-        for variant in ("smem", "window", "crack"):
-            if variant == "smem" and h > 1024:
+        for variant in ("rank", "smem", "window", "crack"):
+            if variant in ("smem", "rank") and h > 1024:
                 continue
             os.environ["MEDSEG_TRACE"] = variant
             polys = eng.mask2polygon_dev(d.data_ptr(), h, w, b, 127, st)

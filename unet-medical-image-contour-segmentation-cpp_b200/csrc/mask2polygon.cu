@@ -8,7 +8,8 @@
 //   (2) external test: the pixel left of the start must belong to the 4-connected background
 //       component that reaches the image frame                       -> second ccl + border flag
 //   (3) contours ordered by descending start index                   -> count / scan / scatter
-//   (4)-(6) contour ordering + CHAIN_APPROX_SIMPLE, three interchangeable bit-exact variants (MEDSEG_TRACE):
+//   (4)-(6) contour ordering + CHAIN_APPROX_SIMPLE, four interchangeable bit-exact variants (MEDSEG_TRACE):
+//       rank   : (default when the slice fits in shared memory) one CTA per slice ranks the border cracks on chip
 //       smem   : one thread per contour follows the border (contour_trace.cuh) on the slice's bit image in shared
 //                memory, ONE walk: kept vertices -> 64-vertex chunks, counts -> scan -> parallel gather
 //       crack  : slices too large for shared memory: list ranking on directed pixel edges, nothing walks (below)
@@ -612,6 +613,278 @@ __global__ void __launch_bounds__(1024) pos_emit_kernel(const uint32_t* __restri
 
 }  // namespace crack
 
+// ---------------------------------------------------------------------------------------------------------------------
+// The same list ranking for slices whose bit image fits in shared memory (the pipeline's case): ONE CTA per slice does
+// everything on chip -- bits, crack table, pointer jumping, CHAIN_APPROX_SIMPLE flags, prefix sums -- and hands the kept
+// vertices to the chunk store that gather_kernel reads.  A CT-like slice has one to three borders of ~1,500 pixels; walking
+// them costs ~170 ns per step with one thread busy per border (0.24 ms per batch), ranking them takes ~12 rounds over a few
+// thousand table entries with 1,024 threads.
+// Crack slots are indexed by border pixel: slot = (rank of the pixel among the slice's border pixels) * 4 + side, the
+// pixel's rank = pix_off[word] + popc(border bits below it).  A slot is 32 bits, {next : 16, rank : 16}; next >= kMark
+// is a marker: kInvalidNext (side not open) or kMark + contour (list end).  A slice with more border pixels than the
+// table holds (or > 16 k contours) is walked sequentially by this same kernel, exactly as trace_smem_kernel does.
+namespace srank {
+
+constexpr uint32_t kMark = 0xC000u, kInvalidNext = 0xFFFFu;
+constexpr int kMaxBorder = kMark / 4;            // slot ids stay below kMark
+constexpr int kBytesPerBorder = 16 + 16 + 4;     // slots (later: prefix sums), positions, pixel index
+constexpr int kInfo = 6;                         // per-contour scratch arrays in global memory
+__device__ __forceinline__ uint32_t pack(uint32_t next, uint32_t rank) { return (rank << 16) | (next & 0xFFFFu); }
+__device__ __forceinline__ uint32_t next_of(uint32_t v) { return v & 0xFFFFu; }
+__device__ __forceinline__ uint32_t rank_of(uint32_t v) { return v >> 16; }
+
+// 34-bit row windows of word (y, wx) out of the zero-framed shared-memory copy (row y+1, word wx+1)
+__device__ __forceinline__ crack::Nbhd nbhd(const uint32_t* sb, int P, int y, int wx) {
+    auto window = [&](int ry) -> crack::u64 {
+        const uint32_t* r = sb + ry * P + wx;
+        return (crack::u64)(r[0] >> 31) | ((crack::u64)r[1] << 1) | ((crack::u64)(r[2] & 1u) << 33);
+    };
+    crack::Nbhd n;
+    n.cu = window(y + 1);
+    n.up = n.dn = 0;
+    n.border = 0;
+    const uint32_t fg = (uint32_t)(n.cu >> 1);
+    if (fg == 0) return n;
+    n.up = window(y);
+    n.dn = window(y + 2);
+    n.border = fg & ~((uint32_t)(n.up >> 1) & (uint32_t)(n.dn >> 1) & (uint32_t)n.cu & (uint32_t)(n.cu >> 2));
+    return n;
+}
+struct Table {
+    const uint32_t* sb;
+    const uint16_t* pix_off;
+    int P, wpitch;
+    // slot of side s of border pixel (x, y)
+    __device__ __forceinline__ uint32_t slot(int x, int y, int s) const {
+        const int wx = x >> 5;
+        const crack::Nbhd n = nbhd(sb, P, y, wx);
+        return ((uint32_t)pix_off[y * wpitch + wx] + (uint32_t)__popc(n.border & ((1u << (x & 31)) - 1u))) * 4u + (uint32_t)s;
+    }
+    __device__ __forceinline__ unsigned code(int x, int y) const { return crack::code_at(nbhd(sb, P, y, x >> 5), x & 31); }
+};
+
+__global__ void __launch_bounds__(1024) rank_smem_kernel(const uint32_t* __restrict__ fgbits, int H, int W, int wpitch,
+                                                          const int* __restrict__ starts, const int* __restrict__ slice_start,
+                                                          long long* __restrict__ header, int cap_contours, int* __restrict__ npts,
+                                                          int2* __restrict__ chunk_tmp, int2* __restrict__ chunk_meta, long long cap_chunks,
+                                                          int* __restrict__ cinfo, int cap_border) {
+    extern __shared__ uint32_t smem[];
+    __shared__ uint16_t lut[kTraceLutEntries];   // only the sequential fallback uses it
+    const int tid = threadIdx.x, b = blockIdx.x;
+    const int P = wpitch + 2, nwords = H * wpitch;
+    const int c_lo = slice_start[b], c_hi = min(slice_start[b + 1], cap_contours);
+    if (c_lo >= c_hi) return;
+    uint32_t* sbits = smem;
+    uint16_t* pix_off = reinterpret_cast<uint16_t*>(sbits + (H + 2) * P);
+    uint32_t* slots = reinterpret_cast<uint32_t*>(pix_off + ((nwords + 1) & ~1));   // [4 * cap_border + 1]
+    uint32_t* pos = slots + 4 * cap_border + 1;                                     // [4 * cap_border]
+    uint32_t* slot_px = pos + 4 * cap_border;                                       // [cap_border]
+    // per-contour scratch (global, indexed by contour): position base, rotation, start slot, border length, first chunk, vertex base
+    int* c_base = cinfo;
+    int* c_rot = cinfo + (size_t)(cap_contours + 1);
+    int* c_slot = cinfo + 2 * (size_t)(cap_contours + 1);
+    int* c_len = cinfo + 3 * (size_t)(cap_contours + 1);
+    int* c_chunk = cinfo + 4 * (size_t)(cap_contours + 1);
+    int* c_vbase = cinfo + 5 * (size_t)(cap_contours + 1);
+
+    for (int i = tid; i < (H + 2) * P; i += 1024) {
+        const int r = i / P, c = i % P;
+        sbits[i] = (r >= 1 && r <= H && c >= 1 && c <= wpitch) ? fgbits[((size_t)b * H + (r - 1)) * wpitch + (c - 1)] : 0u;
+    }
+    __syncthreads();
+
+    // ---- border pixels per word -> exclusive offsets
+    int n_border = 0;
+    for (int base = 0; base < nwords; base += 1024) {
+        const int w = base + tid;
+        int cnt = 0;
+        if (w < nwords) cnt = __popc(nbhd(sbits, P, w / wpitch, w % wpitch).border);
+        int tot;
+        const int ex = block_exscan_1024(cnt, &tot);
+        if (w < nwords) pix_off[w] = (uint16_t)min(n_border + ex, 0xFFFF);
+        n_border += tot;
+    }
+    if (n_border > cap_border || c_hi - c_lo >= (int)(kInvalidNext - kMark)) {
+        // ---- does not fit the table: one thread per contour walks its border (contour_trace.cuh)
+        build_trace_lut(lut);
+        __syncthreads();
+        const PaddedBitsWindow bits{sbits, P};
+        for (int c = c_lo + tid; c < c_hi; c += 1024) {
+            TraceState ts;
+            trace_begin(ts, W, starts[c]);
+            ChunkEmit emit{chunk_tmp, chunk_meta, (unsigned long long*)&header[4], cap_chunks, c, 0, nullptr};
+            const int cnt = trace_run(bits, lut, W, ts, 8 * H * W + 8, emit, TraceAlwaysInside{}) == 1 ? ts.n : -1;
+            if (cnt < 0) atomicAdd((unsigned long long*)&header[3], 1ull);
+            npts[c] = cnt < 0 ? 0 : cnt;
+        }
+        return;
+    }
+    __syncthreads();
+    const Table T{sbits, pix_off, P, wpitch};
+    const int n_slots = 4 * n_border;
+
+    // ---- init: every open side points at its successor
+    for (int w = tid; w < nwords; w += 1024) {
+        const int y = w / wpitch, wx = w - y * wpitch;
+        const crack::Nbhd n = nbhd(sbits, P, y, wx);
+        uint32_t m = n.border;
+        uint32_t idx = pix_off[w];
+        while (m) {
+            const int j = __ffs((int)m) - 1;
+            m &= m - 1;
+            const unsigned code = crack::code_at(n, j);
+            const int x = wx * 32 + j;
+            slot_px[idx] = (uint32_t)(y * W + x);
+#pragma unroll
+            for (int sd = 0; sd < 4; ++sd) {
+                uint32_t v = pack(kInvalidNext, 0);
+                if (crack::side_open(code, sd)) {
+                    uint32_t nx;   // crack::succ, resolved to a slot
+                    if (crack::has(code, 5 + 2 * sd)) nx = T.slot(x + trace_dx((5 + 2 * sd) & 7), y + trace_dy((5 + 2 * sd) & 7), (sd + 3) & 3);
+                    else if (crack::has(code, 6 + 2 * sd)) nx = T.slot(x + trace_dx((6 + 2 * sd) & 7), y + trace_dy((6 + 2 * sd) & 7), sd);
+                    else nx = idx * 4u + (uint32_t)((sd + 1) & 3);
+                    v = pack(nx, 1);
+                }
+                slots[idx * 4 + sd] = v;
+            }
+            ++idx;
+        }
+    }
+    __syncthreads();
+
+    // ---- cut: the predecessor of each contour's start crack ends the list and names the contour
+    for (int c = c_lo + tid; c < c_hi; c += 1024) {
+        const int p = starts[c], x = p % W, y = p / W;
+        const unsigned code = T.code(x, y);
+        int back = 0, sd = 0;
+        while (back < 3 && crack::pred_dir(code, sd) < 0) {
+            sd = (sd + 3) & 3;
+            ++back;
+        }
+        c_rot[c] = back;
+        const uint32_t s0 = T.slot(x, y, 0);
+        c_slot[c] = (int)s0;
+        uint32_t pr;       // crack::pred of (p, side 0)
+        if (crack::has(code, 3)) pr = T.slot(x - 1, y - 1, 1);
+        else if (crack::has(code, 2)) pr = T.slot(x, y - 1, 0);
+        else pr = (s0 & ~3u) | 3u;
+        slots[pr] = pack(kMark + (uint32_t)(c - c_lo), 1);
+    }
+    __syncthreads();
+
+    // ---- pointer jumping (in place: every observable {next, rank} is a true statement); a border of length L is done once
+    //      its start crack is ranked and 2^rounds >= L
+    for (int round = 0; round < 20; ++round) {
+        for (int i = tid; i < n_slots; i += 1024) {
+            const uint32_t v = slots[i];
+            const uint32_t nx = next_of(v);
+            if (nx < kMark) {
+                const uint32_t t = slots[nx];
+                slots[i] = pack(next_of(t), rank_of(v) + rank_of(t));
+            }
+        }
+        __syncthreads();
+        int busy = 0;
+        for (int c = c_lo + tid; c < c_hi; c += 1024) {
+            const uint32_t t = slots[c_slot[c]];
+            if (next_of(t) < kMark || rank_of(t) > (1u << (round + 1))) busy = 1;
+        }
+        if (!__syncthreads_or(busy)) break;
+    }
+
+    // ---- border lengths -> position bases
+    int n_pos = 0;
+    for (int base = 0; base < c_hi - c_lo; base += 1024) {
+        const int c = c_lo + base + tid;
+        int len = 0;
+        if (c < c_hi) {
+            const uint32_t t = slots[c_slot[c]];
+            if (next_of(t) == kMark + (uint32_t)(c - c_lo)) len = (int)rank_of(t);
+            else atomicAdd((unsigned long long*)&header[3], 1ull);   // unranked border: cannot happen
+            c_len[c] = len;
+        }
+        int tot;
+        const int ex = block_exscan_1024(len, &tot);
+        if (c < c_hi) c_base[c] = n_pos + ex;
+        n_pos += tot;
+    }
+    __syncthreads();
+
+    // ---- flags: position of every crack of an external border; the first crack of a pixel visit decides CHAIN_APPROX_SIMPLE
+    for (int i = tid; i < n_slots; i += 1024) {
+        const uint32_t v = slots[i];
+        const uint32_t nx = next_of(v);
+        if (nx < kMark || nx == kInvalidNext) continue;       // hole border / border of a non-external component / closed side
+        const int c = c_lo + (int)(nx - kMark);
+        const int len = c_len[c];
+        int ps = len - (int)rank_of(v) + c_rot[c];
+        if (ps >= len) ps -= len;
+        const int p = (int)slot_px[i >> 2], sd = i & 3;
+        const unsigned code = T.code(p % W, p / W);
+        bool kept = false;
+        const int pd = crack::pred_dir(code, sd);
+        if (pd >= 0) {
+            const int d_prev = (pd + 4) & 7;
+            int d_out = -1;
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+                const int ss = (sd + t) & 3;
+                if (d_out < 0 && crack::has(code, 5 + 2 * ss)) d_out = (5 + 2 * ss) & 7;
+                if (d_out < 0 && crack::has(code, 6 + 2 * ss)) d_out = (6 + 2 * ss) & 7;
+            }
+            kept = d_out != d_prev;
+        } else if (code == 0 && sd == 0) {
+            kept = true;
+        }
+        pos[c_base[c] + ps] = (uint32_t)p | (kept ? crack::kKept : 0u);
+    }
+    __syncthreads();
+
+    // ---- kept-vertex prefix over positions (reuses the slot table's memory)
+    uint32_t* prefix = slots;
+    int n_kept = 0;
+    for (int base = 0; base < n_pos; base += 1024) {
+        const int i = base + tid;
+        const int k = (i < n_pos && (pos[i] & crack::kKept)) ? 1 : 0;
+        int tot;
+        const int ex = block_exscan_1024(k, &tot);
+        if (i < n_pos) prefix[i] = (uint32_t)(n_kept + ex);
+        n_kept += tot;
+    }
+    if (tid == 0) prefix[n_pos] = (uint32_t)n_kept;
+    __syncthreads();
+
+    // ---- per contour: vertex count, chunks
+    for (int c = c_lo + tid; c < c_hi; c += 1024) {
+        const int k0 = (int)prefix[c_base[c]], n = (int)prefix[c_base[c] + c_len[c]] - k0;
+        npts[c] = n;
+        const int m = (n + kChunk - 1) / kChunk;
+        const unsigned long long j0 = atomicAdd((unsigned long long*)&header[4], (unsigned long long)m);
+        for (int q = 0; q < m; ++q)
+            if ((long long)(j0 + q) < cap_chunks) chunk_meta[j0 + q] = make_int2(c, q);
+        c_chunk[c] = (int)min(j0, (unsigned long long)0x7FFFFFFF);
+        c_vbase[c] = k0;
+    }
+    __syncthreads();
+
+    // ---- emit kept vertices into their chunks, in position order
+    for (int i = tid; i < n_pos; i += 1024) {
+        const uint32_t e = pos[i];
+        if (!(e & crack::kKept)) continue;
+        int lo = c_lo, hi = c_hi - 1;                          // last contour whose base is <= i
+        while (lo < hi) {
+            const int mid = (lo + hi + 1) >> 1;
+            if (c_base[mid] <= i) lo = mid; else hi = mid - 1;
+        }
+        const int k = (int)prefix[i] - c_vbase[lo];
+        const long long j = (long long)c_chunk[lo] + k / kChunk;
+        const int p = (int)(e & ~crack::kKept);
+        if (j < cap_chunks) chunk_tmp[j * kChunk + (k % kChunk)] = make_int2(p % W, p / W);
+    }
+}
+
+}  // namespace srank
+
 // 1 block of 1024: in-place exclusive scan of npts[0..n) ; npts[n] = header[1] = total
 __global__ void __launch_bounds__(1024) scan_points_kernel(int* __restrict__ npts, int cap_contours, long long* __restrict__ header) {
     const long long n64 = header[0];
@@ -633,9 +906,18 @@ __global__ void __launch_bounds__(1024) scan_points_kernel(int* __restrict__ npt
     }
 }
 
-enum TraceMode { kTraceSmem = 0, kTraceWindow = 1, kTraceCrack = 2 };
+enum TraceMode { kTraceSmem = 0, kTraceWindow = 1, kTraceCrack = 2, kTraceRank = 3 };
 
-// MEDSEG_TRACE = smem | window | crack forces a variant (tests exercise all three on the same masks)
+constexpr size_t kRankSmemMax = 218 * 1024;   // rank_smem_kernel: bits + offsets + tables (8 KiB static step table on top)
+// border pixels the in-shared-memory crack table can hold for an h x w slice (0: does not fit at all)
+int rank_border_capacity(int h, int w) {
+    const int wpitch = cdiv(w, 32);
+    const int64_t fixed = (int64_t)(h + 2) * (wpitch + 2) * 4 + (((int64_t)h * wpitch + 1) & ~1) * 2 + 16;
+    const int64_t cap = ((int64_t)kRankSmemMax - fixed) / srank::kBytesPerBorder;
+    return (int)std::max<int64_t>(0, std::min<int64_t>(cap, srank::kMaxBorder));
+}
+
+// MEDSEG_TRACE = rank | smem | window | crack forces a variant (tests exercise all of them on the same masks)
 TraceMode pick_trace_mode(int h, int w, int batch) {
     const int wpitch = cdiv(w, 32);
     const size_t trace_smem = (size_t)(h + 2) * (wpitch + 2) * 4;
@@ -645,8 +927,9 @@ TraceMode pick_trace_mode(int h, int w, int batch) {
         if (!std::strcmp(e, "window")) return kTraceWindow;
         if (!std::strcmp(e, "crack") && crack_ok) return kTraceCrack;
         if (!std::strcmp(e, "smem") && smem_ok) return kTraceSmem;
+        if (!std::strcmp(e, "rank") && smem_ok && rank_border_capacity(h, w) > 0) return kTraceRank;
     }
-    if (smem_ok) return kTraceSmem;
+    if (smem_ok) return rank_border_capacity(h, w) >= 1024 ? kTraceRank : kTraceSmem;
     return crack_ok ? kTraceCrack : kTraceWindow;
 }
 
@@ -656,7 +939,20 @@ void launch_trace(M2pWs& ws, PolyDev& P, TraceMode mode, int h, int w, int batch
     const size_t trace_smem = (size_t)(h + 2) * (wpitch + 2) * 4;
     long long* header = P.header.as<long long>();
     const long long cap_chunks = chunk_capacity(P);
-    if (mode == kTraceSmem) {
+    if (mode == kTraceRank) {
+        static bool attr = false;
+        if (!attr) {
+            MS_CUDA(cudaFuncSetAttribute(srank::rank_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kRankSmemMax));
+            attr = true;
+        }
+        const int cap_border = rank_border_capacity(h, w);
+        const size_t smem = (size_t)(h + 2) * (wpitch + 2) * 4 + (((size_t)h * wpitch + 1) & ~(size_t)1) * 2 + 16 +
+                            (size_t)cap_border * srank::kBytesPerBorder;
+        ws.crack_contour.reserve(((size_t)P.cap_contours + 1) * srank::kInfo * sizeof(int));
+        srank::rank_smem_kernel<<<batch, 1024, smem, st>>>(ws.fgbits.as<uint32_t>(), h, w, wpitch, P.starts.as<int>(), P.slice_start.as<int>(),
+                                                          header, (int)P.cap_contours, P.npts.as<int>(), P.chunks.as<int2>(),
+                                                          P.chunk_meta.as<int2>(), cap_chunks, ws.crack_contour.as<int>(), cap_border);
+    } else if (mode == kTraceSmem) {
         static bool attr = false;
         if (!attr) {
             MS_CUDA(cudaFuncSetAttribute(trace_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTraceSmemMax));
