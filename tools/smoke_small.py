@@ -1,7 +1,7 @@
 """Small smoke workload (seconds): every stage kernel, all four contour-ordering variants,
 one UNet forward at batch 1, the batched file path.
 
-    python tools/sanitize_small.py
+    python tools/smoke_small.py
 """
 import os
 import sys
