@@ -58,3 +58,33 @@ def test_cfg4_1024_four_labels_per_class_contours(ms, tmp_path):
         n_found += len(ref)
     assert n_found >= 1
     eng.cleanup()
+
+
+@pytest.mark.parametrize("net_h,net_w", [(128, 256), (256, 512), (384, 256)])
+def test_other_net_sizes_whole_path(ms, tmp_path, net_h, net_w):
+    """Configurable network size (multiples of 128 x 256): the smallest net has ONE 8 x 16 tile at
+    the bottleneck, non-square nets exercise the tile decomposition; logits vs the fp32 oracle, then the integer stages
+    bit-exact on the kernel's own mask, with a resample from a different raw size."""
+    from medseg_b200 import synth, weights as W
+    from oracle.unet_torch import load_unet, unet_logits
+    blob = ms.make_weight_blob(str(tmp_path / "u.msegw"), n_classes=3, seed=5)
+    eng = ms.Engine({"weights": blob, "max_batch": 3, "net_h": net_h, "net_w": net_w})
+    vol = np.stack([synth.ct_slice(300 + i, w=640, h=400) for i in range(3)])
+    norm = eng.preprocess(vol)
+    for i in range(3):
+        assert (norm[i] == op.preprocess_raw(vol[i], net_w, net_h)).all()
+    mask, logits = eng.process(norm, want_logits=True)
+    arch, w = W.load_blob(blob)
+    want = unet_logits(load_unet(w, 3), norm)
+    err = np.abs(logits - want)
+    print(net_h, net_w, "logits: max err %.4g p99.9 %.4g" % (err.max(), np.quantile(err, 0.999)))
+    assert np.quantile(err, 0.999) < 2e-2
+    for i in range(3):
+        assert (mask[i] == op.argmax_first3(logits[i])).all()
+    polys, norm2, clean = eng.process_batch(vol, want_norm=True, want_mask=True)
+    assert (norm2 == norm).all()
+    for i in range(3):
+        assert (clean[i] == op.postprocess_mask(mask[i])).all()
+        ref = op.map_contour_points(op.extract_contours(op.mask_to_image(clean[i])), 640 / net_w, 400 / net_h)
+        assert contours_equal(polys.slice(i), ref), i
+    eng.cleanup()
