@@ -14,7 +14,7 @@
 // label plane, so the label traffic scales with the number of runs, not pixels (CT-like masks: ~2 runs per row), and
 // everything else -- neighbourhood tests, hole filling, 3x3 morphology -- is word-wide bit arithmetic.  One thread owns
 // one word:
-//   heads   : L[head] = head (area / flag cleared)                       -- fused into the kernels that produce bits
+//   heads   : L[head] = head (area / flag cleared)                       -- fused into the kernels that produce the bits
 //   merge   : seam with the previous word, then for the row above only the leftmost pixel of every "both rows set"
 //             stretch (plus the two diagonal cases for 8-connectivity) issues a lock-free atomicMin union
 //   resolve : every head is compressed to its root; per-root area (run lengths) and "touches the border" flag
@@ -99,32 +99,24 @@ __device__ __forceinline__ int root_of(const uint32_t* bits, const int* L, int w
     const int y = widx / wpitch, wx = widx - y * wpitch;                 \
     const int sl = blockIdx.y
 
-// ---- heads: L[head] = head, statistics cleared.  One thread per word.  INVERT labels the complement of `bits`.
+// ---- heads: L[head] = head, statistics cleared, for the runs of one word.  INVERT labels the complement of `bits`.
 template <bool INVERT>
-__global__ void __launch_bounds__(kThreads) heads_kernel(const uint32_t* __restrict__ bits_all, int H, int W, int wpitch,
-                                                          int* __restrict__ L_all, int* __restrict__ area_all, uint8_t* __restrict__ flag_all) {
-    MS_CCL_WORD_COORDS();
-    const size_t slice = (size_t)sl * H * W;
-    uint32_t b = bits_all[((size_t)sl * H + y) * wpitch + wx];
+__device__ __forceinline__ void init_heads(uint32_t b, int W, int y, int wx, int* __restrict__ L, int* __restrict__ area,
+                                           uint8_t* __restrict__ flag) {   // L / area / flag: this slice's planes
     if (INVERT) b = ~b & valid_mask(W, wx);
     uint32_t h = head_mask(b);
     while (h) {
         const int x = __ffs((int)h) - 1;
         h &= h - 1;
-        const size_t p = slice + (size_t)y * W + wx * 32 + x;
-        L_all[p] = y * W + wx * 32 + x;
-        if (area_all) area_all[p] = 0;
-        if (flag_all) flag_all[p] = 0;
+        const int p = y * W + wx * 32 + x;
+        L[p] = p;
+        if (area) area[p] = 0;
+        if (flag) flag[p] = 0;
     }
 }
-
 // ---- merge.  One thread per word.  CONN = 4 or 8.
 template <int CONN, bool INVERT>
-__global__ void __launch_bounds__(kThreads) merge_kernel(const uint32_t* __restrict__ bits_all, int H, int W, int wpitch,
-                                                          int* __restrict__ L_all) {
-    MS_CCL_WORD_COORDS();
-    const uint32_t* B = bits_all + (size_t)sl * H * wpitch;
-    int* L = L_all + (size_t)sl * H * W;
+__device__ __forceinline__ void merge_word(const uint32_t* __restrict__ B, int W, int wpitch, int y, int wx, int* __restrict__ L) {
     auto word = [&](int yy, int ww) -> uint32_t {
         if (yy < 0 || ww < 0 || ww >= wpitch) return 0u;
         uint32_t v = __ldg(B + (size_t)yy * wpitch + ww);
@@ -168,16 +160,25 @@ __global__ void __launch_bounds__(kThreads) merge_kernel(const uint32_t* __restr
         }
     }
 }
+template <int CONN, bool INVERT>
+__global__ void __launch_bounds__(kThreads) merge_kernel(const uint32_t* __restrict__ bits_all, int H, int W, int wpitch,
+                                                          int* __restrict__ L_all) {
+    MS_CCL_WORD_COORDS();
+    merge_word<CONN, INVERT>(bits_all + (size_t)sl * H * wpitch, W, wpitch, y, wx, L_all + (size_t)sl * H * W);
+}
+// the two labellings mask2polygon needs, in one launch: 8-connected foreground into L_fg, 4-connected background into L_bg
+static __global__ void __launch_bounds__(kThreads) merge_fg8_bg4_kernel(const uint32_t* __restrict__ bits_all, int H, int W, int wpitch,
+                                                                  int* __restrict__ L_fg, int* __restrict__ L_bg) {
+    MS_CCL_WORD_COORDS();
+    const uint32_t* B = bits_all + (size_t)sl * H * wpitch;
+    merge_word<8, false>(B, W, wpitch, y, wx, L_fg + (size_t)sl * H * W);
+    merge_word<4, true>(B, W, wpitch, y, wx, L_bg + (size_t)sl * H * W);
+}
 
 // ---- resolve.  One thread per word: heads -> roots, per-root area and border flag.
 template <bool INVERT>
-__global__ void __launch_bounds__(kThreads) resolve_kernel(const uint32_t* __restrict__ bits_all, int H, int W, int wpitch,
-                                                            int* __restrict__ L_all, int* __restrict__ area_all,
-                                                            uint8_t* __restrict__ flag_all) {
-    MS_CCL_WORD_COORDS();
-    const size_t slice = (size_t)sl * H * W;
-    int* L = L_all + slice;
-    uint32_t b = bits_all[((size_t)sl * H + y) * wpitch + wx];
+__device__ __forceinline__ void resolve_word(uint32_t b, int H, int W, int y, int wx, int* __restrict__ L, int* __restrict__ area,
+                                             uint8_t* __restrict__ flag) {   // L / area / flag: this slice's planes
     if (INVERT) b = ~b & valid_mask(W, wx);
     uint32_t h = head_mask(b);
     while (h) {
@@ -187,12 +188,30 @@ __global__ void __launch_bounds__(kThreads) resolve_kernel(const uint32_t* __res
         const int r = find_root(L, p);
         L[p] = r;
         const uint32_t rm = run_mask(b, x);
-        if (area_all) atomicAdd(&area_all[slice + r], __popc(rm));
-        if (flag_all) {
+        if (area) atomicAdd(&area[r], __popc(rm));
+        if (flag) {
             const int x_first = wx * 32 + x, x_last = wx * 32 + 31 - __clz(rm);
-            if (y == 0 || y == H - 1 || x_first == 0 || x_last == W - 1) flag_all[slice + r] = 1;
+            if (y == 0 || y == H - 1 || x_first == 0 || x_last == W - 1) flag[r] = 1;
         }
     }
+}
+template <bool INVERT>
+__global__ void __launch_bounds__(kThreads) resolve_kernel(const uint32_t* __restrict__ bits_all, int H, int W, int wpitch,
+                                                            int* __restrict__ L_all, int* __restrict__ area_all,
+                                                            uint8_t* __restrict__ flag_all) {
+    MS_CCL_WORD_COORDS();
+    const size_t slice = (size_t)sl * H * W;
+    resolve_word<INVERT>(bits_all[((size_t)sl * H + y) * wpitch + wx], H, W, y, wx, L_all + slice, area_all ? area_all + slice : nullptr,
+                         flag_all ? flag_all + slice : nullptr);
+}
+static __global__ void __launch_bounds__(kThreads) resolve_fg_bg_kernel(const uint32_t* __restrict__ bits_all, int H, int W, int wpitch,
+                                                                  int* __restrict__ L_fg, int* __restrict__ L_bg,
+                                                                  uint8_t* __restrict__ bg_flag) {
+    MS_CCL_WORD_COORDS();
+    const size_t slice = (size_t)sl * H * W;
+    const uint32_t b = bits_all[((size_t)sl * H + y) * wpitch + wx];
+    resolve_word<false>(b, H, W, y, wx, L_fg + slice, nullptr, nullptr);
+    resolve_word<true>(b, H, W, y, wx, L_bg + slice, nullptr, bg_flag + slice);
 }
 
 inline dim3 grid_for(int H, int wpitch, int batch) { return dim3(cdiv(H * wpitch, kThreads), batch); }

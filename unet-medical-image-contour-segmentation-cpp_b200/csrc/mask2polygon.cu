@@ -30,13 +30,20 @@ namespace {
 
 constexpr size_t kTraceSmemMax = 200 * 1024;   // slices up to ~1264 x 1264 trace out of shared memory (+ the 8 KiB step table)
 
-// mask -> bits of (mask > thr), one word per warp.  grid = (ceil(W / 256), H, batch), block = 256 (8 words)
+// mask -> bits of (mask > thr), one word per warp, and the run heads of both labellings (8-connected foreground,
+// 4-connected background + frame flag).  grid = (ceil(W / 256), H, batch), block = 256 (8 words)
 __global__ void __launch_bounds__(256) thr_bits_kernel(const uint8_t* __restrict__ mask, int H, int W, int wpitch, int thr,
-                                                        uint32_t* __restrict__ bits) {
+                                                        uint32_t* __restrict__ bits, int* __restrict__ L_fg, int* __restrict__ L_bg,
+                                                        uint8_t* __restrict__ bg_flag) {
     const int x = blockIdx.x * 256 + threadIdx.x, y = blockIdx.y;
     const bool fg = x < W && mask[((size_t)blockIdx.z * H + y) * W + x] > thr;   // src/mask2polygon.cpp:31 threshold(127)
     const unsigned b = __ballot_sync(0xFFFFFFFFu, fg);
-    if ((threadIdx.x & 31) == 0 && (x >> 5) < wpitch) bits[((size_t)blockIdx.z * H + y) * wpitch + (x >> 5)] = b;
+    if ((threadIdx.x & 31) == 0 && (x >> 5) < wpitch) {
+        bits[((size_t)blockIdx.z * H + y) * wpitch + (x >> 5)] = b;
+        const size_t slice = (size_t)blockIdx.z * H * W;
+        ccl::init_heads<false>(b, W, y, x >> 5, L_fg + slice, nullptr, nullptr);
+        ccl::init_heads<true>(b, W, y, x >> 5, L_bg + slice, nullptr, bg_flag + slice);
+    }
 }
 
 // number of external contour starts among the run heads of word `wx` of row `y`, and (optionally) their pixel indices.
@@ -1061,19 +1068,11 @@ void m2p_phase_a(M2pWs& ws, PolyDev& P, const uint8_t* d_mask, int h, int w, int
     long long* header = P.header.as<long long>();
     const dim3 gw = ccl::grid_for(h, wpitch, batch);
 
-    thr_bits_kernel<<<dim3(cdiv(w, 256), h, batch), 256, 0, st>>>(d_mask, h, w, wpitch, threshold, B);
+    thr_bits_kernel<<<dim3(cdiv(w, 256), h, batch), 256, 0, st>>>(d_mask, h, w, wpitch, threshold, B, Lfg, Lbg, flag);
     MS_LAUNCH_CHECK();
-    ccl::heads_kernel<false><<<gw, ccl::kThreads, 0, st>>>(B, h, w, wpitch, Lfg, nullptr, nullptr);      // 8-connected foreground
+    ccl::merge_fg8_bg4_kernel<<<gw, ccl::kThreads, 0, st>>>(B, h, w, wpitch, Lfg, Lbg);      // 8-connected foreground, 4-connected background
     MS_LAUNCH_CHECK();
-    ccl::heads_kernel<true><<<gw, ccl::kThreads, 0, st>>>(B, h, w, wpitch, Lbg, nullptr, flag);          // 4-connected background
-    MS_LAUNCH_CHECK();
-    ccl::merge_kernel<8, false><<<gw, ccl::kThreads, 0, st>>>(B, h, w, wpitch, Lfg);
-    MS_LAUNCH_CHECK();
-    ccl::merge_kernel<4, true><<<gw, ccl::kThreads, 0, st>>>(B, h, w, wpitch, Lbg);
-    MS_LAUNCH_CHECK();
-    ccl::resolve_kernel<false><<<gw, ccl::kThreads, 0, st>>>(B, h, w, wpitch, Lfg, nullptr, nullptr);
-    MS_LAUNCH_CHECK();
-    ccl::resolve_kernel<true><<<gw, ccl::kThreads, 0, st>>>(B, h, w, wpitch, Lbg, nullptr, flag);
+    ccl::resolve_fg_bg_kernel<<<gw, ccl::kThreads, 0, st>>>(B, h, w, wpitch, Lfg, Lbg, flag);
     MS_LAUNCH_CHECK();
     count_starts_kernel<<<dim3(bps, batch), 256, 0, st>>>(B, Lfg, Lbg, flag, h, w, wpitch, bc);
     MS_LAUNCH_CHECK();

@@ -22,12 +22,17 @@ namespace {
 // mask -> bits of (mask == fg), one word per warp; also initialises the heads of the INVERSE image's runs
 // grid = (ceil(W / 256), H, batch), block = 256 (8 words)
 __global__ void __launch_bounds__(256) fg_bits_kernel(const uint8_t* __restrict__ mask, int H, int W, int wpitch, int fg_value,
-                                                       uint32_t* __restrict__ bits) {
+                                                       uint32_t* __restrict__ bits, int* __restrict__ L_all, int* __restrict__ area_all,
+                                                       uint8_t* __restrict__ flag_all) {
     const int x = blockIdx.x * 256 + threadIdx.x, y = blockIdx.y;
     const bool in = x < W;
     const bool fg = in && mask[((size_t)blockIdx.z * H + y) * W + x] == fg_value;
     const unsigned b = __ballot_sync(0xFFFFFFFFu, fg);
-    if ((threadIdx.x & 31) == 0 && (x >> 5) < wpitch) bits[((size_t)blockIdx.z * H + y) * wpitch + (x >> 5)] = b;
+    if ((threadIdx.x & 31) == 0 && (x >> 5) < wpitch) {
+        bits[((size_t)blockIdx.z * H + y) * wpitch + (x >> 5)] = b;
+        const size_t slice = (size_t)blockIdx.z * H * W;
+        ccl::init_heads<true>(b, W, y, x >> 5, L_all + slice, area_all + slice, flag_all + slice);   // runs of the inverse image
+    }
 }
 
 // filled = fg | (runs of inverse components that are holes).  One thread per word.
@@ -151,9 +156,7 @@ void postprocess_launch(PostprocessWs& ws, const uint8_t* d_in, uint8_t* d_out, 
     uint32_t* Bfill = ws.bin_b.as<uint32_t>();
     const dim3 gw = ccl::grid_for(h, wpitch, batch);
 
-    fg_bits_kernel<<<dim3(cdiv(w, 256), h, batch), 256, 0, st>>>(d_in, h, w, wpitch, fg_value, Bfg);
-    MS_LAUNCH_CHECK();
-    ccl::heads_kernel<true><<<gw, ccl::kThreads, 0, st>>>(Bfg, h, w, wpitch, L, A, F);           // runs of the inverse image
+    fg_bits_kernel<<<dim3(cdiv(w, 256), h, batch), 256, 0, st>>>(d_in, h, w, wpitch, fg_value, Bfg, L, A, F);
     MS_LAUNCH_CHECK();
     ccl::merge_kernel<8, true><<<gw, ccl::kThreads, 0, st>>>(Bfg, h, w, wpitch, L);
     MS_LAUNCH_CHECK();
