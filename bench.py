@@ -12,7 +12,9 @@ torch.distributed traffic is the barrier and the max-over-ranks of the timing.
 Keys of the JSON line (rank 0):
   value / ms_per_step : whole-job slices/s with inputs already resident in HBM, CUDA-event timed
   e2e                 : same metric through the C-ABI call with pinned HOST buffers (H2D + polygons D2H inside)
-  roofline            : the dominant kernel (tcgen05 implicit-GEMM conv): algorithmic FLOP / event-timed duration
+  roofline            : the dominant kernel instantiation (by time): algorithmic FLOP of its launches / their CUDA-event
+                        durations vs the measured BURST cuBLAS bf16 peak (kernels are timed alone); `forward_pass` = the
+                        whole UNet forward in a sustained loop vs the SUSTAINED peak; `by_kernel` = every instantiation
   cpu_baseline        : the oracle port of the reference's CPU pipeline on a bounded sample (rank 0, N=1 only)
   clocks, gpu_launches, p50_ms_per_slice (batch-1 latency)
 `--impl reference` times the oracle port (the reference cannot be built here: OpenCV C++ SDK + TensorRT
@@ -78,8 +80,19 @@ class ClockSampler(threading.Thread):
             self.nv = pynvml
             self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
             self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            # the first queries can take ~100 ms: pay for them before the timed region starts
+            pynvml.nvmlDeviceGetClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
         except Exception:
             self.nv = None
+        self.proc = None
+        if self.nv is None:   # no NVML binding: let nvidia-smi sample (the recipe's clocks line)
+            try:
+                import subprocess
+                self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=clocks.sm,clocks.max.sm,clocks_throttle_reasons.active",
+                                              "--format=csv,noheader,nounits", "-lms", "20"], stdout=subprocess.PIPE, text=True)
+            except Exception:
+                self.proc = None
 
     def run(self):
         if not self.nv:
@@ -96,10 +109,28 @@ class ClockSampler(threading.Thread):
                         self.reasons.add(name)
             except Exception:
                 pass
-            time.sleep(0.01)
+            time.sleep(0.005)
 
     def result(self):
         self.stop_flag = True
+        if self.proc is not None:
+            self.proc.terminate()
+            try:
+                out = self.proc.communicate(timeout=5)[0]
+            except Exception:
+                out = ""
+            masks = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
+            for line in out.splitlines():
+                f = [x.strip() for x in line.split(",")]
+                try:
+                    self.samples.append(float(f[0]))
+                    self.max_mhz = int(float(f[1]))
+                    bits = int(f[2], 16)
+                    self.reasons |= {n for b, n in masks.items() if bits & b}
+                except Exception:
+                    pass
+        elif self.is_alive():
+            self.join(timeout=1.0)
         if not self.samples:
             return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": []}
         return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
@@ -261,29 +292,61 @@ def run_ours(args, rank, world, local):
 
     # ---------------- roofline of the dominant kernel (tcgen05 conv), live, CUDA events per layer
     peaks = measured_peaks()
-    names = eng.layer_names()
-    table, tc_flops, tc_ms, all_ms = [], 0.0, 0.0, 0.0
+    names, kernels = eng.layer_names(), eng.layer_kernels()
+    table = []
+    by_kernel = {}
     for li, name in enumerate(names):
         ms_l, fl = eng.time_layer(li, B, iters=max(3, min(10, args.steps)))
-        table.append({"layer": name, "ms": ms_l, "gflop": fl / 1e9, "tflops": fl / ms_l / 1e9 if ms_l > 0 else None})
-        all_ms += ms_l
-        if name != "enc1a":
-            tc_flops += fl
-            tc_ms += ms_l
-    achieved = tc_flops / (tc_ms / 1e3) / 1e12
-    peak = peaks["bf16_sustained"]
-    # DRAM bytes of the same 21 launches from the committed `ncu --set full` capture (tools/forward_once.py, same batch)
-    traffic, traffic_src = None, None
+        table.append({"layer": name, "kernel": kernels[li], "ms": ms_l, "gflop": fl / 1e9, "tflops": fl / ms_l / 1e9 if ms_l > 0 else None})
+        k = by_kernel.setdefault(kernels[li], {"kernel": kernels[li], "launches": 0, "ms": 0.0, "flop": 0.0})
+        k["launches"] += 1
+        k["ms"] += ms_l
+        k["flop"] += fl
+    # Denominators (MEASURED_PEAKS.json): a kernel timed alone (ms_time_layer: a few back-to-back launches of one layer)
+    # is compared with the BURST cuBLAS bf16 figure, the whole forward pass inside a long loop with the SUSTAINED one.
+    burst, sustained = peaks["bf16_burst"], peaks["bf16_sustained"]
+    kernel_rows = sorted(by_kernel.values(), key=lambda r: -r["ms"])
+    for r in kernel_rows:   # per kernel instantiation: algorithmic FLOP of its launches / their event-timed durations
+        r["achieved"] = r["flop"] / (r["ms"] / 1e3) / 1e12
+        r["frac"] = r["achieved"] / burst
+        r["share_of_step"] = r["ms"] / ms_per_step
+        del r["flop"]
+    dominant = kernel_rows[0]
+    # the forward pass alone, sustained: `steps` passes back to back on resident input
+    d_norm = torch.empty((B, S, S), dtype=torch.uint8, device="cuda")
+    d_cls = torch.empty_like(d_norm)
+    eng.preprocess_dev(dev[0].data_ptr(), S, S, B, d_norm.data_ptr(), 0, stream)
+    for _ in range(args.warmup):
+        eng.unet_forward_dev(d_norm.data_ptr(), B, d_cls.data_ptr(), 0, stream)
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0.record()
+    for _ in range(args.steps):
+        eng.unet_forward_dev(d_norm.data_ptr(), B, d_cls.data_ptr(), 0, stream)
+    f1.record()
+    torch.cuda.synchronize()
+    fwd_ms = f0.elapsed_time(f1) / args.steps
+    fwd_tflops = eng.info.flops_per_slice * B / (fwd_ms / 1e3) / 1e12
+    # DRAM bytes from the committed `ncu --set full` capture of one forward pass at this batch (tools/forward_once.py)
+    traffic, traffic_all, traffic_src = None, None, None
     prof = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r1_ncu_full_forward_b32.json")
     if os.path.exists(prof):
         with open(prof) as f:
             pj = json.load(f)
-        if pj.get("batch") == B and S == 512:
-            traffic = pj["tcgen05_dram_bytes"]
-            traffic_src = "profiles/r1_ncu_full_forward_b32.json: dram__bytes_read.sum + dram__bytes_write.sum summed over the 21 tcgen05 launches of one step"
-    roofline = {"bound": "tensor", "kernel": "ms::tc::conv_halo2_kernel / conv_halo_kernel / conv_gemm_kernel (21 tcgen05 launches per step)", "achieved": achieved, "peak": peak,
-                "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peaks["source"] + " (sustained cuBLAS bf16)",
-                "unet_ms_per_step": all_ms, "unet_share_of_step": all_ms / ms_per_step}
+        if pj.get("batch") == B and S == 512 and len(pj["layers"]) == len(names):
+            per_layer = [l["dram_read_bytes"] + l["dram_write_bytes"] for l in pj["layers"]]
+            traffic = sum(b for b, k in zip(per_layer, kernels) if k == dominant["kernel"])
+            traffic_all = pj["tcgen05_dram_bytes"]
+            traffic_src = "profiles/r1_ncu_full_forward_b32.json: dram__bytes_read.sum + dram__bytes_write.sum per launch, summed over this kernel's launches of one step"
+    roofline = {"bound": "tensor", "kernel": dominant["kernel"], "launches_per_step": dominant["launches"],
+                "achieved": dominant["achieved"], "peak": burst, "unit": "TFLOP/s", "frac": dominant["achieved"] / burst,
+                "traffic": traffic, "traffic_source": traffic_src,
+                "peak_source": peaks["source"] + " cuBLAS bf16, burst (the kernel is timed alone); nominal dense bf16 is 2250",
+                "frac_of_nominal": dominant["achieved"] / 2250.0, "share_of_step": dominant["share_of_step"],
+                "timing": "CUDA events around back-to-back launches of each layer (ms_time_layer), summed over the kernel's layers",
+                "forward_pass": {"achieved": fwd_tflops, "peak": sustained, "frac": fwd_tflops / sustained, "ms": fwd_ms,
+                                 "what": "whole UNet forward (22 launches), %d passes back to back, vs sustained cuBLAS bf16" % args.steps,
+                                 "traffic": traffic_all, "share_of_step": fwd_ms / ms_per_step},
+                "by_kernel": kernel_rows}
     if args.layer_table and rank == 0:
         with open(args.layer_table, "w") as f:
             json.dump({"batch": B, "layers": table}, f, indent=1)

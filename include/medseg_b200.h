@@ -207,6 +207,8 @@ MS_API int64_t ms_launch_count(ms_handle* h);
 MS_API int ms_time_layer(ms_handle* h, int layer, int batch, int iters, float* ms_per_launch, double* flops);
 MS_API int ms_layer_count(ms_handle* h);
 MS_API const char* ms_layer_name(ms_handle* h, int layer);
+/* Kernel instantiation that layer runs on (as ncu prints it), valid until the next call on this thread. */
+MS_API const char* ms_layer_kernel(ms_handle* h, int layer);
 
 /* Debug: copy an internal activation (bf16 NHWC) of the last forward to host as fp32 NCHW.
  * Returns element count or negative status.  `name` as in ms_layer_name. */

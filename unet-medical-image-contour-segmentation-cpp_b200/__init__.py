@@ -80,6 +80,7 @@ ABI = {
     "ms_time_layer": (_I, [_P, _I, _I, _I, C.POINTER(C.c_float), C.POINTER(C.c_double)]),
     "ms_layer_count": (_I, [_P]),
     "ms_layer_name": (C.c_char_p, [_P, _I]),
+    "ms_layer_kernel": (C.c_char_p, [_P, _I]),
     "ms_debug_read_activation": (_L, [_P, C.c_char_p, _I, _P, _L]),
 }
 
@@ -349,6 +350,10 @@ class Engine:
 
     def layer_names(self) -> List[str]:
         return [self._l.ms_layer_name(self._h, i).decode() for i in range(self._l.ms_layer_count(self._h))]
+
+    def layer_kernels(self) -> List[str]:
+        """Kernel instantiation each UNet layer runs on (as ncu prints it)."""
+        return [self._l.ms_layer_kernel(self._h, i).decode() for i in range(self._l.ms_layer_count(self._h))]
 
     def time_layer(self, layer: int, batch: int, iters: int = 20):
         ms, fl = C.c_float(0), C.c_double(0)

@@ -926,6 +926,12 @@ const char* ms_layer_name(ms_handle* h, int layer) {
     if (!h || !h->unet.loaded() || layer < 0 || layer >= (int)h->unet.layers().size()) return "";
     return h->unet.layers()[layer].name.c_str();
 }
+const char* ms_layer_kernel(ms_handle* h, int layer) {
+    static thread_local std::string name;
+    if (!h || !h->unet.loaded() || layer < 0 || layer >= (int)h->unet.layers().size()) return "";
+    name = h->unet.layers()[layer].kernel_name();
+    return name.c_str();
+}
 int ms_time_layer(ms_handle* h, int layer, int batch, int iters, float* ms_per_launch, double* flops) {
     if (!h) return MS_ERR_ARG;
     return guarded(h, [&] {

@@ -28,6 +28,14 @@ struct UNetLayer {
     int resident_kc = 0;         // halo kernel: > 0 when all weights stay in shared memory
     int halo_pitch = 16;         // halo kernel: shared-memory rows per halo image row (10 dense / 16 aligned)
     double flops_per_slice = 0;  // 2 * MAC
+    // the kernel instantiation run_layer launches for this layer, as ncu prints it
+    std::string kernel_name() const {
+        const char* epi = kind == 3 ? "EPI_HEAD" : (kind == 2 ? "EPI_CONVT" : "EPI_STORE");
+        if (kind == 0) return "first_conv_kernel";
+        if (halo == 2) return "tc::conv_halo2_kernel<" + std::to_string(block_n) + ", " + epi + ", " + std::to_string(resident_kc) + ">";
+        if (halo == 1) return "tc::conv_halo_kernel<" + std::to_string(block_n) + ", " + epi + ", " + std::to_string(resident_kc) + ", 10>";
+        return "tc::conv_gemm_kernel<" + std::to_string(block_n) + ", " + epi + ">";
+    }
 };
 
 struct ActBuf {
