@@ -137,7 +137,7 @@ class ClockSampler(threading.Thread):
 
 
 # ------------------------------------------------------------------------------------------ reference arm
-def oracle_runner(n_classes, head, size):
+def oracle_runner(n_classes, head, size, with_files=False):
     """The reference's CPU pipeline as restated by the oracle (oracle/pipeline.py + torch-CPU UNet)."""
     import torch
     import medseg_b200 as ms
@@ -156,7 +156,11 @@ def oracle_runner(n_classes, head, size):
             r = op.process_slice(s, net, head="argmax" if head == "argmax" else "binary", n_classes=n_classes)
             out.append(op.generate_json(r["mapped"], "s", s.shape[1], s.shape[0]) if r["mapped"] else "")
         return out
-    return run, cores
+
+    def run_files(paths, out_dir):   # the reference as shipped: through PNG / JSON files
+        for p in paths:
+            op.process_single_image_files(p, size, size, out_dir, net, head="argmax" if head == "argmax" else "binary")
+    return (run, cores, run_files) if with_files else (run, cores)
 
 
 def run_reference(args, rank, world):
@@ -354,7 +358,7 @@ def run_ours(args, rank, world, local):
     # ---------------- CPU baseline beside it (rank 0, N=1 only)
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        run, cores = oracle_runner(n_classes, args.head, S)
+        run, cores, run_files = oracle_runner(n_classes, args.head, S, with_files=True)
         vol = host[0].numpy()
         run(vol[:1])
         sample = args.cpu_sample or min(32, len(vol))
@@ -363,6 +367,16 @@ def run_ours(args, rank, world, local):
         dtc = time.perf_counter() - t0
         cpu = {"value": sample / dtc, "unit": "slices/s", "cores": cores, "kind": "port",
                "sample": f"first {sample} slices of the step's batch, in memory (no PNG round trips), JSON text included, {dtc:.1f} s"}
+        # the reference as shipped: the same call sequence with every PNG / JSON round trip (src/process.cpp:188-262)
+        n_files = min(8, sample)
+        fdir = os.path.join(td, "as_shipped")
+        os.makedirs(fdir, exist_ok=True)
+        for i in range(n_files):
+            vol[i].tofile(os.path.join(fdir, f"s{i:03d}.raw"))
+        t0 = time.perf_counter()
+        run_files([os.path.join(fdir, f"s{i:03d}.raw") for i in range(n_files)], os.path.join(fdir, "out"))
+        cpu["as_shipped_value"] = n_files / (time.perf_counter() - t0)
+        cpu["as_shipped_sample"] = f"{n_files} slices through files: RAW -> PNG/JSON artefacts -> re-read, as process_single_image does"
 
     info = eng.info
     eng.cleanup()

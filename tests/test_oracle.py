@@ -172,3 +172,21 @@ def test_map_points_truncates():
     c = [np.array([[3, 5], [511, 511]], np.int32)]
     m = op.map_contour_points(c, 600 / 512, 400 / 512)
     assert m[0].tolist() == [[3, 3], [598, 399]]
+
+
+def test_as_shipped_file_path_equals_in_memory(tmp_path):
+    """The oracle's as-shipped form (every PNG / JSON round trip of src/process.cpp:188-262) gives the in-memory
+    restatement's results: PNG is lossless, the sidecar carries the sizes."""
+    import cv2
+    from medseg_b200 import synth, weights as W
+    from oracle.unet_torch import load_unet
+    net = load_unet(W.make_weights(1234, 3), 3)
+    src = synth.ct_slice(3, w=600, h=400)
+    src.tofile(tmp_path / "a.raw")
+    r = op.process_single_image_files(str(tmp_path / "a.raw"), 600, 400, str(tmp_path / "out"), net)
+    m = op.process_slice(src, net)
+    assert [os.path.basename(p) for p in r["written"]] == ["a_normalized.png", "a_original_sizes.json", "a_mask.png", "a_contour_overlay.png", "a.json"]
+    assert (cv2.imread(str(tmp_path / "out" / "a_normalized.png"), cv2.IMREAD_UNCHANGED) == m["norm"]).all()
+    assert (cv2.imread(str(tmp_path / "out" / "a_mask.png"), cv2.IMREAD_UNCHANGED) == m["vis"]).all()
+    assert open(tmp_path / "out" / "a.json").read() == op.generate_json(m["mapped"], "a", 600, 400)
+    assert open(tmp_path / "out" / "a_original_sizes.json").read() == op.sidecar_json_text("a.raw", 600, 400)
