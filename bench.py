@@ -292,6 +292,15 @@ def run_ours(args, rank, world, local):
         eng.process_batch(one)
         if i >= 3:
             lat.append((time.perf_counter() - t) * 1e3)
+    p50_sync = float(np.median(lat))
+    # the same slice through submit + wait: the kernel chain of a slot is one CUDA graph launch
+    lat = []
+    for i in range(5 + 30):
+        t = time.perf_counter()
+        eng.submit_batch(0, one)
+        eng.wait_batch(0)
+        if i >= 5:
+            lat.append((time.perf_counter() - t) * 1e3)
     p50 = float(np.median(lat))
 
     # ---------------- roofline of the dominant kernel (tcgen05 conv), live, CUDA events per layer
@@ -389,7 +398,8 @@ def run_ours(args, rank, world, local):
                            "l2": "per-step working set (~0.29 GB of activations per slice) >> 126 MB L2; input batches rotate"},
                 "e2e": {"value": e2e_value, "unit": "slices/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "api": "ms_submit_batch_host + ms_wait_batch (double buffered)", "sync_call_value": e2e_sync},
-                "gpu_launches": int(launches), "clocks": clocks, "p50_ms_per_slice": p50, "roofline": roofline,
+                "gpu_launches": int(launches), "clocks": clocks, "p50_ms_per_slice": p50, "p50_api": "ms_submit_batch_host + ms_wait_batch, batch 1 (CUDA graph replay)",
+                "p50_sync_call_ms": p50_sync, "roofline": roofline,
                 "polygons_last_step": {"contours": int(n_cnt), "points": int(n_pts)},
                 "flops_per_slice": int(info.flops_per_slice)}
         if cpu:

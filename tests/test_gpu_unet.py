@@ -260,18 +260,23 @@ def test_binary_head(ms, tmp_path):
 
 
 def test_async_pipeline_matches_sync(unet_engine, ms):
-    """ms_submit_batch_host / ms_wait_batch (double buffered) returns exactly what ms_process_batch_host returns."""
-    vols = [_slices(ms, 4, first=60 + 4 * i) for i in range(3)]
+    """ms_submit_batch_host / ms_wait_batch (double buffered) returns exactly what ms_process_batch_host returns -- on the
+    eager first call of a slot, on the call that captures the slot's CUDA graph, on graph replays, and across a shape
+    change (which drops the graph) and back."""
+    sizes = [4, 4, 4, 4, 4, 4, 2, 2, 2, 4, 4, 3, 3, 3]
+    vols = [_slices(ms, n, first=60 + 4 * i) for i, n in enumerate(sizes)]
     want = [unet_engine.process_batch(v)[0] for v in vols]
+    l0 = unet_engine.launch_count()
     unet_engine.submit_batch(0, vols[0])
     got = []
-    for i in range(3):
-        if i + 1 < 3:
+    for i in range(len(vols)):
+        if i + 1 < len(vols):
             unet_engine.submit_batch((i + 1) % 2, vols[i + 1])
         got.append(unet_engine.wait_batch(i % 2))
     for a, b in zip(got, want):
         assert a.n_contours == b.n_contours and a.n_points == b.n_points
         assert (a.slice_start == b.slice_start).all() and (a.contour_start == b.contour_start).all() and (a.xy == b.xy).all()
+    assert unet_engine.launch_count() - l0 >= 40 * len(vols)      # replayed graphs count their kernels too
     with pytest.raises(ms.MedsegError) as ei:
         unet_engine.wait_batch(0)                  # nothing submitted
     assert ei.value.code == ms.MS_ERR_STATE

@@ -31,6 +31,23 @@ def main():
         e.process_batch(src)
         lat.append((time.perf_counter() - t) * 1e3)
     out = {"p50_ms": float(np.median(lat)), "p90_ms": float(np.quantile(lat, 0.9)), "min_ms": float(np.min(lat))}
+    # the same slice through ms_submit_batch_host + ms_wait_batch: the kernel chain is one CUDA graph launch
+    pin = torch.from_numpy(src).pin_memory()
+    for graph in ("1", "0"):
+        os.environ["MEDSEG_GRAPH"] = graph
+        eg = ms.Engine({"weights": blob, "max_batch": 4})
+        for _ in range(5):
+            eg.submit_batch(0, pin.numpy())
+            eg.wait_batch(0)
+        lat = []
+        for _ in range(100):
+            t = time.perf_counter()
+            eg.submit_batch(0, pin.numpy())
+            eg.wait_batch(0)
+            lat.append((time.perf_counter() - t) * 1e3)
+        out["p50_submit_wait_graph" + graph + "_ms"] = float(np.median(lat))
+        eg.cleanup()
+    os.environ.pop("MEDSEG_GRAPH")
     ts = torch.cuda.Stream()
     torch.cuda.set_stream(ts)
     st = ts.cuda_stream

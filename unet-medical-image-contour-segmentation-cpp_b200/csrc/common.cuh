@@ -1,5 +1,6 @@
 // common.cuh -- shared declarations for libmedseg_b200 (sm_100a only).
 #pragma once
+#include <atomic>
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
 #include <algorithm>
@@ -52,12 +53,17 @@ extern thread_local LaunchCounter* g_counter;
 static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 static inline int64_t cdiv64(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
+// Bumped whenever a device buffer is (re)allocated or freed: a captured CUDA graph holds raw pointers, so it is only
+// replayed while the epoch it was captured under is still current.
+extern std::atomic<uint64_t> g_alloc_epoch;   // process-wide and monotonic, so a stale graph can never look current
+
 // Simple growable device buffer (never shrinks; growth is outside any timed / captured region).
 struct DevBuf {
     void* p = nullptr;
     size_t cap = 0;
     void reserve(size_t bytes) {
         if (bytes <= cap) return;
+        ++g_alloc_epoch;
         if (p) MS_CUDA(cudaFree(p));
         p = nullptr;
         cap = 0;
@@ -65,7 +71,10 @@ struct DevBuf {
         cap = bytes;
     }
     void release() {
-        if (p) cudaFree(p);
+        if (p) {
+            ++g_alloc_epoch;
+            cudaFree(p);
+        }
         p = nullptr;
         cap = 0;
     }

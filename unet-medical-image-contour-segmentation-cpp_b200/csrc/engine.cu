@@ -27,6 +27,7 @@
 namespace ms {
 
 thread_local LaunchCounter* g_counter = nullptr;
+std::atomic<uint64_t> g_alloc_epoch{1};
 static thread_local std::string t_last_error = "";
 
 void fail(int code, const std::string& what) { throw Error{code, what}; }
@@ -71,7 +72,14 @@ struct ms_handle {
         cudaEvent_t ev_h2d = nullptr, ev_m2p = nullptr, ev_done = nullptr;
         int batch = 0;
         bool busy = false;
+        // CUDA graph of the slot's kernel chain (K1 .. K6), replayed while shape and buffers are unchanged
+        cudaGraphExec_t gexec = nullptr;
+        int g_w = 0, g_h = 0, g_batch = 0;      // shape the graph was captured for
+        int seen_w = 0, seen_h = 0, seen_batch = 0;   // shape of the last eager run (buffers are sized for it)
+        uint64_t g_epoch = 0, seen_epoch = 0;
+        int64_t g_launches = 0;
     } slots[2];
+    bool graphs_on = true;     // MEDSEG_GRAPH=0 disables graph replay
     cudaStream_t copy_stream = nullptr, d2h_stream = nullptr;
     BatchHost file_host[2];   // ms_process_raw_file(s) / ms_process_directory
     // log: every line is appended with open/append/close, so the C++ facade's own std::ofstream
@@ -206,6 +214,7 @@ void finish_init(ms_handle* h, const char* log_dir) {
     }
     MS_REQUIRE(h->device >= 0 && h->device < ndev, MS_ERR_ARG, "device ordinal out of range");
     MS_CUDA(cudaSetDevice(h->device));
+    if (const char* g = std::getenv("MEDSEG_GRAPH")) h->graphs_on = g[0] != '0';
     cudaDeviceProp prop{};
     MS_CUDA(cudaGetDeviceProperties(&prop, h->device));
     MS_REQUIRE(prop.major == 10, MS_ERR_CUDA,
@@ -370,6 +379,7 @@ void ms_destroy(ms_handle* h) {
         S.poly.release();
         for (PinBuf* b : {&S.h_src, &S.h_header, &S.h_slice_start, &S.h_cstart, &S.h_xy}) b->release();
         if (S.ev_h2d) cudaEventDestroy(S.ev_h2d);
+        if (S.gexec) cudaGraphExecDestroy(S.gexec);
         if (S.ev_m2p) cudaEventDestroy(S.ev_m2p);
         if (S.ev_done) cudaEventDestroy(S.ev_done);
     }
@@ -876,11 +886,56 @@ int ms_submit_batch_host(ms_handle* h, int slot, const uint16_t* h_src, int w, i
         uint8_t* norm = h->d_norm.as<uint8_t>();
         uint8_t* raw = h->d_mask_raw.as<uint8_t>();
         uint8_t* mask = h->d_mask.as<uint8_t>();
-        preprocess_launch(h->pre, S.d_src.as<uint16_t>(), w, hgt, batch, h->net_w, h->net_h, norm, nullptr, st);
-        h->unet.forward(norm, batch, raw, nullptr, st);
-        postprocess_launch(h->post, raw, mask, h->net_h, h->net_w, batch, h->fg_value, h->min_area_ratio, st);
-        m2p_phase_a(h->m2p, S.poly, mask, h->net_h, h->net_w, batch, h->fg_value - 1, st);
-        m2p_phase_b(h->m2p, S.poly, h->net_h, h->net_w, batch, w, hgt, st);
+        auto enqueue = [&] {
+            preprocess_launch(h->pre, S.d_src.as<uint16_t>(), w, hgt, batch, h->net_w, h->net_h, norm, nullptr, st);
+            h->unet.forward(norm, batch, raw, nullptr, st);
+            postprocess_launch(h->post, raw, mask, h->net_h, h->net_w, batch, h->fg_value, h->min_area_ratio, st);
+            m2p_phase_a(h->m2p, S.poly, mask, h->net_h, h->net_w, batch, h->fg_value - 1, st);
+            m2p_phase_b(h->m2p, S.poly, h->net_h, h->net_w, batch, w, hgt, st);
+        };
+        // The chain has no host round trip, so it is captured once per (slot, shape) and replayed: the reference does the
+        // same for its inference (cudaGraphLaunch, src/process.cpp:147).  First call with a shape: eager (sizes every
+        // buffer).  Second call: capture + launch.  Later calls: launch.  Any reallocation bumps the epoch and drops it.
+        const bool same_graph = S.gexec && S.g_w == w && S.g_h == hgt && S.g_batch == batch && S.g_epoch == g_alloc_epoch;
+        const bool same_eager = S.seen_w == w && S.seen_h == hgt && S.seen_batch == batch && S.seen_epoch == g_alloc_epoch;
+        if (h->graphs_on && same_graph) {
+            MS_CUDA(cudaGraphLaunch(S.gexec, st));
+            h->counter.n += S.g_launches;
+        } else if (h->graphs_on && same_eager) {
+            if (S.gexec) {
+                cudaGraphExecDestroy(S.gexec);
+                S.gexec = nullptr;
+            }
+            const int64_t l0 = h->counter.n;
+            const uint64_t e0 = g_alloc_epoch;
+            cudaGraph_t graph = nullptr;
+            MS_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeRelaxed));
+            try {
+                enqueue();
+            } catch (...) {
+                cudaStreamEndCapture(st, &graph);
+                if (graph) cudaGraphDestroy(graph);
+                throw;
+            }
+            MS_CUDA(cudaStreamEndCapture(st, &graph));
+            const int64_t captured = h->counter.n - l0;
+            h->counter.n = l0;
+            if (g_alloc_epoch == e0 && cudaGraphInstantiate(&S.gexec, graph, 0) == cudaSuccess) {
+                S.g_w = w; S.g_h = hgt; S.g_batch = batch; S.g_epoch = e0; S.g_launches = captured;
+                cudaGraphDestroy(graph);
+                MS_CUDA(cudaGraphLaunch(S.gexec, st));
+                h->counter.n += captured;
+            } else {            // a buffer moved while capturing (or instantiation failed): run this batch eagerly
+                cudaGetLastError();
+                S.gexec = nullptr;
+                if (graph) cudaGraphDestroy(graph);
+                enqueue();
+                S.seen_epoch = g_alloc_epoch;
+            }
+        } else {
+            enqueue();
+            S.seen_w = w; S.seen_h = hgt; S.seen_batch = batch; S.seen_epoch = g_alloc_epoch;
+        }
         // results leave on their own stream so the next batch's kernels are not held up; sizes are not known on the
         // host yet, so the capacity-sized buffers are copied and trimmed in ms_wait_batch
         MS_CUDA(cudaEventRecord(S.ev_m2p, st));
