@@ -164,7 +164,7 @@ MS_API int ms_process_batch_dev(ms_handle* h, const uint16_t* d_src, int w, int 
  * it must stay valid until the matching ms_wait_batch returns.  Polygon capacities are fixed per slot
  * (64 contours and 8,192 points per slice on average); a batch that exceeds them fails with MS_ERR_CAPACITY in
  * ms_wait_batch and can be re-run through ms_process_batch_host.
- * The slot's kernel chain (K1 .. K6, ~47 launches, no host round trip) is captured into a CUDA graph on the second call with
+ * The slot's kernel chain (K1 .. K6, 42 launches, no host round trip) is captured into a CUDA graph on the second call with
  * the same (w, hgt, batch) and replayed afterwards -- what the reference does for its inference (cudaGraphLaunch,
  * src/process.cpp:147); a change of shape or any buffer reallocation drops the graph.  MEDSEG_GRAPH=0 disables it. */
 MS_API int ms_submit_batch_host(ms_handle* h, int slot, const uint16_t* h_src, int w, int hgt, int batch);
