@@ -6,6 +6,8 @@
 #include <algorithm>
 #include <cstdint>
 #include <cstdio>
+#include <mutex>
+#include <set>
 #include <string>
 #include <vector>
 
@@ -49,6 +51,21 @@ extern thread_local LaunchCounter* g_counter;
         if (::ms::g_counter) ::ms::g_counter->n++;                                                  \
         MS_CUDA(cudaGetLastError());                                                                \
     } while (0)
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-device property of a kernel: set it once per (kernel, device), so
+// several handles on different GPUs of one process all get it (thread-safe).
+template <class Kernel>
+inline void set_max_dynamic_smem(Kernel kernel, int bytes) {
+    static std::mutex mu;
+    static std::set<std::pair<const void*, int>> done;
+    int dev = 0;
+    MS_CUDA(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lock(mu);
+    const auto key = std::make_pair(reinterpret_cast<const void*>(kernel), dev);
+    if (done.count(key)) return;
+    MS_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    done.insert(key);
+}
 
 static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 static inline int64_t cdiv64(int64_t a, int64_t b) { return (a + b - 1) / b; }

@@ -947,11 +947,7 @@ void launch_trace(M2pWs& ws, PolyDev& P, TraceMode mode, int h, int w, int batch
     long long* header = P.header.as<long long>();
     const long long cap_chunks = chunk_capacity(P);
     if (mode == kTraceRank) {
-        static bool attr = false;
-        if (!attr) {
-            MS_CUDA(cudaFuncSetAttribute(srank::rank_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kRankSmemMax));
-            attr = true;
-        }
+        set_max_dynamic_smem(srank::rank_smem_kernel, (int)kRankSmemMax);
         const int cap_border = rank_border_capacity(h, w);
         const size_t smem = (size_t)(h + 2) * (wpitch + 2) * 4 + (((size_t)h * wpitch + 1) & ~(size_t)1) * 2 + 16 +
                             (size_t)cap_border * srank::kBytesPerBorder;
@@ -960,11 +956,7 @@ void launch_trace(M2pWs& ws, PolyDev& P, TraceMode mode, int h, int w, int batch
                                                           header, (int)P.cap_contours, P.npts.as<int>(), P.chunks.as<int2>(),
                                                           P.chunk_meta.as<int2>(), cap_chunks, ws.crack_contour.as<int>(), cap_border);
     } else if (mode == kTraceSmem) {
-        static bool attr = false;
-        if (!attr) {
-            MS_CUDA(cudaFuncSetAttribute(trace_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTraceSmemMax));
-            attr = true;
-        }
+        set_max_dynamic_smem(trace_smem_kernel, (int)kTraceSmemMax);
         trace_smem_kernel<<<batch, 128, trace_smem, st>>>(ws.fgbits.as<uint32_t>(), h, w, wpitch, P.starts.as<int>(), P.slice_start.as<int>(),
                                                          header, (int)P.cap_contours, P.npts.as<int>(), P.chunks.as<int2>(),
                                                          P.chunk_meta.as<int2>(), cap_chunks);

@@ -248,11 +248,7 @@ void make_wgt_map(CUtensorMap* m, const __nv_bfloat16* base, int N, int K, int b
 template <int BN, int EPI>
 void launch_tc(const UNetLayer& L, const tc::ConvArgs& a, int sm_count, cudaStream_t st) {
     using C = tc::Cfg<BN>;
-    static bool attr_set = false;
-    if (!attr_set) {
-        MS_CUDA(cudaFuncSetAttribute(tc::conv_gemm_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
-        attr_set = true;
-    }
+    set_max_dynamic_smem(tc::conv_gemm_kernel<BN, EPI>, C::SMEM_BYTES);
     const int total = a.batch * (a.H / tc::TILE_H) * (a.W / tc::TILE_W) * (a.n_total / BN);
     const int grid = std::min(total, sm_count);
     tc::conv_gemm_kernel<BN, EPI><<<grid, tc::NUM_THREADS, C::SMEM_BYTES, st>>>(L.map_a, L.map_b, L.map_out, a);
@@ -262,11 +258,7 @@ void launch_tc(const UNetLayer& L, const tc::ConvArgs& a, int sm_count, cudaStre
 template <int BN, int EPI, int RKC, int PITCH>
 void launch_halo_p(const UNetLayer& L, const tc::ConvArgs& a, int sm_count, cudaStream_t st) {
     using C = tc::HaloCfg<BN, RKC, PITCH>;
-    static bool attr_set = false;
-    if (!attr_set) {
-        MS_CUDA(cudaFuncSetAttribute(tc::conv_halo_kernel<BN, EPI, RKC, PITCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
-        attr_set = true;
-    }
+    set_max_dynamic_smem(tc::conv_halo_kernel<BN, EPI, RKC, PITCH>, C::SMEM_BYTES);
     const int total = a.batch * (a.H / tc::HALO_TH) * (a.W / tc::HALO_TW);
     const int grid = std::min(total, sm_count);
     tc::conv_halo_kernel<BN, EPI, RKC, PITCH><<<grid, tc::NUM_THREADS, C::SMEM_BYTES, st>>>(L.map_a_row, L.map_b, L.map_out, a);
@@ -280,11 +272,7 @@ void launch_halo(const UNetLayer& L, const tc::ConvArgs& a, int sm_count, cudaSt
 template <int BN, int EPI, int RKC>
 void launch_halo2(const UNetLayer& L, const tc::ConvArgs& a, int sm_count, cudaStream_t st) {
     using C = tc::Halo2Cfg<BN, RKC>;
-    static bool attr_set = false;
-    if (!attr_set) {
-        MS_CUDA(cudaFuncSetAttribute(tc::conv_halo2_kernel<BN, EPI, RKC>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
-        attr_set = true;
-    }
+    set_max_dynamic_smem(tc::conv_halo2_kernel<BN, EPI, RKC>, C::SMEM_BYTES);
     const int pairs = a.batch * (a.H / tc::HALO_TH) * (a.W / tc::HALO_TW) / 2 * (a.n_total / BN);
     const int grid = 2 * std::min(pairs, sm_count / 2);
     tc::conv_halo2_kernel<BN, EPI, RKC><<<grid, tc::HALO2_THREADS, C::SMEM_BYTES, st>>>(L.map_a_row, L.map_b_half, L.map_out, a);
