@@ -88,3 +88,26 @@ def test_other_net_sizes_whole_path(ms, tmp_path, net_h, net_w):
         ref = op.map_contour_points(op.extract_contours(op.mask_to_image(clean[i])), 640 / net_w, 400 / net_h)
         assert contours_equal(polys.slice(i), ref), i
     eng.cleanup()
+
+
+def test_two_devices_in_one_process(ms, blob3):
+    """One handle per GPU inside ONE process: same results on both devices, calls interleaved."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    from medseg_b200 import synth
+    engs = [ms.Engine({"weights": blob3, "max_batch": 4, "device": d}) for d in (0, 1)]
+    vols = [synth.ct_volume(4, first_seed=500 + 4 * i) for i in range(3)]
+    res = [[], []]
+    for v in vols:
+        for d in (1, 0):
+            res[d].append(engs[d].process_batch(v)[0])
+    for a, b in zip(res[0], res[1]):
+        assert a.n_contours == b.n_contours and (a.xy == b.xy).all() and (a.contour_start == b.contour_start).all()
+    for d in (0, 1):                       # the asynchronous (graph) path too
+        for i in range(4):
+            engs[d].submit_batch(i % 2, vols[i % 3])
+            got = engs[d].wait_batch(i % 2)
+            assert (got.xy == res[d][i % 3].xy).all()
+    for e in engs:
+        e.cleanup()
