@@ -22,6 +22,8 @@ struct UNetLayer {
     float* bias = nullptr;       // device [Cout] fp32
     CUtensorMap map_a, map_b;
     CUtensorMap map_b_half;      // cta_group::2 kernel: box {64 k, block_n / 2 rows}
+    CUtensorMap map_b_half_alt;  // same for the small-batch tiling (block_n_alt / 2 rows)
+    int block_n_alt = 0;         // 0 = none; 128 = deep layers switch to 128-wide N tiles when 256-wide ones cannot fill a wave
     CUtensorMap map_out;         // TMA store of the epilogue (one epilogue warp's 32-pixel x 64-channel slab)
     CUtensorMap map_a_row;       // halo kernel: box {64 ch, 10 px, 18 rows}
     int halo = 0;                // 0 = per-tap streaming kernel, 1 = halo-stationary kernel, 2 = its cta_group::2 version
