@@ -209,6 +209,12 @@ MS_API int64_t ms_launch_count(ms_handle* h);
  * events; `flops` receives the layer's 2*MAC count for `batch` slices.  For roofline reporting. */
 MS_API int ms_time_layer(ms_handle* h, int layer, int batch, int iters, float* ms_per_launch, double* flops);
 MS_API int ms_layer_count(ms_handle* h);
+/* In-step layer timing: after ms_profile_layers_begin(h, n) the next n UNet forward passes of the eager entry points
+ * (ms_unet_forward_*, ms_process_batch_host/_dev; not the graph-replayed ms_submit_batch_host) bracket every layer launch
+ * with CUDA events on the launching stream.  ms_profile_layers_read waits for them, returns the average milliseconds per
+ * layer (ms_layer_count entries) and the number of passes recorded, and switches the timing off again. */
+MS_API int ms_profile_layers_begin(ms_handle* h, int max_forwards);
+MS_API int ms_profile_layers_read(ms_handle* h, float* ms_per_layer, int n_layers, int* n_forwards);
 MS_API const char* ms_layer_name(ms_handle* h, int layer);
 /* Kernel instantiation that layer runs on (as ncu prints it), valid until the next call on this thread. */
 MS_API const char* ms_layer_kernel(ms_handle* h, int layer);

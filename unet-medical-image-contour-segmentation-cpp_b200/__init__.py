@@ -79,6 +79,8 @@ ABI = {
     "ms_launch_count": (_L, [_P]),
     "ms_time_layer": (_I, [_P, _I, _I, _I, C.POINTER(C.c_float), C.POINTER(C.c_double)]),
     "ms_layer_count": (_I, [_P]),
+    "ms_profile_layers_begin": (_I, [_P, _I]),
+    "ms_profile_layers_read": (_I, [_P, C.POINTER(C.c_float), _I, C.POINTER(_I)]),
     "ms_layer_name": (C.c_char_p, [_P, _I]),
     "ms_layer_kernel": (C.c_char_p, [_P, _I]),
     "ms_debug_read_activation": (_L, [_P, C.c_char_p, _I, _P, _L]),
@@ -350,6 +352,18 @@ class Engine:
 
     def layer_names(self) -> List[str]:
         return [self._l.ms_layer_name(self._h, i).decode() for i in range(self._l.ms_layer_count(self._h))]
+
+    def profile_layers_begin(self, max_forwards: int) -> None:
+        """Bracket every layer launch of the next `max_forwards` eager forward passes with CUDA events."""
+        self._check(self._l.ms_profile_layers_begin(self._h, max_forwards))
+
+    def profile_layers_read(self):
+        """-> (average ms per layer, number of passes recorded); switches the timing off."""
+        n = self._l.ms_layer_count(self._h)
+        buf = (C.c_float * n)()
+        passes = _I(0)
+        self._check(self._l.ms_profile_layers_read(self._h, buf, n, C.byref(passes)))
+        return [float(v) for v in buf], passes.value
 
     def layer_kernels(self) -> List[str]:
         """Kernel instantiation each UNet layer runs on (as ncu prints it)."""

@@ -1009,6 +1009,26 @@ int ms_time_layer(ms_handle* h, int layer, int batch, int iters, float* ms_per_l
     });
 }
 
+int ms_profile_layers_begin(ms_handle* h, int max_forwards) {
+    if (!h) return MS_ERR_ARG;
+    return guarded(h, [&] {
+        MS_REQUIRE(h->unet.loaded(), MS_ERR_STATE, "no weights loaded");
+        MS_REQUIRE(max_forwards >= 0 && max_forwards <= 4096, MS_ERR_ARG, "profile_layers_begin: bad argument");
+        h->unet.profile_begin(max_forwards);
+    });
+}
+int ms_profile_layers_read(ms_handle* h, float* ms_per_layer, int n_layers, int* n_forwards) {
+    if (!h) return MS_ERR_ARG;
+    return guarded(h, [&] {
+        MS_REQUIRE(h->unet.loaded(), MS_ERR_STATE, "no weights loaded");
+        MS_REQUIRE(ms_per_layer && n_layers == (int)h->unet.layers().size(), MS_ERR_ARG, "profile_layers_read: bad argument");
+        std::vector<float> v;
+        const int passes = h->unet.profile_read(v);
+        std::copy(v.begin(), v.end(), ms_per_layer);
+        if (n_forwards) *n_forwards = passes;
+    });
+}
+
 int64_t ms_debug_read_activation(ms_handle* h, const char* name, int batch, float* h_dst, int64_t cap) {
     if (!h || !name) return MS_ERR_ARG;
     int64_t result = 0;

@@ -330,6 +330,7 @@ Blob read_blob(const std::string& path) {
 }  // namespace
 
 UNet::~UNet() {
+    for (cudaEvent_t e : prof_events_) cudaEventDestroy(e);
     for (void* p : allocs_) cudaFree(p);
     scratch_mask_.release();
 }
@@ -619,7 +620,45 @@ void UNet::run_layer(int li, const uint8_t* d_in_u8, int batch, uint8_t* d_mask,
 }
 
 void UNet::forward(const uint8_t* d_in_u8, int batch, uint8_t* d_mask, float* d_logits, cudaStream_t st) {
-    for (int i = 0; i < (int)layers_.size(); ++i) run_layer(i, d_in_u8, batch, d_mask, d_logits, st);
+    const int n = (int)layers_.size();
+    cudaEvent_t* ev = prof_n_ < prof_cap_ ? prof_events_.data() + (size_t)prof_n_ * (n + 1) : nullptr;
+    for (int i = 0; i < n; ++i) {
+        if (ev) MS_CUDA(cudaEventRecord(ev[i], st));
+        run_layer(i, d_in_u8, batch, d_mask, d_logits, st);
+    }
+    if (ev) {
+        MS_CUDA(cudaEventRecord(ev[n], st));
+        ++prof_n_;
+    }
+}
+
+void UNet::profile_begin(int max_forwards) {
+    const size_t need = (size_t)std::max(0, max_forwards) * (layers_.size() + 1);
+    while (prof_events_.size() < need) {
+        cudaEvent_t e;
+        MS_CUDA(cudaEventCreate(&e));
+        prof_events_.push_back(e);
+    }
+    prof_cap_ = std::max(0, max_forwards);
+    prof_n_ = 0;
+}
+
+int UNet::profile_read(std::vector<float>& ms_per_layer) {
+    const int n = (int)layers_.size(), passes = prof_n_;
+    ms_per_layer.assign(n, 0.0f);
+    for (int f = 0; f < passes; ++f) {
+        cudaEvent_t* ev = prof_events_.data() + (size_t)f * (n + 1);
+        MS_CUDA(cudaEventSynchronize(ev[n]));
+        for (int i = 0; i < n; ++i) {
+            float ms = 0;
+            MS_CUDA(cudaEventElapsedTime(&ms, ev[i], ev[i + 1]));
+            ms_per_layer[i] += ms;
+        }
+    }
+    for (float& v : ms_per_layer) v = passes ? v / passes : 0.0f;
+    prof_cap_ = 0;
+    prof_n_ = 0;
+    return passes;
 }
 
 }  // namespace ms

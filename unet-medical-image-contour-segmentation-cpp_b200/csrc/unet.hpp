@@ -63,8 +63,14 @@ class UNet {
     int net_w() const { return W_; }
     int max_batch() const { return max_batch_; }
     uint8_t* scratch_mask() { return scratch_mask_.as<uint8_t>(); }
+    // In-step layer timing: while enabled, forward() brackets every layer launch with CUDA events (up to `max_forwards`
+    // passes); profile_read() waits for them and returns the average milliseconds per layer and the number of passes.
+    void profile_begin(int max_forwards);
+    int profile_read(std::vector<float>& ms_per_layer);
 
   private:
+    std::vector<cudaEvent_t> prof_events_;   // [pass][layer + 1]
+    int prof_cap_ = 0, prof_n_ = 0;          // passes: capacity / recorded
     bool loaded_ = false;
     int H_ = 0, W_ = 0, n_classes_ = 0, max_batch_ = 0, fg_value_ = 2, sm_count_ = 148;
     bool naive_ = false;  // MEDSEG_NAIVE_CONV=1: CUDA-core reference kernels (debug / validation only)
