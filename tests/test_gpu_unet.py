@@ -213,6 +213,20 @@ def test_process_directory_matches_per_file(unet_engine, ms, tmp_path):
     assert unet_engine.process_raw_files([], 576, 448, str(tmp_path)).tolist() == []
 
 
+def test_layer_profile_api(unet_engine, ms):
+    """ms_profile_layers_*: CUDA events around every layer launch of the next n eager forward passes."""
+    vol = _slices(ms, 2, first=5)
+    unet_engine.profile_layers_begin(3)
+    for _ in range(4):                               # the fourth pass is not recorded
+        unet_engine.process_batch(vol)
+    ms_l, passes = unet_engine.profile_layers_read()
+    assert passes == 3 and len(ms_l) == len(unet_engine.layer_names()) == len(unet_engine.layer_kernels()) == 22
+    assert all(0.0 < v < 50.0 for v in ms_l)
+    assert unet_engine.layer_kernels()[0] == "first_conv_kernel" and "EPI_HEAD" in unet_engine.layer_kernels()[-1]
+    assert unet_engine.profile_layers_read()[1] == 0  # switched off again
+    unet_engine.process_batch(vol)
+
+
 def test_log_file(ms, blob3, tmp_path):
     from medseg_b200 import synth
     e = ms.Engine(blob3, str(tmp_path / "log"))
