@@ -573,7 +573,14 @@ struct SliceJob {
     int slot = -1;               // index inside its batch (-1: never reached the GPU)
 };
 // the five artefacts of src/process.cpp:207-242 / src/mask2polygon.cpp:134-222 for one slice
-void write_artefacts(SliceJob& J, const BatchHost& B, int w, int hgt, int net_w, int net_h, int fg_value) {
+// `spare_threads` > 0 (fewer slices than writer threads, e.g. the single-file call): the two grey PNGs are encoded by helper
+// threads while this one draws and encodes the overlay.
+void write_artefacts(SliceJob& J, const BatchHost& B, int w, int hgt, int net_w, int net_h, int fg_value, int spare_threads = 0) {
+    std::thread helper_norm, helper_mask;
+    auto join_helpers = [&] {
+        if (helper_norm.joinable()) helper_norm.join();
+        if (helper_mask.joinable()) helper_mask.join();
+    };
     try {
         const size_t npx = (size_t)net_w * net_h;
         const uint8_t* norm = B.norm.as<uint8_t>() + (size_t)J.slot * npx;
@@ -585,16 +592,25 @@ void write_artefacts(SliceJob& J, const BatchHost& B, int w, int hgt, int net_w,
         const std::string png_path = J.dir + "/" + J.base + "_normalized.png";                 // src/process.cpp:207
         const std::string sizes_path = J.dir + "/" + J.base + "_original_sizes.json";          // :208
         const std::string mask_path = J.dir + "/" + J.base + "_mask.png";                      // :209
-        // src/preprocess.cpp:121-134
-        MS_REQUIRE(png::write_file(png_path, norm, net_w, net_h, 1), MS_ERR_IO, "imwrite failed: " + png_path);
-        {
+        bool ok_norm = true, ok_mask = true;
+        auto write_norm = [&] { ok_norm = png::write_file(png_path, norm, net_w, net_h, 1); };                  // src/preprocess.cpp:121-122
+        auto write_mask = [&] {
+            std::vector<uint8_t> vis(npx);
+            for (size_t i = 0; i < npx; ++i) vis[i] = mask[i] == 1 ? 128 : (mask[i] == 2 ? 255 : (mask[i] == fg_value ? 255 : 0));  // src/process.cpp:178-185
+            ok_mask = png::write_file(mask_path, vis.data(), net_w, net_h, 1);                                  // :236-239
+        };
+        if (spare_threads >= 2) {
+            helper_norm = std::thread(write_norm);
+            helper_mask = std::thread(write_mask);
+        } else {
+            write_norm();
+            write_mask();
+        }
+        {   // src/preprocess.cpp:126-134
             std::ofstream jf(sizes_path, std::ios::binary);
             MS_REQUIRE(jf.good(), MS_ERR_IO, "cannot write " + sizes_path);
             jf << json::sidecar_text(basename_of(J.raw), w, hgt, net_w, net_h);
         }
-        std::vector<uint8_t> vis(npx);
-        for (size_t i = 0; i < npx; ++i) vis[i] = mask[i] == 1 ? 128 : (mask[i] == 2 ? 255 : (mask[i] == fg_value ? 255 : 0));  // :178-185
-        MS_REQUIRE(png::write_file(mask_path, vis.data(), net_w, net_h, 1), MS_ERR_IO, "Failed to save mask");   // :236-239
         out << "Processing Mask: " << J.base + ".png" << "\n";                                // src/mask2polygon.cpp:141
         out << "Original Size: " << w << "x" << hgt << "\n";                                  // :162
         out << "Scaled Size: " << net_w << "x" << net_h << "\n";                              // :163
@@ -615,11 +631,16 @@ void write_artefacts(SliceJob& J, const BatchHost& B, int w, int hgt, int net_w,
             f << json::labelme_text(B.xy.data(), cstart, nc, J.base, w, hgt);                  // :207
             out << "JSON Saved to: " << out_json << "\n";                                     // :208
         }
+        join_helpers();
+        MS_REQUIRE(ok_norm, MS_ERR_IO, "imwrite failed: " + png_path);
+        MS_REQUIRE(ok_mask, MS_ERR_IO, "Failed to save mask");
         J.console = out.str();
     } catch (const Error& e) {
+        join_helpers();
         J.status = e.code;
         J.error = e.what;
     } catch (const std::exception& e) {
+        join_helpers();
         J.status = MS_ERR_INTERNAL;
         J.error = e.what();
     }
@@ -732,10 +753,11 @@ void process_jobs(ms_handle* h, std::vector<SliceJob>& jobs, int w, int hgt, boo
             if (k > 0) report(k - 1, infer_ms[(k - 1) & 1]);
             next_job = r.first;
             const int nt = std::min<int>(writer_threads(), std::max(nb, 1));
+            const int spare = writer_threads() / std::max(nb, 1) - 1;   // helper threads each slice may use
             for (int t = 0; t < nt; ++t)
-                writers.emplace_back([&, r, k] {
+                writers.emplace_back([&, r, k, spare] {
                     for (size_t i = next_job.fetch_add(1); i < r.second; i = next_job.fetch_add(1))
-                        if (jobs[i].slot >= 0) write_artefacts(jobs[i], host[k & 1], w, hgt, h->net_w, h->net_h, h->fg_value);
+                        if (jobs[i].slot >= 0) write_artefacts(jobs[i], host[k & 1], w, hgt, h->net_w, h->net_h, h->fg_value, spare);
                 });
             if (reader.joinable()) reader.join();
         }
