@@ -60,7 +60,7 @@ def test_cfg4_1024_four_labels_per_class_contours(ms, tmp_path):
     eng.cleanup()
 
 
-@pytest.mark.parametrize("net_h,net_w", [(128, 256), (256, 512), (384, 256)])
+@pytest.mark.parametrize("net_h,net_w", [(128, 256), (256, 512), (384, 256), (128, 1536)])
 def test_other_net_sizes_whole_path(ms, tmp_path, net_h, net_w):
     """Configurable network size (multiples of 128 x 256): the smallest net has ONE 8 x 16 tile at
     the bottleneck, non-square nets exercise the tile decomposition; logits vs the fp32 oracle, then the integer stages

@@ -551,10 +551,14 @@ void UNet::run_layer(int li, const uint8_t* d_in_u8, int batch, uint8_t* d_mask,
     if (L.kind == 0) {
         const unsigned grid = (unsigned)(batch * h / kFirstRows);
         const size_t smem = (kFirstRows + 2) * (w + 2) * sizeof(float);
-        if (w % 16 == 0 && (reinterpret_cast<uintptr_t>(d_in_u8) & 15) == 0)
+        MS_REQUIRE(smem <= 200 * 1024, MS_ERR_ARG, "network width too large for the first-conv row buffer");
+        if (w % 16 == 0 && (reinterpret_cast<uintptr_t>(d_in_u8) & 15) == 0) {
+            if (smem > 48 * 1024) set_max_dynamic_smem(first_conv_kernel<true>, 200 * 1024);   // nets wider than ~1200 px
             first_conv_kernel<true><<<grid, 256, smem, st>>>(d_in_u8, h, w, L.w_f32, L.bias, bufs_[L.dst].p);
-        else
+        } else {
+            if (smem > 48 * 1024) set_max_dynamic_smem(first_conv_kernel<false>, 200 * 1024);
             first_conv_kernel<false><<<grid, 256, smem, st>>>(d_in_u8, h, w, L.w_f32, L.bias, bufs_[L.dst].p);
+        }
         MS_LAUNCH_CHECK();
         return;
     }
