@@ -354,17 +354,24 @@ __device__ __forceinline__ void epilogue_tile(const ConvArgs& args, const float*
                 const int l0 = (q % (TW / 2)) * 2 + (q / (TW / 2)) * 2 * TW;
                 const int px = e.x0 + (l0 % TW), py = e.y0 + e.slab_y + (l0 / TW);
                 uint4* dst = reinterpret_cast<uint4*>(args.pool + (((size_t)e.b * (args.H / 2) + (py >> 1)) * (args.W / 2) + (px >> 1)) * args.pool_cstride + col);
+                uint4 v[2][4];     // all eight loads first: one exposed shared-memory latency, not two
 #pragma unroll
                 for (int it = 0; it < 2; ++it) {
                     const int j = (e.lane & 3) * 2 + it;
-                    uint4 m = make_uint4(0u, 0u, 0u, 0u);   // post-ReLU values are >= +0
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {
                         const int row = l0 + (k & 1) + (k >> 1) * TW;
-                        const uint4 v = ld_shared_v4(e.slab + (uint32_t)row * 128u + (uint32_t)((j ^ (row & 7)) << 4));
-                        m.x = max_bf16x2(m.x, v.x); m.y = max_bf16x2(m.y, v.y); m.z = max_bf16x2(m.z, v.z); m.w = max_bf16x2(m.w, v.w);
+                        v[it][k] = ld_shared_v4(e.slab + (uint32_t)row * 128u + (uint32_t)((j ^ (row & 7)) << 4));
                     }
-                    dst[j] = m;
+                }
+#pragma unroll
+                for (int it = 0; it < 2; ++it) {
+                    uint4 m;
+                    m.x = max_bf16x2(max_bf16x2(v[it][0].x, v[it][1].x), max_bf16x2(v[it][2].x, v[it][3].x));
+                    m.y = max_bf16x2(max_bf16x2(v[it][0].y, v[it][1].y), max_bf16x2(v[it][2].y, v[it][3].y));
+                    m.z = max_bf16x2(max_bf16x2(v[it][0].z, v[it][1].z), max_bf16x2(v[it][2].z, v[it][3].z));
+                    m.w = max_bf16x2(max_bf16x2(v[it][0].w, v[it][1].w), max_bf16x2(v[it][2].w, v[it][3].w));
+                    dst[(e.lane & 3) * 2 + it] = m;
                 }
             }
         }
