@@ -81,3 +81,35 @@ def json_cases():
         "two": ("vol-1.slice_2", 1024, 768, [[(0, 0)], [(5, 6), (7, 8), (9, 10)]]),
         "none": ("empty", 64, 64, []),
     }
+
+
+# scale factors (orig / scaled) for map_contour_points: identity, up, down, non-representable ratios
+MAP_SCALES = [(1.0, 1.0), (600 / 512, 400 / 512), (2048 / 512, 1536 / 512), (333 / 512, 517 / 512), (1000 / 48, 7 / 3)]
+
+
+def ref_mask_cases():
+    """512 x 512 class masks {0,1,2}: a body with holes of both background classes, border-touching holes, small blobs
+    on either side of the 6 % area threshold (15,728 px), 1-2 px bridges that the 3 x 3 open cuts."""
+    rng = np.random.default_rng(31337)
+    out = []
+    yy, xx = np.mgrid[0:512, 0:512]
+    for k in range(4):
+        m = np.zeros((512, 512), np.uint8)
+        cy, cx = 256 + rng.normal(0, 12), 256 + rng.normal(0, 12)
+        m[((yy - cy) / 170) ** 2 + ((xx - cx) / 215) ** 2 < 1] = 2
+        for _ in range(10):                                     # holes of class 0 / 1 inside the body
+            hy, hx, r = rng.integers(120, 390), rng.integers(100, 410), rng.integers(2, 70)
+            m[(yy - hy) ** 2 + (xx - hx) ** 2 < r * r] = rng.integers(0, 2)
+        for _ in range(6):                                      # blobs around the area threshold: r ~ 71 px <-> 15.7 k px
+            by, bx, r = rng.integers(30, 480), rng.integers(30, 480), rng.integers(3, 80)
+            m[(yy - by) ** 2 + (xx - bx) ** 2 < r * r] = 2
+        m[200 + 10 * k:202 + 10 * k, :] = 2                      # a 2-px bar across the image (erased by the open, cut at the body)
+        sp = rng.random((512, 512))
+        m[sp < 0.01] = 0
+        m[sp > 0.99] = 2
+        m[(sp > 0.50) & (sp < 0.505)] = 1
+        if k == 3:
+            m[:, :3] = 2                                        # foreground hugging the left edge
+            m[0:40, 100:140] = 0
+        out.append(m)
+    return out
