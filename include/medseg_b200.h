@@ -154,16 +154,22 @@ MS_API int ms_process_batch_host(ms_handle* h, const uint16_t* h_src, int w, int
                                  ms_polygons* out, uint8_t* h_norm_u8, uint8_t* h_mask_u8);
 
 /* Device-resident variant used for kernel-only timing: input already in HBM, polygons stay in the
- * handle's device workspace; only the two totals are read back at the end. */
+ * handle's device workspace.  With n_points / n_contours given the call waits for the two totals (and grows the
+ * device polygon capacities when the batch needed more); with both NULL it is fully asynchronous on `stream` -- no
+ * host round trip, the 32-byte result header lands in pinned memory behind the kernels -- and ms_last_counts
+ * collects it later (MS_ERR_CAPACITY there = the workspace was too small for that batch and has been grown). */
 MS_API int ms_process_batch_dev(ms_handle* h, const uint16_t* d_src, int w, int hgt, int batch,
                                 int64_t* n_points, int64_t* n_contours, void* stream);
+MS_API int ms_last_counts(ms_handle* h, int64_t* n_points, int64_t* n_contours);
 
 /* Asynchronous, double-buffered form of ms_process_batch_host for streaming a volume (the serial per-file loop at
  * src/main.cpp:148-164): submit batch i+1 on the other slot before collecting batch i, and the H2D copy of i+1 and
  * the host-side collection of i overlap the GPU work.  slot is 0 or 1.  h_src should be pinned (ms_alloc_pinned);
- * it must stay valid until the matching ms_wait_batch returns.  Polygon capacities are fixed per slot
- * (64 contours and 8,192 points per slice on average); a batch that exceeds them fails with MS_ERR_CAPACITY in
- * ms_wait_batch and can be re-run through ms_process_batch_host.
+ * it must stay valid until the matching ms_wait_batch returns.  Device-side polygon capacities start at
+ * max(64, 1 / min_area_ratio + 1) contours and 8,192 points per slice; a batch that exceeds them is re-run inside
+ * ms_wait_batch on the slot's still-resident input with grown buffers (the call still succeeds).  The D2H issued behind
+ * the kernels is sized from the slot's previous batch (+25 %); ms_wait_batch fetches a remainder only when needed, so the
+ * bytes copied track the bytes used (ms_get_transfer_bytes reports them).
  * The slot's kernel chain (K1 .. K6, 42 launches, no host round trip) is captured into a CUDA graph on the second call with
  * the same (w, hgt, batch) and replayed afterwards -- what the reference does for its inference (cudaGraphLaunch,
  * src/process.cpp:147); a change of shape or any buffer reallocation drops the graph.  MEDSEG_GRAPH=0 disables it. */
@@ -204,6 +210,10 @@ MS_API int64_t ms_polygons_to_json(const int32_t* xy, const int32_t* contour_sta
 /* Number of kernels this library launched on the handle since creation (bench.py `gpu_launches`). */
 MS_API int64_t ms_launch_count(ms_handle* h);
 
+/* Bytes this handle has copied host->device / device->host with its own transfers since creation (bench.py reports
+ * the per-step difference as e2e.h2d_bytes_per_step / d2h_bytes_per_step: what was copied, not what was useful). */
+MS_API int ms_get_transfer_bytes(ms_handle* h, int64_t* h2d_bytes, int64_t* d2h_bytes);
+
 /* Run only UNet conv layer `layer` (0-based index into the layer table, see ms_layer_name) `iters`
  * times on the handle's stream and return the average milliseconds per launch measured with CUDA
  * events; `flops` receives the layer's 2*MAC count for `batch` slices.  For roofline reporting. */
@@ -215,6 +225,9 @@ MS_API int ms_layer_count(ms_handle* h);
  * layer (ms_layer_count entries) and the number of passes recorded, and switches the timing off again. */
 MS_API int ms_profile_layers_begin(ms_handle* h, int max_forwards);
 MS_API int ms_profile_layers_read(ms_handle* h, float* ms_per_layer, int n_layers, int* n_forwards);
+/* Same switch, stage granularity: average milliseconds of K1 preprocess | UNet | K5 postprocess | K6 mask2polygon
+ * (ms4[0..3]) over the passes of ms_process_batch_host/_dev recorded since ms_profile_layers_begin. */
+MS_API int ms_profile_stages_read(ms_handle* h, float* ms4, int* n_passes);
 MS_API const char* ms_layer_name(ms_handle* h, int layer);
 /* Kernel instantiation that layer runs on (as ncu prints it), valid until the next call on this thread. */
 MS_API const char* ms_layer_kernel(ms_handle* h, int layer);

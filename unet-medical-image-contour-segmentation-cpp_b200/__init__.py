@@ -70,6 +70,8 @@ ABI = {
     "ms_mask2polygon_dev": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, C.POINTER(ms_polygons), _P]),
     "ms_process_batch_host": (_I, [_P, _P, _I, _I, _I, C.POINTER(ms_polygons), _P, _P]),
     "ms_process_batch_dev": (_I, [_P, _P, _I, _I, _I, C.POINTER(_L), C.POINTER(_L), _P]),
+    "ms_last_counts": (_I, [_P, C.POINTER(_L), C.POINTER(_L)]),
+    "ms_get_transfer_bytes": (_I, [_P, C.POINTER(_L), C.POINTER(_L)]),
     "ms_submit_batch_host": (_I, [_P, _I, _P, _I, _I, _I]),
     "ms_wait_batch": (_I, [_P, _I, C.POINTER(ms_polygons)]),
     "ms_process_raw_file": (_I, [_P, C.c_char_p, _I, _I, C.c_char_p]),
@@ -81,6 +83,7 @@ ABI = {
     "ms_layer_count": (_I, [_P]),
     "ms_profile_layers_begin": (_I, [_P, _I]),
     "ms_profile_layers_read": (_I, [_P, C.POINTER(C.c_float), _I, C.POINTER(_I)]),
+    "ms_profile_stages_read": (_I, [_P, C.POINTER(C.c_float), C.POINTER(_I)]),
     "ms_layer_name": (C.c_char_p, [_P, _I]),
     "ms_layer_kernel": (C.c_char_p, [_P, _I]),
     "ms_debug_read_activation": (_L, [_P, C.c_char_p, _I, _P, _L]),
@@ -337,10 +340,27 @@ class Engine:
     def postprocess_dev(self, d_in: int, d_out: int, h: int, w: int, batch: int, fg_value: int = 0, stream: int = 0):
         self._check(self._l.ms_postprocess_dev(self._h, d_in, d_out, h, w, batch, fg_value, stream or None))
 
-    def process_batch_dev(self, d_src: int, w: int, h: int, batch: int, stream: int = 0):
+    def process_batch_dev(self, d_src: int, w: int, h: int, batch: int, stream: int = 0, wait: bool = True):
+        """Whole path on device-resident input.  wait=False: nothing is read back and the host does not block
+        (collect the totals later with last_counts())."""
+        if not wait:
+            self._check(self._l.ms_process_batch_dev(self._h, d_src, w, h, batch, None, None, stream or None))
+            return None
         npts, ncnt = _L(0), _L(0)
         self._check(self._l.ms_process_batch_dev(self._h, d_src, w, h, batch, C.byref(npts), C.byref(ncnt), stream or None))
         return npts.value, ncnt.value
+
+    def last_counts(self):
+        """(n_points, n_contours) of the last process_batch_dev(wait=False); waits for it."""
+        npts, ncnt = _L(0), _L(0)
+        self._check(self._l.ms_last_counts(self._h, C.byref(npts), C.byref(ncnt)))
+        return npts.value, ncnt.value
+
+    def transfer_bytes(self):
+        """(host->device, device->host) bytes this handle has copied since creation."""
+        a, b = _L(0), _L(0)
+        self._check(self._l.ms_get_transfer_bytes(self._h, C.byref(a), C.byref(b)))
+        return a.value, b.value
 
     def mask2polygon_dev(self, d_mask: int, h: int, w: int, batch: int, threshold: int = 127, stream: int = 0) -> Polygons:
         return self._poly_call(
@@ -364,6 +384,13 @@ class Engine:
         passes = _I(0)
         self._check(self._l.ms_profile_layers_read(self._h, buf, n, C.byref(passes)))
         return [float(v) for v in buf], passes.value
+
+    def profile_stages_read(self):
+        """-> ({"K1": ms, "unet": ms, "K5": ms, "K6": ms}, passes) recorded since profile_layers_begin."""
+        buf = (C.c_float * 4)()
+        passes = _I(0)
+        self._check(self._l.ms_profile_stages_read(self._h, buf, C.byref(passes)))
+        return dict(zip(("K1", "unet", "K5", "K6"), (float(v) for v in buf))), passes.value
 
     def layer_kernels(self) -> List[str]:
         """Kernel instantiation each UNet layer runs on (as ncu prints it)."""

@@ -74,10 +74,18 @@ static inline int64_t cdiv64(int64_t a, int64_t b) { return (a + b - 1) / b; }
 // replayed while the epoch it was captured under is still current.
 extern std::atomic<uint64_t> g_alloc_epoch;   // process-wide and monotonic, so a stale graph can never look current
 
+// Device-side pipeline watchdog (unet_conv_tc.cuh: mbar_wait): one word of mapped pinned host memory, process-wide.
+// A kernel whose mbarrier wait exceeded 20 s of wall time sets it; every C-ABI entry point checks it on return.
+unsigned* watchdog_host_word();        // allocates on first use (cudaHostAllocMapped | Portable); never freed
+
 // Simple growable device buffer (never shrinks; growth is outside any timed / captured region).
 struct DevBuf {
     void* p = nullptr;
     size_t cap = 0;
+    DevBuf() = default;
+    DevBuf(const DevBuf&) = delete;
+    DevBuf& operator=(const DevBuf&) = delete;
+    ~DevBuf() { release(); }     // RAII: a handle (or a half-initialised one) frees everything it reserved
     void reserve(size_t bytes) {
         if (bytes <= cap) return;
         ++g_alloc_epoch;
@@ -102,6 +110,10 @@ struct DevBuf {
 struct PinBuf {
     void* p = nullptr;
     size_t cap = 0;
+    PinBuf() = default;
+    PinBuf(const PinBuf&) = delete;
+    PinBuf& operator=(const PinBuf&) = delete;
+    ~PinBuf() { release(); }
     void reserve(size_t bytes) {
         if (bytes <= cap) return;
         if (p) MS_CUDA(cudaFreeHost(p));

@@ -32,6 +32,20 @@ static thread_local std::string t_last_error = "";
 
 void fail(int code, const std::string& what) { throw Error{code, what}; }
 
+unsigned* watchdog_host_word() {
+    static std::mutex mu;
+    static unsigned* word = nullptr;
+    std::lock_guard<std::mutex> lock(mu);
+    if (!word) {
+        void* p = nullptr;
+        MS_CUDA(cudaHostAlloc(&p, 64, cudaHostAllocMapped | cudaHostAllocPortable));
+        word = static_cast<unsigned*>(p);
+        *word = 0u;
+    }
+    return word;
+}
+static unsigned* g_watchdog_seen = nullptr;   // non-null once any handle loaded a UNet
+
 }  // namespace ms
 
 using namespace ms;
@@ -70,8 +84,11 @@ struct ms_handle {
         PolyDev poly;
         PinBuf h_src, h_header, h_slice_start, h_cstart, h_xy;
         cudaEvent_t ev_h2d = nullptr, ev_m2p = nullptr, ev_done = nullptr;
-        int batch = 0;
+        int batch = 0, w = 0, hgt = 0;
         bool busy = false;
+        // the D2H issued with the header is sized from the previous batch on this slot (+25 %); ms_wait_batch fetches the
+        // remainder only when a batch turned out larger, so the steady state copies ~what it uses, in one round trip
+        int64_t spec_contours = 0, spec_points = 0, last_contours = 0, last_points = 0;
         // CUDA graph of the slot's kernel chain (K1 .. K6), replayed while shape and buffers are unchanged
         cudaGraphExec_t gexec = nullptr;
         int g_w = 0, g_h = 0, g_batch = 0;      // shape the graph was captured for
@@ -96,6 +113,15 @@ struct ms_handle {
     }
     std::string last_error;
     LaunchCounter counter;
+    // bytes this handle moved over PCIe with its own copies (bench.py: e2e.h2d/d2h_bytes_per_step are read from here)
+    int64_t h2d_bytes = 0, d2h_bytes = 0;
+    // ms_process_batch_dev without result pointers: header lands in h_header asynchronously, ms_last_counts collects it
+    cudaEvent_t ev_header = nullptr;
+    bool header_pending = false;
+    // in-step stage timing (ms_profile_layers_begin switches it on together with the per-layer events): five events per
+    // pass of pipeline_dev -> K1 | UNet | K5 | K6
+    std::vector<cudaEvent_t> stage_events;
+    int stage_cap = 0, stage_n = 0;
 };
 
 namespace {
@@ -133,6 +159,15 @@ std::string read_text(const std::string& path) {
     return ss.str();
 }
 
+// An entry point that fails may have copies into CALLER memory (or kernels reading caller buffers) still in flight on the
+// handle's streams: wait for them before the error is reported, so the caller may free or reuse its buffers at once.
+void drain(ms_handle* h) {
+    if (!h) return;
+    for (cudaStream_t st : {h->stream, h->copy_stream, h->d2h_stream})
+        if (st) cudaStreamSynchronize(st);
+    cudaGetLastError();
+}
+
 template <class F>
 int guarded(ms_handle* h, F&& f) {
     try {
@@ -142,18 +177,23 @@ int guarded(ms_handle* h, F&& f) {
         }
         f();
         g_counter = nullptr;
+        if (g_watchdog_seen && *reinterpret_cast<volatile unsigned*>(g_watchdog_seen))
+            fail(MS_ERR_INTERNAL, "device pipeline watchdog expired (an mbarrier wait exceeded 20 s): results of this process are not trustworthy");
         return MS_OK;
     } catch (const Error& e) {
         g_counter = nullptr;
+        drain(h);
         (h ? h->last_error : t_last_error) = e.what;
         if (h) h->log("error: " + e.what);
         return e.code;
     } catch (const std::exception& e) {
         g_counter = nullptr;
+        drain(h);
         (h ? h->last_error : t_last_error) = e.what();
         return MS_ERR_INTERNAL;
     } catch (...) {
         g_counter = nullptr;
+        drain(h);
         (h ? h->last_error : t_last_error) = "unknown exception";
         return MS_ERR_INTERNAL;
     }
@@ -172,6 +212,7 @@ bool is_cuda_host_ptr(const void* p) {
 
 // H2D of caller memory: pinned -> direct async copy, pageable -> through the handle's pinned staging buffer.
 void upload(ms_handle* h, void* d_dst, const void* h_src, size_t bytes, cudaStream_t st) {
+    h->h2d_bytes += (int64_t)bytes;
     if (is_cuda_host_ptr(h_src)) {
         MS_CUDA(cudaMemcpyAsync(d_dst, h_src, bytes, cudaMemcpyHostToDevice, st));
     } else {
@@ -180,9 +221,12 @@ void upload(ms_handle* h, void* d_dst, const void* h_src, size_t bytes, cudaStre
         MS_CUDA(cudaMemcpyAsync(d_dst, h->staging.p, bytes, cudaMemcpyHostToDevice, st));
     }
 }
-void download_sync(ms_handle* h, void* h_dst, const void* d_src, size_t bytes, cudaStream_t st) {
-    (void)h;
+void download(ms_handle* h, void* h_dst, const void* d_src, size_t bytes, cudaStream_t st) {
+    h->d2h_bytes += (int64_t)bytes;
     MS_CUDA(cudaMemcpyAsync(h_dst, d_src, bytes, cudaMemcpyDeviceToHost, st));
+}
+void download_sync(ms_handle* h, void* h_dst, const void* d_src, size_t bytes, cudaStream_t st) {
+    download(h, h_dst, d_src, bytes, st);
     MS_CUDA(cudaStreamSynchronize(st));
 }
 
@@ -238,6 +282,7 @@ void finish_init(ms_handle* h, const char* log_dir) {
     if (!h->weights_path.empty()) {
         g_counter = &h->counter;
         h->unet.load(h->weights_path, h->net_h, h->net_w, h->n_classes_cfg, h->max_batch, h->fg_value, h->sm_count);
+        g_watchdog_seen = watchdog_host_word();
         h->log("UNet loaded: " + std::to_string(h->unet.n_params()) + " parameters, " +
                std::to_string(h->unet.flops_per_slice() / 1e9) + " GFLOP per slice, n_classes=" + std::to_string(h->unet.n_classes()));
     }
@@ -273,9 +318,9 @@ void copy_polygons_out(ms_handle* h, int batch, ms_polygons* out, cudaStream_t s
     out->n_points = hh[1];
     MS_REQUIRE(out->cap_contours >= hh[0] && out->cap_points >= hh[1], MS_ERR_CAPACITY,
                "polygon buffers too small: need " + std::to_string(hh[0]) + " contours, " + std::to_string(hh[1]) + " points");
-    MS_CUDA(cudaMemcpyAsync(out->slice_start, h->m2p.poly.slice_start.p, ((size_t)batch + 1) * 4, cudaMemcpyDeviceToHost, st));
-    MS_CUDA(cudaMemcpyAsync(out->contour_start, h->m2p.poly.npts.p, ((size_t)hh[0] + 1) * 4, cudaMemcpyDeviceToHost, st));
-    if (hh[1] > 0) MS_CUDA(cudaMemcpyAsync(out->xy, h->m2p.poly.xy.p, (size_t)hh[1] * 8, cudaMemcpyDeviceToHost, st));
+    download(h, out->slice_start, h->m2p.poly.slice_start.p, ((size_t)batch + 1) * 4, st);
+    download(h, out->contour_start, h->m2p.poly.npts.p, ((size_t)hh[0] + 1) * 4, st);
+    if (hh[1] > 0) download(h, out->xy, h->m2p.poly.xy.p, (size_t)hh[1] * 8, st);
     MS_CUDA(cudaStreamSynchronize(st));
 }
 
@@ -285,20 +330,58 @@ void check_polys(const ms_polygons* out, int batch) {
                MS_ERR_ARG, "ms_polygons: null buffer or negative capacity");
 }
 
-// device pipeline shared by the batch entry points; input u16 already at d_src
-void pipeline_dev(ms_handle* h, const uint16_t* d_src, int w, int hgt, int batch, cudaStream_t st) {
+// device pipeline shared by the batch entry points; input u16 already at d_src.  `sync` = false: one pass with the current
+// polygon capacities, the header is copied to pinned memory asynchronously and collected by ms_last_counts (no host
+// round trip inside the call); true: wait, and grow the capacities / re-run mask2polygon when they were too small.
+void pipeline_dev(ms_handle* h, const uint16_t* d_src, int w, int hgt, int batch, cudaStream_t st, bool sync = true) {
     MS_REQUIRE(h->unet.loaded(), MS_ERR_STATE, "no weights loaded (handle was created without a weight blob)");
     MS_REQUIRE(batch >= 1 && batch <= h->max_batch, MS_ERR_ARG, "batch exceeds max_batch of this handle");
     MS_REQUIRE(w > 0 && hgt > 0, MS_ERR_ARG, "bad slice size");
     uint8_t* norm = h->d_norm.as<uint8_t>();
     uint8_t* raw = h->d_mask_raw.as<uint8_t>();
     uint8_t* mask = h->d_mask.as<uint8_t>();
+    cudaEvent_t* sev = h->stage_n < h->stage_cap ? h->stage_events.data() + (size_t)h->stage_n * 5 : nullptr;
+    if (sev) MS_CUDA(cudaEventRecord(sev[0], st));
     preprocess_launch(h->pre, d_src, w, hgt, batch, h->net_w, h->net_h, norm, nullptr, st);         // src/process.cpp:211
+    if (sev) MS_CUDA(cudaEventRecord(sev[1], st));
     h->unet.forward(norm, batch, raw, nullptr, st);                                                  // :224
+    if (sev) MS_CUDA(cudaEventRecord(sev[2], st));
     postprocess_launch(h->post, raw, mask, h->net_h, h->net_w, batch, h->fg_value, h->min_area_ratio, st);  // :231
+    if (sev) MS_CUDA(cudaEventRecord(sev[3], st));
     // mask_to_image + threshold(127) (:234, src/mask2polygon.cpp:31): after postprocess the mask is {0, fg};
     // LUT(fg) > 127 <=> value == fg <=> value > fg - 1.
-    run_m2p(h, mask, h->net_h, h->net_w, batch, h->fg_value - 1, w, hgt, st);                        // :242
+    if (sync) {
+        run_m2p(h, mask, h->net_h, h->net_w, batch, h->fg_value - 1, w, hgt, st);                    // :242
+        h->header_pending = false;
+        return;
+    }
+    m2p_phase_a(h->m2p, h->m2p.poly, mask, h->net_h, h->net_w, batch, h->fg_value - 1, st);
+    m2p_phase_b(h->m2p, h->m2p.poly, h->net_h, h->net_w, batch, w, hgt, st);
+    if (sev) {
+        MS_CUDA(cudaEventRecord(sev[4], st));
+        ++h->stage_n;
+    }
+    if (!h->ev_header) MS_CUDA(cudaEventCreateWithFlags(&h->ev_header, cudaEventDisableTiming));
+    download(h, h->h_header.p, h->m2p.poly.header.p, 4 * sizeof(long long), st);
+    MS_CUDA(cudaEventRecord(h->ev_header, st));
+    h->header_pending = true;
+}
+
+// waits for the header of the last asynchronous pipeline_dev and validates it; grows the capacities on overflow so that
+// the next call fits
+void collect_header(ms_handle* h) {
+    if (h->header_pending) {
+        MS_CUDA(cudaEventSynchronize(h->ev_header));
+        h->header_pending = false;
+    }
+    const long long* hh = h->h_header.as<long long>();
+    MS_REQUIRE(hh[3] == 0, MS_ERR_INTERNAL, "mask2polygon: border following did not terminate");
+    MS_REQUIRE((hh[2] & 4) == 0, MS_ERR_CAPACITY, "mask2polygon: more than 2^31 points");
+    bool grown = false;
+    if (hh[0] > h->m2p.poly.cap_contours) { h->m2p.poly.cap_contours = hh[0] + hh[0] / 4 + 64; grown = true; }
+    if (hh[1] > h->m2p.poly.cap_points) { h->m2p.poly.cap_points = hh[1] + hh[1] / 4 + 1024; grown = true; }
+    MS_REQUIRE(!grown && (hh[2] & 3) == 0, MS_ERR_CAPACITY,
+               "device polygon workspace was too small for the last batch (it has been grown: run the batch again)");
 }
 
 }  // namespace
@@ -311,6 +394,7 @@ static int init_common(ms_handle* h, const char* log_dir, ms_handle** out) {
     if (rc != MS_OK) {
         t_last_error = t_last_error.empty() ? h->last_error : t_last_error;
         if (h->stream) cudaStreamDestroy(h->stream);
+        h->stream = nullptr;
         delete h;
         return rc;
     }
@@ -365,30 +449,21 @@ void ms_destroy(ms_handle* h) {
     if (h->stream) cudaStreamSynchronize(h->stream);
     h->log("\n=== Cleaning Up Resources ===");          // src/cleanup.cpp:13
     h->log("All resources cleaned up successfully");    // :52
-    for (DevBuf* b : {&h->d_src, &h->d_norm, &h->d_mask_raw, &h->d_mask, &h->d_logits, &h->d_scratch_in, &h->d_scratch_out,
-                      &h->pre.minmax, &h->post.ccl.labels, &h->post.ccl.area, &h->post.ccl.flag, &h->post.bin_a, &h->post.bin_b,
-                      &h->m2p.fg.labels, &h->m2p.fg.area, &h->m2p.fg.flag, &h->m2p.bg.labels, &h->m2p.bg.area, &h->m2p.bg.flag, &h->m2p.fgbits,
-                      &h->m2p.poly.starts, &h->m2p.poly.start_slice, &h->m2p.poly.npts, &h->m2p.poly.slice_start,
-                      &h->m2p.poly.block_counts, &h->m2p.poly.xy, &h->m2p.poly.header})
-        b->release();
-    h->m2p.release_crack();
-    for (auto& B : h->file_host) B.release();
     for (auto& S : h->slots) {
         if (S.ev_done) cudaEventSynchronize(S.ev_done);
-        S.d_src.release();
-        S.poly.release();
-        for (PinBuf* b : {&S.h_src, &S.h_header, &S.h_slice_start, &S.h_cstart, &S.h_xy}) b->release();
-        if (S.ev_h2d) cudaEventDestroy(S.ev_h2d);
         if (S.gexec) cudaGraphExecDestroy(S.gexec);
-        if (S.ev_m2p) cudaEventDestroy(S.ev_m2p);
-        if (S.ev_done) cudaEventDestroy(S.ev_done);
+        for (cudaEvent_t e : {S.ev_h2d, S.ev_m2p, S.ev_done})
+            if (e) cudaEventDestroy(e);
     }
-    if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
-    if (h->d2h_stream) cudaStreamDestroy(h->d2h_stream);
-    h->staging.release();
-    h->h_header.release();
-    h->m2p.h_header.release();
-    if (h->stream) cudaStreamDestroy(h->stream);
+    if (h->ev_header) cudaEventDestroy(h->ev_header);
+    for (cudaEvent_t e : h->stage_events) cudaEventDestroy(e);
+    for (cudaStream_t st : {h->copy_stream, h->d2h_stream, h->stream})
+        if (st) {
+            cudaStreamSynchronize(st);
+            cudaStreamDestroy(st);
+        }
+    // every DevBuf / PinBuf member (stage workspaces, polygon stores incl. the chunk store, slots, file staging) frees
+    // itself in its destructor, on the success path here and on a failed ms_init alike
     delete h;  // ~UNet frees weights and activations
 }
 
@@ -542,11 +617,29 @@ int ms_process_batch_dev(ms_handle* h, const uint16_t* d_src, int w, int hgt, in
     if (!h) return MS_ERR_ARG;
     return guarded(h, [&] {
         MS_REQUIRE(d_src, MS_ERR_ARG, "process_batch_dev: null pointer");
-        pipeline_dev(h, d_src, w, hgt, batch, pick_stream(h, stream));
+        const bool sync = n_points || n_contours;
+        pipeline_dev(h, d_src, w, hgt, batch, pick_stream(h, stream), sync);
         const long long* hh = h->h_header.as<long long>();
         if (n_contours) *n_contours = hh[0];
         if (n_points) *n_points = hh[1];
     });
+}
+
+int ms_last_counts(ms_handle* h, int64_t* n_points, int64_t* n_contours) {
+    if (!h) return MS_ERR_ARG;
+    return guarded(h, [&] {
+        collect_header(h);
+        const long long* hh = h->h_header.as<long long>();
+        if (n_contours) *n_contours = hh[0];
+        if (n_points) *n_points = hh[1];
+    });
+}
+
+int ms_get_transfer_bytes(ms_handle* h, int64_t* h2d_bytes, int64_t* d2h_bytes) {
+    if (!h) return MS_ERR_ARG;
+    if (h2d_bytes) *h2d_bytes = h->h2d_bytes;
+    if (d2h_bytes) *d2h_bytes = h->d2h_bytes;
+    return MS_OK;
 }
 
 int64_t ms_polygons_to_json(const int32_t* xy, const int32_t* contour_start, int n_contours, const char* base_name, int orig_w,
@@ -867,6 +960,38 @@ int ms_process_directory(ms_handle* h, const char* input_dir, int w, int hgt, co
 }
 
 // ---------------------------------------------------------------- asynchronous double-buffered pipeline
+namespace {
+
+// the slot's kernel chain K1 .. K6 (no host round trip: capturable)
+void enqueue_chain(ms_handle* h, ms_handle::Slot& S, int w, int hgt, int batch, cudaStream_t st) {
+    uint8_t* norm = h->d_norm.as<uint8_t>();
+    uint8_t* raw = h->d_mask_raw.as<uint8_t>();
+    uint8_t* mask = h->d_mask.as<uint8_t>();
+    preprocess_launch(h->pre, S.d_src.as<uint16_t>(), w, hgt, batch, h->net_w, h->net_h, norm, nullptr, st);
+    h->unet.forward(norm, batch, raw, nullptr, st);
+    postprocess_launch(h->post, raw, mask, h->net_h, h->net_w, batch, h->fg_value, h->min_area_ratio, st);
+    m2p_phase_a(h->m2p, S.poly, mask, h->net_h, h->net_w, batch, h->fg_value - 1, st);
+    m2p_phase_b(h->m2p, S.poly, h->net_h, h->net_w, batch, w, hgt, st);
+}
+
+// pinned result buffers follow the device capacities
+void size_slot_host(ms_handle* h, ms_handle::Slot& S) {
+    S.h_header.reserve(4 * sizeof(long long));
+    S.h_slice_start.reserve(((size_t)h->max_batch + 1) * 4);
+    S.h_cstart.reserve(((size_t)S.poly.cap_contours + 1) * 4);
+    S.h_xy.reserve((size_t)S.poly.cap_points * 8);
+}
+
+// header + slice offsets + the first spec_contours + 1 offsets and spec_points vertices, on the D2H stream
+void enqueue_slot_d2h(ms_handle* h, ms_handle::Slot& S, cudaStream_t ds) {
+    download(h, S.h_header.p, S.poly.header.p, 4 * sizeof(long long), ds);
+    download(h, S.h_slice_start.p, S.poly.slice_start.p, ((size_t)S.batch + 1) * 4, ds);
+    download(h, S.h_cstart.p, S.poly.npts.p, ((size_t)S.spec_contours + 1) * 4, ds);
+    if (S.spec_points > 0) download(h, S.h_xy.p, S.poly.xy.p, (size_t)S.spec_points * 8, ds);
+}
+
+}  // namespace
+
 int ms_submit_batch_host(ms_handle* h, int slot, const uint16_t* h_src, int w, int hgt, int batch) {
     if (!h) return MS_ERR_ARG;
     return guarded(h, [&] {
@@ -884,14 +1009,15 @@ int ms_submit_batch_host(ms_handle* h, int slot, const uint16_t* h_src, int w, i
             MS_CUDA(cudaEventCreateWithFlags(&S.ev_m2p, cudaEventDisableTiming));
             MS_CUDA(cudaEventCreateWithFlags(&S.ev_done, cudaEventDisableTiming));
         }
-        // fixed capacities: at most floor(1 / min_area_ratio) components survive postprocess per slice
+        // initial capacities: postprocess keeps at most floor(1 / min_area_ratio) components per slice (the
+        // ratio is configurable, hence derived, not a literal) and CT-like borders have ~10^3 vertices; a batch that needs
+        // more grows the slot inside ms_wait_batch
         if (S.poly.cap_contours == 0) {
-            S.poly.cap_contours = (int64_t)h->max_batch * 64;
+            const double r = (double)h->min_area_ratio;
+            const int64_t per_slice = r > 0.0 ? std::min<int64_t>(4096, (int64_t)(1.0 / r) + 1) : 4096;
+            S.poly.cap_contours = (int64_t)h->max_batch * std::max<int64_t>(64, per_slice);
             S.poly.cap_points = (int64_t)h->max_batch * 8192;
-            S.h_header.reserve(4 * sizeof(long long));
-            S.h_slice_start.reserve(((size_t)h->max_batch + 1) * 4);
-            S.h_cstart.reserve(((size_t)S.poly.cap_contours + 1) * 4);
-            S.h_xy.reserve((size_t)S.poly.cap_points * 8);
+            size_slot_host(h, S);
         }
         const size_t in_bytes = (size_t)w * hgt * 2 * batch;
         S.d_src.reserve(in_bytes);
@@ -901,20 +1027,11 @@ int ms_submit_batch_host(ms_handle* h, int slot, const uint16_t* h_src, int w, i
             std::memcpy(S.h_src.p, h_src, in_bytes);
             src = S.h_src.p;
         }
+        h->h2d_bytes += (int64_t)in_bytes;
         MS_CUDA(cudaMemcpyAsync(S.d_src.p, src, in_bytes, cudaMemcpyHostToDevice, h->copy_stream));
         MS_CUDA(cudaEventRecord(S.ev_h2d, h->copy_stream));
         cudaStream_t st = h->stream;
         MS_CUDA(cudaStreamWaitEvent(st, S.ev_h2d, 0));
-        uint8_t* norm = h->d_norm.as<uint8_t>();
-        uint8_t* raw = h->d_mask_raw.as<uint8_t>();
-        uint8_t* mask = h->d_mask.as<uint8_t>();
-        auto enqueue = [&] {
-            preprocess_launch(h->pre, S.d_src.as<uint16_t>(), w, hgt, batch, h->net_w, h->net_h, norm, nullptr, st);
-            h->unet.forward(norm, batch, raw, nullptr, st);
-            postprocess_launch(h->post, raw, mask, h->net_h, h->net_w, batch, h->fg_value, h->min_area_ratio, st);
-            m2p_phase_a(h->m2p, S.poly, mask, h->net_h, h->net_w, batch, h->fg_value - 1, st);
-            m2p_phase_b(h->m2p, S.poly, h->net_h, h->net_w, batch, w, hgt, st);
-        };
         // The chain has no host round trip, so it is captured once per (slot, shape) and replayed: the reference does the
         // same for its inference (cudaGraphLaunch, src/process.cpp:147).  First call with a shape: eager (sizes every
         // buffer).  Second call: capture + launch.  Later calls: launch.  Any reallocation bumps the epoch and drops it.
@@ -933,7 +1050,7 @@ int ms_submit_batch_host(ms_handle* h, int slot, const uint16_t* h_src, int w, i
             cudaGraph_t graph = nullptr;
             MS_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeRelaxed));
             try {
-                enqueue();
+                enqueue_chain(h, S, w, hgt, batch, st);
             } catch (...) {
                 cudaStreamEndCapture(st, &graph);
                 if (graph) cudaGraphDestroy(graph);
@@ -951,24 +1068,23 @@ int ms_submit_batch_host(ms_handle* h, int slot, const uint16_t* h_src, int w, i
                 cudaGetLastError();
                 S.gexec = nullptr;
                 if (graph) cudaGraphDestroy(graph);
-                enqueue();
+                enqueue_chain(h, S, w, hgt, batch, st);
                 S.seen_epoch = g_alloc_epoch;
             }
         } else {
-            enqueue();
+            enqueue_chain(h, S, w, hgt, batch, st);
             S.seen_w = w; S.seen_h = hgt; S.seen_batch = batch; S.seen_epoch = g_alloc_epoch;
         }
-        // results leave on their own stream so the next batch's kernels are not held up; sizes are not known on the
-        // host yet, so the capacity-sized buffers are copied and trimmed in ms_wait_batch
+        // results leave on their own stream so the next batch's kernels are not held up.  Their sizes are not known on the
+        // host yet: copy what the previous batch of this slot needed plus a quarter, fetch any remainder in ms_wait_batch.
+        S.batch = batch; S.w = w; S.hgt = hgt;
+        S.spec_contours = std::min<int64_t>(S.poly.cap_contours, std::max<int64_t>(S.last_contours + S.last_contours / 4 + 8, 2 * (int64_t)batch));
+        S.spec_points = std::min<int64_t>(S.poly.cap_points, std::max<int64_t>(S.last_points + S.last_points / 4 + 256, 256 * (int64_t)batch));
         MS_CUDA(cudaEventRecord(S.ev_m2p, st));
         cudaStream_t ds = h->d2h_stream;
         MS_CUDA(cudaStreamWaitEvent(ds, S.ev_m2p, 0));
-        MS_CUDA(cudaMemcpyAsync(S.h_header.p, S.poly.header.p, 4 * sizeof(long long), cudaMemcpyDeviceToHost, ds));
-        MS_CUDA(cudaMemcpyAsync(S.h_slice_start.p, S.poly.slice_start.p, ((size_t)batch + 1) * 4, cudaMemcpyDeviceToHost, ds));
-        MS_CUDA(cudaMemcpyAsync(S.h_cstart.p, S.poly.npts.p, ((size_t)S.poly.cap_contours + 1) * 4, cudaMemcpyDeviceToHost, ds));
-        MS_CUDA(cudaMemcpyAsync(S.h_xy.p, S.poly.xy.p, (size_t)S.poly.cap_points * 8, cudaMemcpyDeviceToHost, ds));
+        enqueue_slot_d2h(h, S, ds);
         MS_CUDA(cudaEventRecord(S.ev_done, ds));
-        S.batch = batch;
         S.busy = true;
     });
 }
@@ -983,13 +1099,42 @@ int ms_wait_batch(ms_handle* h, int slot, ms_polygons* out) {
         MS_CUDA(cudaEventSynchronize(S.ev_done));
         S.busy = false;
         const long long* hh = S.h_header.as<long long>();
+        cudaStream_t ds = h->d2h_stream;
+        // the batch did not fit the slot's device capacities: grow them (and the pinned buffers) and run the slot's chain
+        // again on its still-resident input -- stream order keeps the other slot's in-flight batch intact
+        for (int attempt = 0; hh[0] > S.poly.cap_contours || hh[1] > S.poly.cap_points || (hh[2] & 3); ++attempt) {
+            MS_REQUIRE(attempt < 3, MS_ERR_INTERNAL, "async pipeline: capacity growth did not converge");
+            MS_REQUIRE(hh[3] == 0 && (hh[2] & 4) == 0, MS_ERR_INTERNAL, "mask2polygon failed on an oversized batch");
+            if (hh[0] > S.poly.cap_contours) S.poly.cap_contours = hh[0] + hh[0] / 4 + 64;
+            if (hh[1] > S.poly.cap_points) S.poly.cap_points = hh[1] + hh[1] / 4 + 1024;
+            size_slot_host(h, S);
+            enqueue_chain(h, S, S.w, S.hgt, S.batch, h->stream);
+            MS_CUDA(cudaEventRecord(S.ev_m2p, h->stream));
+            MS_CUDA(cudaStreamWaitEvent(ds, S.ev_m2p, 0));
+            S.spec_contours = S.spec_points = 0;
+            enqueue_slot_d2h(h, S, ds);
+            MS_CUDA(cudaStreamSynchronize(ds));
+            hh = S.h_header.as<long long>();
+        }
         MS_REQUIRE(hh[3] == 0, MS_ERR_INTERNAL, "mask2polygon: border following did not terminate");
-        MS_REQUIRE(hh[2] == 0 && hh[0] <= S.poly.cap_contours && hh[1] <= S.poly.cap_points, MS_ERR_CAPACITY,
-                   "async pipeline: polygon set exceeds the slot capacity (use ms_process_batch_host for this batch)");
         out->n_contours = hh[0];
         out->n_points = hh[1];
         MS_REQUIRE(out->cap_contours >= hh[0] && out->cap_points >= hh[1], MS_ERR_CAPACITY,
                    "polygon buffers too small: need " + std::to_string(hh[0]) + " contours, " + std::to_string(hh[1]) + " points");
+        bool more = false;
+        if (hh[0] > S.spec_contours) {
+            download(h, S.h_cstart.as<int32_t>() + S.spec_contours + 1, S.poly.npts.as<int32_t>() + S.spec_contours + 1,
+                     (size_t)(hh[0] - S.spec_contours) * 4, ds);
+            more = true;
+        }
+        if (hh[1] > S.spec_points) {
+            download(h, S.h_xy.as<int32_t>() + 2 * S.spec_points, S.poly.xy.as<int32_t>() + 2 * S.spec_points,
+                     (size_t)(hh[1] - S.spec_points) * 8, ds);
+            more = true;
+        }
+        if (more) MS_CUDA(cudaStreamSynchronize(ds));
+        S.last_contours = hh[0];
+        S.last_points = hh[1];
         std::memcpy(out->slice_start, S.h_slice_start.p, ((size_t)S.batch + 1) * 4);
         std::memcpy(out->contour_start, S.h_cstart.p, ((size_t)hh[0] + 1) * 4);
         if (hh[1] > 0) std::memcpy(out->xy, S.h_xy.p, (size_t)hh[1] * 8);
@@ -1037,6 +1182,32 @@ int ms_profile_layers_begin(ms_handle* h, int max_forwards) {
         MS_REQUIRE(h->unet.loaded(), MS_ERR_STATE, "no weights loaded");
         MS_REQUIRE(max_forwards >= 0 && max_forwards <= 4096, MS_ERR_ARG, "profile_layers_begin: bad argument");
         h->unet.profile_begin(max_forwards);
+        while (h->stage_events.size() < (size_t)max_forwards * 5) {
+            cudaEvent_t e;
+            MS_CUDA(cudaEventCreate(&e));
+            h->stage_events.push_back(e);
+        }
+        h->stage_cap = max_forwards;
+        h->stage_n = 0;
+    });
+}
+int ms_profile_stages_read(ms_handle* h, float* ms4, int* n_passes) {
+    if (!h) return MS_ERR_ARG;
+    return guarded(h, [&] {
+        MS_REQUIRE(ms4, MS_ERR_ARG, "profile_stages_read: bad argument");
+        const int n = h->stage_n;
+        for (int k = 0; k < 4; ++k) ms4[k] = 0.0f;
+        for (int f = 0; f < n; ++f) {
+            cudaEvent_t* ev = h->stage_events.data() + (size_t)f * 5;
+            MS_CUDA(cudaEventSynchronize(ev[4]));
+            for (int k = 0; k < 4; ++k) {
+                float ms = 0;
+                MS_CUDA(cudaEventElapsedTime(&ms, ev[k], ev[k + 1]));
+                ms4[k] += ms / n;
+            }
+        }
+        if (n_passes) *n_passes = n;
+        h->stage_cap = h->stage_n = 0;
     });
 }
 int ms_profile_layers_read(ms_handle* h, float* ms_per_layer, int n_layers, int* n_forwards) {

@@ -332,7 +332,6 @@ Blob read_blob(const std::string& path) {
 UNet::~UNet() {
     for (cudaEvent_t e : prof_events_) cudaEventDestroy(e);
     for (void* p : allocs_) cudaFree(p);
-    scratch_mask_.release();
 }
 
 void UNet::load(const std::string& blob_path, int net_h, int net_w, int n_classes_cfg, int max_batch, int fg_value, int sm_count) {
@@ -359,6 +358,10 @@ void UNet::load(const std::string& blob_path, int net_h, int net_w, int n_classe
     (void)pv;
     const char* dv = std::getenv("MEDSEG_DESC_MODE");
     desc_mode_ = dv ? std::atoi(dv) : 0;
+    {   // publish the watchdog word to this device's copy of the symbol (mapped host memory: same address under UVA)
+        unsigned* wd = watchdog_host_word();
+        MS_CUDA(cudaMemcpyToSymbol(tc::g_watchdog_dev, &wd, sizeof(wd)));
+    }
     Blob blob = read_blob(blob_path);
     n_classes_ = blob.n_classes;
     MS_REQUIRE(n_classes_cfg <= 0 || n_classes_cfg == n_classes_, MS_ERR_FORMAT, "config n_classes does not match the weight blob");

@@ -103,12 +103,40 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
         : "memory");
     return ok != 0;
 }
-// Bounded wait: a pipeline bug traps (-> a CUDA error the host reports) instead of hanging the GPU.
+// Bounded wait.  Real waits are microseconds; a pipeline bug would otherwise hang the GPU.  The bound is 20 s of WALL
+// time (%globaltimer, polled only every ~2^28 cycles so the spin stays cheap), far beyond anything time-slicing (MPS),
+// preemption or a profiler replay can add to a legitimate wait.  On expiry the kernel raises a flag in mapped host
+// memory (checked by every C-ABI entry point -> MS_ERR_INTERNAL) and stops waiting -- its output is garbage, but the
+// context and every other handle in the process survive.  -DMEDSEG_DEBUG_WATCHDOG traps instead (sticky context error).
+__device__ unsigned* g_watchdog_dev = nullptr;    // set per device by UNet::load (cudaMemcpyToSymbol)
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+__device__ __noinline__ void watchdog_expired() {
+    if (g_watchdog_dev) {
+        *reinterpret_cast<volatile unsigned*>(g_watchdog_dev) = 1u;
+        __threadfence_system();
+    }
+#ifdef MEDSEG_DEBUG_WATCHDOG
+    __trap();
+#endif
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     if (mbar_try_wait(bar, parity)) return;
-    const long long t0 = clock64();
+    long long c0 = clock64();
+    unsigned long long t0 = 0;
     while (!mbar_try_wait(bar, parity)) {
-        if (clock64() - t0 > 4000000000ll) __trap();   // ~2 s at 2 GHz; real waits are microseconds
+        if (clock64() - c0 > (1ll << 28)) {
+            const unsigned long long now = global_timer_ns();
+            if (t0 == 0) t0 = now;
+            else if (now - t0 > 20000000000ull) {
+                watchdog_expired();
+                return;
+            }
+            c0 = clock64();
+        }
     }
 }
 // One lane of a fully converged warp (the same lane every time).  Issuing tcgen05 / TMA instructions under this
