@@ -232,6 +232,10 @@ MS_API const char* ms_layer_name(ms_handle* h, int layer);
 /* Kernel instantiation that layer runs on (as ncu prints it), valid until the next call on this thread. */
 MS_API const char* ms_layer_kernel(ms_handle* h, int layer);
 
+/* Debug (MEDSEG_FUSED_DBG=1): clock64 stamps of slice 0 at the phase boundaries of the last one-CTA-per-slice
+ * postprocess / mask2polygon kernel (csrc/slice_fused.cuh); 32 entries.  MS_ERR_STATE when the switch is off. */
+MS_API int ms_debug_fused_phases(long long* out32);
+
 /* Debug: copy an internal activation (bf16 NHWC) of the last forward to host as fp32 NCHW.
  * Returns element count or negative status.  `name` as in ms_layer_name. */
 MS_API int64_t ms_debug_read_activation(ms_handle* h, const char* name, int batch, float* h_dst, int64_t cap);

@@ -290,7 +290,7 @@ def test_async_pipeline_matches_sync(unet_engine, ms):
     for a, b in zip(got, want):
         assert a.n_contours == b.n_contours and a.n_points == b.n_points
         assert (a.slice_start == b.slice_start).all() and (a.contour_start == b.contour_start).all() and (a.xy == b.xy).all()
-    assert unet_engine.launch_count() - l0 >= 40 * len(vols)      # replayed graphs count their kernels too
+    assert unet_engine.launch_count() - l0 >= 24 * len(vols)      # replayed graphs count their kernels too (K1 2 + UNet 22 + K5/K6 2)
     with pytest.raises(ms.MedsegError) as ei:
         unet_engine.wait_batch(0)                  # nothing submitted
     assert ei.value.code == ms.MS_ERR_STATE

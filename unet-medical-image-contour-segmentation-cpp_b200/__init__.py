@@ -86,6 +86,7 @@ ABI = {
     "ms_profile_stages_read": (_I, [_P, C.POINTER(C.c_float), C.POINTER(_I)]),
     "ms_layer_name": (C.c_char_p, [_P, _I]),
     "ms_layer_kernel": (C.c_char_p, [_P, _I]),
+    "ms_debug_fused_phases": (_I, [_P]),
     "ms_debug_read_activation": (_L, [_P, C.c_char_p, _I, _P, _L]),
 }
 

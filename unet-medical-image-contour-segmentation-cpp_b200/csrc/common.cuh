@@ -147,10 +147,17 @@ struct CclWs {
     DevBuf flag;    // u8 per pixel (valid at roots): component touches the image border
 };
 
+// slice_fused.cuh (built into mask2polygon.cu): global fallback run tables of the one-CTA-per-slice kernel, used only by
+// slices with more runs than its shared-memory tables hold
+struct FusedWs {
+    DevBuf tab;           // int32 [batch][3][16 * words per slice]: labels, areas, run head positions
+};
+
 // K5 postprocess.cu
 struct PostprocessWs {
     CclWs ccl;
     DevBuf bin_a, bin_b;  // u8 per pixel
+    FusedWs fused;
 };
 void postprocess_launch(PostprocessWs& ws, const uint8_t* d_in, uint8_t* d_out, int h, int w, int batch, int fg_value,
                         float min_area_ratio, cudaStream_t st);
@@ -166,9 +173,15 @@ struct PolyDev {              // device-resident polygon set + counters
     DevBuf header;            // int64 [8]: n_contours, n_points, overflow, trace_error, n_chunks
     DevBuf chunks;            // int2 [cap_chunks * 64]: kept vertices (unmapped) in walk order, 64 per chunk
     DevBuf chunk_meta;        // int2 [cap_chunks]: {contour, sequence number} of each chunk
+    // one-CTA-per-slice path (slice_fused.cuh): per-slice totals and bases, per-contour {offset, count}, packed vertices
+    DevBuf slice_info;        // int4 [batch]
+    DevBuf rec;               // int2 [cap_contours]
+    DevBuf vstore;            // u32  [cap_points]  x | y << 16
+    bool fused = false;       // phase A ran on the fused path (phase B must finalize accordingly)
     int64_t cap_contours = 0, cap_points = 0;
     void release() {
-        for (DevBuf* b : {&starts, &start_slice, &npts, &slice_start, &block_counts, &xy, &header, &chunks, &chunk_meta}) b->release();
+        for (DevBuf* b : {&starts, &start_slice, &npts, &slice_start, &block_counts, &xy, &header, &chunks, &chunk_meta, &slice_info, &rec, &vstore})
+            b->release();
     }
 };
 struct M2pWs {
@@ -182,6 +195,7 @@ struct M2pWs {
     DevBuf crack_blocks;      // int32 per 1024 positions: kept-vertex counts, then exclusive offsets
     DevBuf crack_contour;     // int32 [2 * (cap_contours + 1)]: position base per contour, rotation
     DevBuf crack_meta;        // int64 total positions, int32 round flags
+    FusedWs fused;
     void release_crack() {
         for (DevBuf* b : {&crack_pair, &crack_pos, &crack_blocks, &crack_contour, &crack_meta}) b->release();
     }
@@ -190,5 +204,17 @@ struct M2pWs {
 void m2p_phase_a(M2pWs& ws, PolyDev& poly, const uint8_t* d_mask, int h, int w, int batch, int threshold, cudaStream_t st);
 // Phase B: emit mapped vertices into ws.poly.xy (requires cap_points >= n_points).
 void m2p_phase_b(M2pWs& ws, PolyDev& poly, int h, int w, int batch, int orig_w, int orig_h, cudaStream_t st);
+
+// One CTA per slice, everything in shared memory (slice_fused.cuh): K5 and / or phase A of K6 in one launch, for slices
+// whose bit image fits on chip.  MEDSEG_FUSED=0 switches it off (A/B measurements, and the tests run both paths).
+bool slice_fused_supported(int h, int w);
+long long* fused_debug_buffer(bool create);   // [32] clock64 stamps of slice 0's phases (debug; null unless MEDSEG_FUSED_DBG)
+// do_post: d_in = class mask, d_out = clean mask {0, fg} (postprocess_mask);  do_poly: contours of the result (do_post) or
+// of d_in > thr (otherwise) staged in `poly` for m2p_phase_b.  `poly` may be null when !do_poly.
+void slice_fused_launch(FusedWs& fws, M2pWs* ws, PolyDev* poly, const uint8_t* d_in, uint8_t* d_out, int h, int w, int batch, bool do_post,
+                        bool do_poly, int fg_value, float min_area_ratio, int thr, cudaStream_t st);
+// K5 + phase A of K6 on the class mask: the fused kernel when the slice fits, else postprocess_launch + m2p_phase_a
+void post_poly_phase_a(PostprocessWs& pws, M2pWs& ws, PolyDev& poly, const uint8_t* d_raw, uint8_t* d_clean, int h, int w, int batch,
+                       int fg_value, float min_area_ratio, cudaStream_t st);
 
 }  // namespace ms

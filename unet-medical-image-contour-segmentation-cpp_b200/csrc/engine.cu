@@ -296,10 +296,13 @@ void finish_init(ms_handle* h, const char* log_dir) {
 
 // Runs phase A (+ B) of mask2polygon with automatic growth of the device-side capacities.  On return
 // the pinned header holds {n_contours, n_points, overflow, trace_errors} and the stream is idle.
-void run_m2p(ms_handle* h, const uint8_t* d_mask, int hgt, int w, int batch, int threshold, int orig_w, int orig_h, cudaStream_t st) {
+// `d_raw` != null: the class mask straight from the head; K5 (clean mask into `d_mask`) then runs as part of phase A.
+void run_m2p(ms_handle* h, const uint8_t* d_mask, int hgt, int w, int batch, int threshold, int orig_w, int orig_h, cudaStream_t st,
+             const uint8_t* d_raw = nullptr) {
     long long* hh = h->h_header.as<long long>();
     for (int attempt = 0; attempt < 3; ++attempt) {
-        m2p_phase_a(h->m2p, h->m2p.poly, d_mask, hgt, w, batch, threshold, st);
+        if (d_raw) post_poly_phase_a(h->post, h->m2p, h->m2p.poly, d_raw, const_cast<uint8_t*>(d_mask), hgt, w, batch, h->fg_value, h->min_area_ratio, st);
+        else m2p_phase_a(h->m2p, h->m2p.poly, d_mask, hgt, w, batch, threshold, st);
         m2p_phase_b(h->m2p, h->m2p.poly, hgt, w, batch, orig_w, orig_h, st);
         download_sync(h, hh, h->m2p.poly.header.p, 4 * sizeof(long long), st);
         MS_REQUIRE(hh[3] == 0, MS_ERR_INTERNAL, "mask2polygon: border following did not terminate");
@@ -346,16 +349,25 @@ void pipeline_dev(ms_handle* h, const uint16_t* d_src, int w, int hgt, int batch
     if (sev) MS_CUDA(cudaEventRecord(sev[1], st));
     h->unet.forward(norm, batch, raw, nullptr, st);                                                  // :224
     if (sev) MS_CUDA(cudaEventRecord(sev[2], st));
-    postprocess_launch(h->post, raw, mask, h->net_h, h->net_w, batch, h->fg_value, h->min_area_ratio, st);  // :231
-    if (sev) MS_CUDA(cudaEventRecord(sev[3], st));
-    // mask_to_image + threshold(127) (:234, src/mask2polygon.cpp:31): after postprocess the mask is {0, fg};
-    // LUT(fg) > 127 <=> value == fg <=> value > fg - 1.
+    // K5 postprocess (:231) + mask_to_image / threshold(127) (:234, src/mask2polygon.cpp:31) + K6: after postprocess the
+    // mask is {0, fg} and LUT(fg) > 127 <=> value == fg, so the kept components ARE mask2polygon's foreground.  Slices that
+    // fit in shared memory run K5 and phase A of K6 as ONE kernel (the K5 | K6 stage boundary then sits before the
+    // finalize kernel: K5's share is not separable, stage timing reports the sum under K6 and 0 under K5).
     if (sync) {
-        run_m2p(h, mask, h->net_h, h->net_w, batch, h->fg_value - 1, w, hgt, st);                    // :242
+        if (sev) MS_CUDA(cudaEventRecord(sev[3], st));
+        run_m2p(h, mask, h->net_h, h->net_w, batch, h->fg_value - 1, w, hgt, st, raw);               // :231-242
         h->header_pending = false;
+        if (sev) {
+            MS_CUDA(cudaEventRecord(sev[4], st));
+            ++h->stage_n;
+        }
         return;
     }
-    m2p_phase_a(h->m2p, h->m2p.poly, mask, h->net_h, h->net_w, batch, h->fg_value - 1, st);
+    const bool one_kernel = slice_fused_supported(h->net_h, h->net_w);
+    if (!one_kernel) postprocess_launch(h->post, raw, mask, h->net_h, h->net_w, batch, h->fg_value, h->min_area_ratio, st);
+    if (sev) MS_CUDA(cudaEventRecord(sev[3], st));
+    if (one_kernel) post_poly_phase_a(h->post, h->m2p, h->m2p.poly, raw, mask, h->net_h, h->net_w, batch, h->fg_value, h->min_area_ratio, st);
+    else m2p_phase_a(h->m2p, h->m2p.poly, mask, h->net_h, h->net_w, batch, h->fg_value - 1, st);
     m2p_phase_b(h->m2p, h->m2p.poly, h->net_h, h->net_w, batch, w, hgt, st);
     if (sev) {
         MS_CUDA(cudaEventRecord(sev[4], st));
@@ -969,8 +981,7 @@ void enqueue_chain(ms_handle* h, ms_handle::Slot& S, int w, int hgt, int batch, 
     uint8_t* mask = h->d_mask.as<uint8_t>();
     preprocess_launch(h->pre, S.d_src.as<uint16_t>(), w, hgt, batch, h->net_w, h->net_h, norm, nullptr, st);
     h->unet.forward(norm, batch, raw, nullptr, st);
-    postprocess_launch(h->post, raw, mask, h->net_h, h->net_w, batch, h->fg_value, h->min_area_ratio, st);
-    m2p_phase_a(h->m2p, S.poly, mask, h->net_h, h->net_w, batch, h->fg_value - 1, st);
+    post_poly_phase_a(h->post, h->m2p, S.poly, raw, mask, h->net_h, h->net_w, batch, h->fg_value, h->min_area_ratio, st);
     m2p_phase_b(h->m2p, S.poly, h->net_h, h->net_w, batch, w, hgt, st);
 }
 
@@ -1220,6 +1231,13 @@ int ms_profile_layers_read(ms_handle* h, float* ms_per_layer, int n_layers, int*
         std::copy(v.begin(), v.end(), ms_per_layer);
         if (n_forwards) *n_forwards = passes;
     });
+}
+
+int ms_debug_fused_phases(long long* out32) {
+    long long* b = fused_debug_buffer(false);
+    if (!b || !out32) return MS_ERR_STATE;
+    std::memcpy(out32, b, 32 * sizeof(long long));
+    return MS_OK;
 }
 
 int64_t ms_debug_read_activation(ms_handle* h, const char* name, int batch, float* h_dst, int64_t cap) {

@@ -913,6 +913,8 @@ __global__ void __launch_bounds__(1024) scan_points_kernel(int* __restrict__ npt
     }
 }
 
+#include "slice_fused.cuh"
+
 enum TraceMode { kTraceSmem = 0, kTraceWindow = 1, kTraceCrack = 2, kTraceRank = 3 };
 
 constexpr size_t kRankSmemMax = 218 * 1024;   // rank_smem_kernel: bits + offsets + tables (8 KiB static step table on top)
@@ -1027,15 +1029,100 @@ void crack_emit(M2pWs& ws, PolyDev& P, int h, int w, int batch, double sx, doubl
     MS_LAUNCH_CHECK();
 }
 
+void default_capacities(PolyDev& P, int batch) {
+    if (P.cap_contours == 0) P.cap_contours = std::max<int64_t>(1024, 64 * (int64_t)batch);
+    if (P.cap_points == 0) P.cap_points = std::max<int64_t>(65536, 4096 * (int64_t)batch);
+}
+
 }  // namespace
+
+// mapped host buffer for the phase timestamps of slice 0 (MEDSEG_FUSED_DBG=1, tools/fused_phases.py); null when off
+long long* fused_debug_buffer(bool create) {
+    static long long* buf = nullptr;
+    if (!buf && (create || std::getenv("MEDSEG_FUSED_DBG"))) {
+        void* p = nullptr;
+        if (cudaHostAlloc(&p, 32 * sizeof(long long), cudaHostAllocMapped | cudaHostAllocPortable) == cudaSuccess) {
+            buf = static_cast<long long*>(p);
+            std::memset(buf, 0, 32 * sizeof(long long));
+        } else {
+            cudaGetLastError();
+        }
+    }
+    return buf;
+}
+
+bool slice_fused_supported(int h, int w) {
+    const char* e = std::getenv("MEDSEG_FUSED");      // read per call: the tests flip it to run both paths in one process
+    if (e && e[0] == '0') return false;
+    return h > 0 && w > 0 && fused::plan(h, w).ok;
+}
+
+void slice_fused_launch(FusedWs& fws, M2pWs* ws, PolyDev* P, const uint8_t* d_in, uint8_t* d_out, int h, int w, int batch, bool do_post,
+                        bool do_poly, int fg_value, float min_area_ratio, int thr, cudaStream_t st) {
+    MS_REQUIRE(h > 0 && w > 0 && batch > 0 && batch <= 65535, MS_ERR_ARG, "slice kernel: bad shape");
+    const fused::Plan pl = fused::plan(h, w);
+    MS_REQUIRE(pl.ok, MS_ERR_INTERNAL, "slice kernel: slice does not fit in shared memory");
+    MS_REQUIRE(!do_poly || (P && ws), MS_ERR_INTERNAL, "slice kernel: polygon store missing");
+    fused::Params a{};
+    a.in = d_in; a.out = d_out;
+    a.H = h; a.W = w; a.wpitch = cdiv(w, 32); a.batch = batch;
+    a.do_post = do_post; a.do_poly = do_poly;
+    a.fg_value = fg_value; a.thr = thr;
+    // src/postprocess.cpp:30,66: static_cast<int>(w * h * MIN_AREA_RATIO) -- int product, float multiply, truncate
+    a.min_area = static_cast<int>(static_cast<float>(w * h) * min_area_ratio);
+    a.off_z = pl.off_z; a.off_y = pl.off_y; a.off_roff = pl.off_roff; a.off_tab = pl.off_tab;
+    a.rcap = pl.rcap; a.cap_border = pl.cap_border;
+    a.g_runs = h * a.wpitch * 16;
+    fws.tab.reserve((size_t)batch * 3 * a.g_runs * 4);
+    a.g_tab = fws.tab.as<int>();
+    if (do_poly) {
+        default_capacities(*P, batch);
+        P->slice_info.reserve((size_t)batch * sizeof(int4));
+        P->rec.reserve((size_t)P->cap_contours * sizeof(int2));
+        P->vstore.reserve((size_t)P->cap_points * 4);
+        P->starts.reserve((size_t)P->cap_contours * 4);
+        P->npts.reserve(((size_t)P->cap_contours + 1) * 4);
+        P->slice_start.reserve(((size_t)batch + 1) * 4);
+        P->xy.reserve((size_t)P->cap_points * 8);
+        P->header.reserve(8 * sizeof(long long));
+        ws->crack_contour.reserve(((size_t)P->cap_contours + 1) * srank::kInfo * sizeof(int));
+        a.slice_info = P->slice_info.as<int4>(); a.rec = P->rec.as<int2>(); a.vstore = P->vstore.as<uint32_t>();
+        a.starts = P->starts.as<int>(); a.cinfo = ws->crack_contour.as<int>();
+        a.header = P->header.as<unsigned long long>();
+        a.cap_contours = (int)std::min<int64_t>(P->cap_contours, 0x7FFFFFF0);
+        a.cap_points = P->cap_points;
+        MS_CUDA(cudaMemsetAsync(P->header.p, 0, 8 * sizeof(long long), st));
+        P->fused = true;
+    }
+    a.dbg = fused_debug_buffer(false);
+    set_max_dynamic_smem(fused::slice_kernel, (int)fused::kSmemTotal);
+    fused::slice_kernel<<<batch, fused::kT, fused::kSmemTotal, st>>>(a);
+    MS_LAUNCH_CHECK();
+}
+
+void post_poly_phase_a(PostprocessWs& pws, M2pWs& ws, PolyDev& P, const uint8_t* d_raw, uint8_t* d_clean, int h, int w, int batch,
+                       int fg_value, float min_area_ratio, cudaStream_t st) {
+    if (slice_fused_supported(h, w)) {
+        slice_fused_launch(ws.fused, &ws, &P, d_raw, d_clean, h, w, batch, true, true, fg_value, min_area_ratio, 0, st);
+        return;
+    }
+    postprocess_launch(pws, d_raw, d_clean, h, w, batch, fg_value, min_area_ratio, st);
+    // mask_to_image + threshold(127) (src/process.cpp:234, src/mask2polygon.cpp:31): after postprocess the mask is {0, fg};
+    // LUT(fg) > 127 <=> value == fg <=> value > fg - 1
+    m2p_phase_a(ws, P, d_clean, h, w, batch, fg_value - 1, st);
+}
 
 void m2p_phase_a(M2pWs& ws, PolyDev& P, const uint8_t* d_mask, int h, int w, int batch, int threshold, cudaStream_t st) {
     MS_REQUIRE(h > 0 && w > 0 && batch > 0 && h <= 65535 && batch <= 32767, MS_ERR_ARG, "mask2polygon: bad shape");
     MS_REQUIRE((int64_t)h * w <= (int64_t)(0x7FFFFFFF - 8) / 8, MS_ERR_ARG, "mask2polygon: slice too large");
+    if (slice_fused_supported(h, w) && !std::getenv("MEDSEG_TRACE")) {
+        slice_fused_launch(ws.fused, &ws, &P, d_mask, nullptr, h, w, batch, false, true, 0, 0.0f, threshold, st);
+        return;
+    }
+    P.fused = false;
     const int n = h * w;
     const size_t nb = (size_t)n * batch;
-    if (P.cap_contours == 0) P.cap_contours = std::max<int64_t>(1024, 64 * (int64_t)batch);
-    if (P.cap_points == 0) P.cap_points = std::max<int64_t>(65536, 4096 * (int64_t)batch);
+    default_capacities(P, batch);
     const int wpitch = cdiv(w, 32);
     ws.fg.labels.reserve(nb * 4);
     ws.bg.labels.reserve(nb * 4);
@@ -1086,6 +1173,13 @@ void m2p_phase_b(M2pWs& ws, PolyDev& P, int h, int w, int batch, int orig_w, int
     // src/mask2polygon.cpp:199-200
     const double sx = static_cast<double>(orig_w) / w;
     const double sy = static_cast<double>(orig_h) / h;
+    if (P.fused) {
+        fused::finalize_kernel<<<batch, 256, 0, st>>>(P.slice_info.as<int4>(), P.rec.as<int2>(), P.vstore.as<uint32_t>(), batch,
+                                                     (int)std::min<int64_t>(P.cap_contours, 0x7FFFFFF0), (long long)P.cap_points, sx, sy,
+                                                     P.slice_start.as<int>(), P.npts.as<int>(), P.xy.as<int2>(), P.header.as<long long>());
+        MS_LAUNCH_CHECK();
+        return;
+    }
     const TraceMode mode = pick_trace_mode(h, w, batch);
     if (mode == kTraceCrack) crack_emit(ws, P, h, w, batch, sx, sy, st);
     else launch_gather(P, sx, sy, st);

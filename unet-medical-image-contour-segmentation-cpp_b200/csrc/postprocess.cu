@@ -139,6 +139,10 @@ void postprocess_launch(PostprocessWs& ws, const uint8_t* d_in, uint8_t* d_out, 
                         float min_area_ratio, cudaStream_t st) {
     MS_REQUIRE(h > 0 && w > 0 && batch > 0 && h <= 65535 && batch <= 65535, MS_ERR_ARG, "postprocess: bad shape");
     MS_REQUIRE((int64_t)h * w < ((int64_t)1 << 31), MS_ERR_ARG, "postprocess: slice too large");
+    if (slice_fused_supported(h, w)) {     // one CTA per slice, everything on chip (slice_fused.cuh)
+        slice_fused_launch(ws.fused, nullptr, nullptr, d_in, d_out, h, w, batch, true, false, fg_value, min_area_ratio, 0, st);
+        return;
+    }
     const size_t n = (size_t)h * w, nb = n * batch;
     const int wpitch = cdiv(w, 32);
     const size_t nwords = (size_t)batch * h * wpitch;
