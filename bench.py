@@ -46,6 +46,7 @@ def parse():
     ap.add_argument("--cpu-sample", type=int, default=0, help="slices in the CPU baseline sample (0 = auto, ~10-30 s)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--layer-table", default="", help="write the per-layer roofline table to this JSON file")
+    ap.add_argument("--volume-slices", type=int, default=256, help="cfg3: slices of the one-call volume run (0 = skip)")
     return ap.parse_args()
 
 
@@ -206,8 +207,13 @@ def run_ours(args, rank, world, local):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device -- the product has no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
+    cpu_group = None
     if use_dist:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        # host-side barrier for the one-process volume run: an NCCL barrier parks a spinning kernel on every waiting GPU,
+        # and rank 0's work on those GPUs would then be time-sliced against it (different processes do not share a GPU
+        # concurrently)
+        cpu_group = dist.new_group(backend="gloo")
     n_classes = 1 if args.head == "binary" else 3
     B, S = args.batch, args.size
 
@@ -456,6 +462,35 @@ def run_ours(args, rank, world, local):
 
     info = eng.info
     eng.cleanup()
+
+    # ---------------- cfg3 as written: ONE 256-slice volume through ONE call of ONE process, sharded by contiguous slice
+    # blocks over the N GPUs (ms_process_volume_host, one host thread + two streams per GPU).  Rank 0 runs it while the
+    # other ranks wait at the barrier with their engines released; strong scaling: the volume is fixed as N grows.
+    volume = None
+    if args.volume_slices > 0:
+        barrier()
+        if rank == 0:
+            nv = args.volume_slices
+            vcfg = dict(cfg)
+            vcfg.pop("device", None)
+            vcfg["devices"] = list(range(world))
+            veng = ms.Engine(vcfg)
+            vhost = torch.from_numpy(synth.ct_volume(nv, S, S, first_seed=0)).pin_memory()
+            vnp = vhost.numpy()
+            for _ in range(3):
+                vp, _, _ = veng.process_volume(vnp)
+            reps = 5
+            t0 = time.perf_counter()
+            for _ in range(reps):
+                vp, _, _ = veng.process_volume(vnp)
+            dtv = (time.perf_counter() - t0) / reps
+            volume = {"slices": nv, "gpus": veng.device_count(), "value": nv / dtv, "unit": "slices/s", "ms_per_volume": dtv * 1e3,
+                      "scaling": "strong", "contours": int(vp.n_contours), "points": int(vp.n_points),
+                      "api": "ms_process_volume_host: one process, one call, contiguous slice blocks per GPU, host buffers (H2D + polygons D2H inside)"}
+            veng.cleanup()
+        torch.cuda.synchronize()
+        if use_dist:
+            dist.barrier(group=cpu_group)
     if rank == 0:
         line = {"metric": "slices_per_sec", "value": value, "unit": "slices/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
@@ -471,6 +506,8 @@ def run_ours(args, rank, world, local):
                 "p50_sync_call_ms": p50_sync, "roofline": roofline,
                 "polygons_last_step": {"contours": int(n_cnt), "points": int(n_pts)},
                 "flops_per_slice": int(info.flops_per_slice)}
+        if volume:
+            line["volume"] = volume
         if parity:
             line["parity_check"] = parity
         if cpu:

@@ -176,6 +176,19 @@ MS_API int ms_last_counts(ms_handle* h, int64_t* n_points, int64_t* n_contours);
 MS_API int ms_submit_batch_host(ms_handle* h, int slot, const uint16_t* h_src, int w, int hgt, int batch);
 MS_API int ms_wait_batch(ms_handle* h, int slot, ms_polygons* out);
 
+/* One volume of n_slices slices (h_src: n_slices x hgt x w u16, pinned preferred) through ONE call on every GPU of the
+ * handle -- BASELINE cfg3, the per-file loop of src/main.cpp:148-164 turned into a sharded batcher.  A handle created with
+ * "devices": [0, 1, ...] (or "all"; MEDSEG_DEVICES supplies the list when the config names no device) owns one full engine
+ * per GPU; GPU g takes the contiguous block [g * n / G, (g + 1) * n / G) and one host thread, which streams it in
+ * max_batch-sized sub-batches through the double-buffered ms_submit_batch_host / ms_wait_batch pair.  No collective: the
+ * blocks' polygon sets are concatenated on the host in slice order (out->slice_start needs n_slices + 1 entries).
+ * h_norm_u8 / h_mask_u8 (n_slices x net_h x net_w, may be NULL) switch the workers to the synchronous per-batch call.
+ * With one device it is simply the streaming batcher. */
+MS_API int ms_process_volume_host(ms_handle* h, const uint16_t* h_src, int w, int hgt, int64_t n_slices, ms_polygons* out,
+                                  uint8_t* h_norm_u8, uint8_t* h_mask_u8);
+/* GPUs behind this handle (1 unless it was created with "devices"). */
+MS_API int ms_device_count(ms_handle* h);
+
 /* Replaces MedicalSeg::process_single_image(raw_path, width, height, output_dir) including its
  * artefacts: <stem>_normalized.png, <stem>_original_sizes.json, <stem>_mask.png,
  * <stem>_contour_overlay.png, <stem>.json (src/process.cpp:207-242, src/mask2polygon.cpp:134-222). */
@@ -183,7 +196,8 @@ MS_API int ms_process_raw_file(ms_handle* h, const char* raw_path, int w, int hg
 
 /* Batched form of the per-file loop of src/main.cpp:148-164: n headerless u16 files of the same w x hgt, artefacts of
  * file i (the same five as ms_process_raw_file, byte-identical to calling it per file) into out_dirs[i].  A prefetch
- * thread reads batch k+1 into pinned memory and a pool of writer threads (MEDSEG_WRITERS, default min(cores, 16))
+ * (a multi-GPU handle splits the list into one contiguous block per GPU, each with its own pipeline and host thread) thread
+ * reads batch k+1 into pinned memory and a pool of writer threads (MEDSEG_WRITERS, default min(cores, 16))
  * encodes batch k-1 while the GPU works on batch k (max_batch files per launch sequence).  A file that cannot be read
  * or written is counted in *n_failed (and ok[i] = 0) without stopping the others -- the reference's success_count /
  * fail_count (src/main.cpp:160-164); the return value is MS_OK unless the call itself failed.  ok, n_ok, n_failed may

@@ -111,3 +111,58 @@ def test_two_devices_in_one_process(ms, blob3):
             assert (got.xy == res[d][i % 3].xy).all()
     for e in engs:
         e.cleanup()
+
+
+def test_cfg3_volume_call_streams_sub_batches(unet_engine, ms):
+    """cfg3 through ONE call (ms_process_volume_host): a 10-slice volume on a max_batch-4 handle is streamed as 4 + 4 + 2
+    through the double-buffered pair and comes back, in slice order, as exactly the per-batch results; the side outputs
+    (normalised slices, clean masks) switch the worker to the synchronous per-batch call and give the same polygons."""
+    from medseg_b200 import synth
+    vol = synth.ct_volume(10, first_seed=700)
+    want, wn, wm = [], [], []
+    for i in range(0, 10, 4):
+        p, n, m = unet_engine.process_batch(vol[i:i + 4], want_norm=True, want_mask=True)
+        want += p.per_slice()
+        wn.append(n)
+        wm.append(m)
+    for it in range(2):                              # second pass replays the slots' CUDA graphs
+        got, _, _ = unet_engine.process_volume(vol)
+        assert len(got.slice_start) == 11 and got.n_contours == sum(len(c) for c in want)
+        for a, b in zip(got.per_slice(), want):
+            assert contours_equal(a, b)
+    got, norm, mask = unet_engine.process_volume(vol, want_norm=True, want_mask=True)
+    assert (norm == np.concatenate(wn)).all() and (mask == np.concatenate(wm)).all()
+    for a, b in zip(got.per_slice(), want):
+        assert contours_equal(a, b)
+    assert unet_engine.device_count() == 1
+
+
+def test_cfg3_volume_sharded_over_gpus_in_one_process(ms, blob3, tmp_path):
+    """cfg3 as written: one volume, one call, contiguous slice blocks per GPU ("devices"), one host thread per GPU, results
+    concatenated in slice order == the single-GPU result; the file-list path fans out the same way and writes the same
+    bytes."""
+    import os
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    from medseg_b200 import synth
+    g = min(4, torch.cuda.device_count())
+    one = ms.Engine({"weights": blob3, "max_batch": 4, "device": 0})
+    many = ms.Engine({"weights": blob3, "max_batch": 4, "devices": list(range(g))})
+    assert many.device_count() == g
+    vol = synth.ct_volume(4 * g + 3, first_seed=800)
+    a, _, _ = one.process_volume(vol)
+    for it in range(2):
+        b, _, _ = many.process_volume(vol)
+        assert (a.slice_start == b.slice_start).all() and (a.contour_start == b.contour_start).all() and (a.xy == b.xy).all()
+    src = tmp_path / "in"
+    src.mkdir()
+    for i in range(len(vol)):
+        vol[i].tofile(src / f"s{i:03d}.raw")
+    assert one.process_directory(str(src), 512, 512, str(tmp_path / "o1")) == (len(vol), len(vol), 0)
+    assert many.process_directory(str(src), 512, 512, str(tmp_path / "oN")) == (len(vol), len(vol), 0)
+    for f in sorted(os.listdir(tmp_path / "o1")):
+        assert open(tmp_path / "o1" / f, "rb").read() == open(tmp_path / "oN" / f, "rb").read(), f
+    assert many.launch_count() > 0
+    one.cleanup()
+    many.cleanup()

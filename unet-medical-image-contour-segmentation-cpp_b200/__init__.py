@@ -74,6 +74,8 @@ ABI = {
     "ms_get_transfer_bytes": (_I, [_P, C.POINTER(_L), C.POINTER(_L)]),
     "ms_submit_batch_host": (_I, [_P, _I, _P, _I, _I, _I]),
     "ms_wait_batch": (_I, [_P, _I, C.POINTER(ms_polygons)]),
+    "ms_process_volume_host": (_I, [_P, _P, _I, _I, _L, C.POINTER(ms_polygons), _P, _P]),
+    "ms_device_count": (_I, [_P]),
     "ms_process_raw_file": (_I, [_P, C.c_char_p, _I, _I, C.c_char_p]),
     "ms_process_raw_files": (_I, [_P, C.POINTER(C.c_char_p), C.POINTER(C.c_char_p), _L, _I, _I, _P, C.POINTER(_L), C.POINTER(_L)]),
     "ms_process_directory": (_I, [_P, C.c_char_p, _I, _I, C.c_char_p, _I, _I, _I, C.POINTER(_L), C.POINTER(_L), C.POINTER(_L)]),
@@ -271,6 +273,22 @@ class Engine:
         polys = self._poly_call(
             lambda pg: self._l.ms_process_batch_host(self._h, _ptr(src), w, h, b, pg, _ptr(norm), _ptr(mask)), b)
         return polys, norm, mask
+
+    def process_volume(self, vol_u16: np.ndarray, want_norm: bool = False, want_mask: bool = False):
+        """cfg3: one volume [N,h,w] through one call, sharded by contiguous slice blocks over the handle's GPUs
+        ("devices" in the config).  Returns (Polygons over all N slices, norm, mask)."""
+        v = vol_u16
+        if v.dtype != np.uint16 or not v.flags.c_contiguous or v.ndim != 3:
+            raise TypeError("volume must be a C-contiguous uint16 [N,h,w] array")
+        n, h, w = v.shape
+        norm = np.empty((n, self.info.net_h, self.info.net_w), np.uint8) if want_norm else None
+        mask = np.empty((n, self.info.net_h, self.info.net_w), np.uint8) if want_mask else None
+        self._cap_pts, self._cap_cnt = max(self._cap_pts, n * 1024), max(self._cap_cnt, n * 8)
+        polys = self._poly_call(lambda pg: self._l.ms_process_volume_host(self._h, _ptr(v), w, h, n, pg, _ptr(norm), _ptr(mask)), n)
+        return polys, norm, mask
+
+    def device_count(self) -> int:
+        return int(self._l.ms_device_count(self._h))
 
     def submit_batch(self, slot: int, src_u16: np.ndarray) -> None:
         """Asynchronous half of the double-buffered pipeline: enqueue H2D + the whole path for `src_u16` [B,h,w]

@@ -113,6 +113,13 @@ struct ms_handle {
     }
     std::string last_error;
     LaunchCounter counter;
+    // single-process multi-GPU ("devices" in the config / MEDSEG_DEVICES): this handle drives devices[0]; `peers` are full
+    // handles (own stream, weights, workspaces) for devices[1..], owned by this one.  Slices are independent, so the
+    // volume / file-list entry points give every GPU a contiguous block and one host thread (src/main.cpp:148-164).
+    std::vector<int> devices;
+    std::vector<ms_handle*> peers;
+    std::string cfg_text;            // the JSON config this handle was created from (peers are created from it)
+    bool quiet_console = false;      // peers: console lines are collected per job and printed in job order by the owner
     // bytes this handle moved over PCIe with its own copies (bench.py: e2e.h2d/d2h_bytes_per_step are read from here)
     int64_t h2d_bytes = 0, d2h_bytes = 0;
     // ms_process_batch_dev without result pointers: header lands in h_header asynchronously, ms_last_counts collects it
@@ -230,6 +237,29 @@ void download_sync(ms_handle* h, void* h_dst, const void* d_src, size_t bytes, c
     MS_CUDA(cudaStreamSynchronize(st));
 }
 
+void parse_devices(ms_handle* h, const std::string& devs) {
+    h->devices.clear();
+    if (devs == "all") {
+        int n = 0;
+        if (cudaGetDeviceCount(&n) != cudaSuccess) {
+            cudaGetLastError();
+            n = 0;
+        }
+        for (int i = 0; i < n; ++i) h->devices.push_back(i);
+    } else if (!devs.empty()) {
+        std::stringstream ss(devs);
+        std::string tok;
+        while (std::getline(ss, tok, ',')) {
+            MS_REQUIRE(!tok.empty() && tok.find_first_not_of("0123456789 ") == std::string::npos, MS_ERR_FORMAT,
+                       "devices: expected a list of ordinals or \"all\"");
+            const int d = std::atoi(tok.c_str());
+            MS_REQUIRE(std::find(h->devices.begin(), h->devices.end(), d) == h->devices.end(), MS_ERR_FORMAT, "devices: duplicate ordinal");
+            h->devices.push_back(d);
+        }
+    }
+    if (!h->devices.empty()) h->device = h->devices[0];
+}
+
 void apply_config(ms_handle* h, const json::Value& cfg, const std::string& base_dir) {
     MS_REQUIRE(cfg.type == json::Value::Obj, MS_ERR_FORMAT, "config must be a JSON object");
     h->net_h = (int)cfg.integer("net_h", cfg.integer("net_size", 512));
@@ -240,6 +270,20 @@ void apply_config(ms_handle* h, const json::Value& cfg, const std::string& base_
     h->threshold = (int)cfg.integer("threshold", 127);
     h->min_area_ratio = (float)cfg.number("min_area_ratio", 0.06f);
     h->device = (int)cfg.integer("device", 0);
+    // "devices": [0, 1, ...] or "all" (MEDSEG_DEVICES=all|0,1,.. supplies it when the config names neither, so the
+    // reference's `init <path>` needs no new argument): one process, one handle per listed GPU
+    std::string devs;
+    if (cfg.has("devices")) {
+        const json::Value& dv = cfg.at("devices");
+        if (dv.type == json::Value::Arr) {
+            for (const auto& e : dv.arr) devs += (devs.empty() ? "" : ",") + std::to_string((int)e.num);
+        } else if (dv.type == json::Value::Str) {
+            devs = dv.str;
+        }
+    } else if (!cfg.has("device")) {
+        if (const char* e = std::getenv("MEDSEG_DEVICES")) devs = e;
+    }
+    parse_devices(h, devs);
     std::string w = cfg.string("weights", "");
     if (!w.empty() && w[0] != '/') w = base_dir + "/" + w;
     h->weights_path = w;
@@ -410,6 +454,28 @@ static int init_common(ms_handle* h, const char* log_dir, ms_handle** out) {
         delete h;
         return rc;
     }
+    // one more full handle per additional GPU (same configuration, quiet console, same log file)
+    for (size_t i = 1; i < h->devices.size(); ++i) {
+        ms_handle* c = new ms_handle();
+        c->device = h->devices[i];
+        c->net_h = h->net_h; c->net_w = h->net_w; c->n_classes_cfg = h->n_classes_cfg; c->max_batch = h->max_batch;
+        c->fg_value = h->fg_value; c->threshold = h->threshold; c->min_area_ratio = h->min_area_ratio;
+        c->weights_path = h->weights_path;
+        c->quiet_console = true;
+        rc = guarded(nullptr, [&] { finish_init(c, nullptr); });
+        if (rc != MS_OK) {
+            t_last_error = "device " + std::to_string(c->device) + ": " + t_last_error;
+            if (c->stream) cudaStreamDestroy(c->stream);
+            c->stream = nullptr;
+            delete c;
+            ms_destroy(h);
+            return rc;
+        }
+        c->log_path = h->log_path;
+        h->peers.push_back(c);
+    }
+    if (!h->peers.empty()) h->log("Devices: " + std::to_string(h->devices.size()) + " GPUs in this process, one worker thread each");
+    cudaSetDevice(h->device);
     *out = h;
     return MS_OK;
 }
@@ -432,6 +498,7 @@ int ms_init(const char* path, const char* log_dir, ms_handle** out) {
             struct stat sb;
             MS_REQUIRE(::stat(p.c_str(), &sb) == 0, MS_ERR_IO, "Error: engine file not found - " + p);  // src/initialize.cpp:42-45
             h->weights_path = p;
+            if (const char* e = std::getenv("MEDSEG_DEVICES")) parse_devices(h, e);
         }
     });
     if (rc != MS_OK) { delete h; return rc; }
@@ -457,6 +524,11 @@ int ms_init_json(const char* cfg_json_text, const char* log_dir, ms_handle** out
 
 void ms_destroy(ms_handle* h) {
     if (!h) return;
+    for (ms_handle* c : h->peers) {
+        c->log_path.clear();          // the owner writes the clean-up lines once
+        ms_destroy(c);
+    }
+    h->peers.clear();
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
     h->log("\n=== Cleaning Up Resources ===");          // src/cleanup.cpp:13
@@ -649,8 +721,10 @@ int ms_last_counts(ms_handle* h, int64_t* n_points, int64_t* n_contours) {
 
 int ms_get_transfer_bytes(ms_handle* h, int64_t* h2d_bytes, int64_t* d2h_bytes) {
     if (!h) return MS_ERR_ARG;
-    if (h2d_bytes) *h2d_bytes = h->h2d_bytes;
-    if (d2h_bytes) *d2h_bytes = h->d2h_bytes;
+    int64_t a = h->h2d_bytes, b = h->d2h_bytes;
+    for (const ms_handle* c : h->peers) { a += c->h2d_bytes; b += c->d2h_bytes; }
+    if (h2d_bytes) *h2d_bytes = a;
+    if (d2h_bytes) *d2h_bytes = b;
     return MS_OK;
 }
 
@@ -668,6 +742,13 @@ int64_t ms_polygons_to_json(const int32_t* xy, const int32_t* contour_start, int
 
 // ---------------------------------------------------------------- file path (P0 + N1 + N3)
 namespace {
+
+// contiguous block of `total` items for part `i` of `parts` (sharding.py: shard_range; earlier parts take the remainder)
+std::pair<int64_t, int64_t> block_of(int64_t total, int parts, int i) {
+    const int64_t base = total / parts, rem = total % parts;
+    const int64_t lo = i * base + std::min<int64_t>(i, rem);
+    return {lo, lo + base + (i < rem ? 1 : 0)};
+}
 
 // Everything the artefact writer of one slice needs; no CUDA, no handle state, so slices are written concurrently.
 struct SliceJob {
@@ -758,7 +839,7 @@ int writer_threads() {
 }
 
 // Reads batch `k` of the job list into B.in (good slices packed), assigning slots.  Runs on the prefetch thread.
-void read_batch(std::vector<SliceJob>& jobs, size_t first, size_t last, BatchHost& B, int w, int hgt) {
+void read_batch(SliceJob* jobs, size_t first, size_t last, BatchHost& B, int w, int hgt) {
     const size_t n_in = (size_t)w * hgt;
     int slot = 0;
     for (size_t i = first; i < last; ++i) {
@@ -783,10 +864,12 @@ void read_batch(std::vector<SliceJob>& jobs, size_t first, size_t last, BatchHos
 
 // The batched file pipeline: prefetch thread (disk -> pinned) | GPU (this thread) | writer threads (artefacts), each
 // working on a different batch.  Per-file failures are recorded in the jobs; only CUDA / argument errors throw.
-void process_jobs(ms_handle* h, std::vector<SliceJob>& jobs, int w, int hgt, bool report_errors = true) {
+// `console`: where the reference's std::cout / std::cerr lines go -- straight out (null), or into a string the caller prints
+// in job order (a GPU of a multi-device handle must not interleave its lines with the others')
+void process_jobs_on(ms_handle* h, SliceJob* jobs, size_t n, int w, int hgt, bool report_errors, std::string* console) {
     MS_REQUIRE(h->unet.loaded(), MS_ERR_STATE, "no weights loaded (handle was created without a weight blob)");
     MS_REQUIRE(w > 0 && hgt > 0, MS_ERR_ARG, "bad slice size");
-    const size_t n = jobs.size(), mb = (size_t)h->max_batch;
+    const size_t mb = (size_t)h->max_batch;
     const size_t n_batches = (n + mb - 1) / mb;
     const size_t n_in = (size_t)w * hgt, npx = (size_t)h->net_w * h->net_h;
     BatchHost* host = h->file_host;   // kept across calls: pinned allocations cost milliseconds
@@ -812,13 +895,15 @@ void process_jobs(ms_handle* h, std::vector<SliceJob>& jobs, int w, int hgt, boo
             h->log("\n=== Processing Image: " + basename_of(J.raw) + " ===");                 // src/process.cpp:198
             if (J.status != MS_OK) {
                 if (report_errors) {
-                    std::cerr << "Processing error: " << J.error << std::endl;                // :257
+                    if (console) *console += "\x01Processing error: " + J.error + "\n";        // \x01: a std::cerr line
+                    else std::cerr << "Processing error: " << J.error << std::endl;           // :257
                     h->log("error: " + J.error);                                              // :259
                 }
                 continue;
             }
             h->log("Inference time: " + std::to_string(infer_ms) + " ms");                    // :228 (the whole batch)
-            std::cout << J.console;
+            if (console) *console += J.console;
+            else std::cout << J.console;
             h->log("Processing completed for: " + J.base);                                    // :250
         }
     };
@@ -829,7 +914,7 @@ void process_jobs(ms_handle* h, std::vector<SliceJob>& jobs, int w, int hgt, boo
             BatchHost& B = host[k & 1];
             if (k + 1 < n_batches) {
                 const auto r = range(k + 1);
-                reader = std::thread(read_batch, std::ref(jobs), r.first, r.second, std::ref(host[(k + 1) & 1]), w, hgt);
+                reader = std::thread(read_batch, jobs, r.first, r.second, std::ref(host[(k + 1) & 1]), w, hgt);
             }
             const auto r = range(k);
             int nb = 0;
@@ -873,6 +958,58 @@ void process_jobs(ms_handle* h, std::vector<SliceJob>& jobs, int w, int hgt, boo
         join_writers();
         throw;
     }
+}
+
+// The per-file loop of src/main.cpp:148-164 over every GPU of the handle: contiguous blocks of the (sorted) job list, one
+// host thread per GPU, each running the prefetch | GPU | writers pipeline on its own handle.  Console lines come out in
+// job order, block after block.
+void process_jobs(ms_handle* h, std::vector<SliceJob>& jobs, int w, int hgt, bool report_errors = true) {
+    std::vector<ms_handle*> devs{h};
+    devs.insert(devs.end(), h->peers.begin(), h->peers.end());
+    const int G = (int)std::min<size_t>(devs.size(), std::max<size_t>(1, (jobs.size() + (size_t)h->max_batch - 1) / (size_t)h->max_batch));
+    if (G <= 1) {
+        process_jobs_on(h, jobs.data(), jobs.size(), w, hgt, report_errors, nullptr);
+        return;
+    }
+    struct Part {
+        std::string console, error;
+        int status = MS_OK;
+    };
+    std::vector<Part> parts((size_t)G);
+    auto run = [&](int g) {
+        const auto r = block_of((int64_t)jobs.size(), G, g);
+        ms_handle* d = devs[g];
+        try {
+            MS_CUDA(cudaSetDevice(d->device));
+            g_counter = &d->counter;
+            process_jobs_on(d, jobs.data() + r.first, (size_t)(r.second - r.first), w, hgt, report_errors, &parts[g].console);
+        } catch (const Error& e) {
+            parts[g].status = e.code;
+            parts[g].error = e.what;
+        } catch (const std::exception& e) {
+            parts[g].status = MS_ERR_INTERNAL;
+            parts[g].error = e.what();
+        }
+        g_counter = nullptr;
+    };
+    std::vector<std::thread> th;
+    for (int g = 1; g < G; ++g) th.emplace_back(run, g);
+    run(0);
+    for (auto& t : th) t.join();
+    MS_CUDA(cudaSetDevice(h->device));
+    g_counter = &h->counter;
+    for (const auto& P : parts) {             // lines in job order; \x01 marks a std::cerr line
+        size_t i = 0;
+        while (i < P.console.size()) {
+            const size_t e = P.console.find('\n', i);
+            const size_t end = e == std::string::npos ? P.console.size() : e + 1;
+            if (P.console[i] == '\x01') std::cerr << P.console.substr(i + 1, end - i - 1) << std::flush;
+            else std::cout << P.console.substr(i, end - i);
+            i = end;
+        }
+    }
+    for (int g = 0; g < G; ++g)
+        if (parts[g].status != MS_OK) fail(parts[g].status, "device " + std::to_string(devs[g]->device) + ": " + parts[g].error);
 }
 
 bool is_16bit_image(const std::string& path) {               // src/main.cpp:18-25
@@ -1108,12 +1245,12 @@ int ms_wait_batch(ms_handle* h, int slot, ms_polygons* out) {
         MS_REQUIRE(S.busy, MS_ERR_STATE, "wait_batch: nothing was submitted on this slot");
         check_polys(out, S.batch);
         MS_CUDA(cudaEventSynchronize(S.ev_done));
-        S.busy = false;
         const long long* hh = S.h_header.as<long long>();
         cudaStream_t ds = h->d2h_stream;
         // the batch did not fit the slot's device capacities: grow them (and the pinned buffers) and run the slot's chain
         // again on its still-resident input -- stream order keeps the other slot's in-flight batch intact
         for (int attempt = 0; hh[0] > S.poly.cap_contours || hh[1] > S.poly.cap_points || (hh[2] & 3); ++attempt) {
+            if (attempt >= 3 || hh[3] != 0 || (hh[2] & 4)) S.busy = false;
             MS_REQUIRE(attempt < 3, MS_ERR_INTERNAL, "async pipeline: capacity growth did not converge");
             MS_REQUIRE(hh[3] == 0 && (hh[2] & 4) == 0, MS_ERR_INTERNAL, "mask2polygon failed on an oversized batch");
             if (hh[0] > S.poly.cap_contours) S.poly.cap_contours = hh[0] + hh[0] / 4 + 64;
@@ -1127,9 +1264,11 @@ int ms_wait_batch(ms_handle* h, int slot, ms_polygons* out) {
             MS_CUDA(cudaStreamSynchronize(ds));
             hh = S.h_header.as<long long>();
         }
+        if (hh[3] != 0) S.busy = false;
         MS_REQUIRE(hh[3] == 0, MS_ERR_INTERNAL, "mask2polygon: border following did not terminate");
         out->n_contours = hh[0];
         out->n_points = hh[1];
+        // (the slot stays collectable: call again with the sizes just reported)
         MS_REQUIRE(out->cap_contours >= hh[0] && out->cap_points >= hh[1], MS_ERR_CAPACITY,
                    "polygon buffers too small: need " + std::to_string(hh[0]) + " contours, " + std::to_string(hh[1]) + " points");
         bool more = false;
@@ -1144,6 +1283,7 @@ int ms_wait_batch(ms_handle* h, int slot, ms_polygons* out) {
             more = true;
         }
         if (more) MS_CUDA(cudaStreamSynchronize(ds));
+        S.busy = false;
         S.last_contours = hh[0];
         S.last_points = hh[1];
         std::memcpy(out->slice_start, S.h_slice_start.p, ((size_t)S.batch + 1) * 4);
@@ -1152,8 +1292,161 @@ int ms_wait_batch(ms_handle* h, int slot, ms_polygons* out) {
     });
 }
 
+// ---------------------------------------------------------------- one volume, all GPUs of the handle (cfg3)
+namespace {
+
+struct VolumePart {                     // one GPU's contiguous block of slices
+    ms_handle* dev = nullptr;
+    int64_t first = 0, count = 0;
+    std::vector<int32_t> per_slice;     // contours per slice
+    std::vector<int32_t> per_contour;   // vertices per contour
+    std::vector<int32_t> xy;
+    int status = MS_OK;
+    std::string error;
+};
+
+// the double-buffered batcher over one block: submit sub-batch k + 1, collect sub-batch k
+void volume_worker(VolumePart& V, const uint16_t* h_src, int w, int hgt, uint8_t* h_norm, uint8_t* h_mask) {
+    ms_handle* d = V.dev;
+    const int64_t mb = d->max_batch, n_sub = (V.count + mb - 1) / mb;
+    const size_t n_in = (size_t)w * hgt, npx = (size_t)d->net_w * d->net_h;
+    std::vector<int32_t> ss((size_t)mb + 1), cs, xy;
+    int64_t cap_c = mb * 64, cap_p = mb * 8192;
+    cs.resize((size_t)cap_c + 1);
+    xy.resize((size_t)cap_p * 2);
+    auto fail_with = [&](int rc) {
+        V.status = rc;
+        V.error = ms_last_error(d);
+    };
+    auto sub = [&](int64_t k) { return std::make_pair(k * mb, std::min(V.count, (k + 1) * mb)); };
+    auto append = [&](const ms_polygons& pg, int nb) {
+        for (int i = 0; i < nb; ++i) V.per_slice.push_back(ss[i + 1] - ss[i]);
+        for (int64_t c = 0; c < pg.n_contours; ++c) V.per_contour.push_back(cs[c + 1] - cs[c]);
+        V.xy.insert(V.xy.end(), xy.begin(), xy.begin() + 2 * pg.n_points);
+    };
+    if (h_norm || h_mask) {               // side outputs wanted: the synchronous call per sub-batch returns them
+        for (int64_t k = 0; k < n_sub; ++k) {
+            const auto r = sub(k);
+            const int nb = (int)(r.second - r.first);
+            const size_t g0 = (size_t)(V.first + r.first);
+            for (;;) {
+                ms_polygons pg{xy.data(), cap_p, cs.data(), cap_c, ss.data(), 0, 0};
+                const int rc = ms_process_batch_host(d, h_src + g0 * n_in, w, hgt, nb, &pg, h_norm ? h_norm + g0 * npx : nullptr,
+                                                     h_mask ? h_mask + g0 * npx : nullptr);
+                if (rc == MS_ERR_CAPACITY && (pg.n_points > cap_p || pg.n_contours > cap_c)) {
+                    cap_p = std::max(cap_p, pg.n_points + pg.n_points / 4 + 16);
+                    cap_c = std::max(cap_c, pg.n_contours + pg.n_contours / 4 + 16);
+                    cs.resize((size_t)cap_c + 1);
+                    xy.resize((size_t)cap_p * 2);
+                    continue;
+                }
+                if (rc != MS_OK) return fail_with(rc);
+                append(pg, nb);
+                break;
+            }
+        }
+        return;
+    }
+    auto submit = [&](int64_t k) {
+        const auto r = sub(k);
+        return ms_submit_batch_host(d, (int)(k & 1), h_src + (size_t)(V.first + r.first) * n_in, w, hgt, (int)(r.second - r.first));
+    };
+    int rc = n_sub > 0 ? submit(0) : MS_OK;
+    if (rc != MS_OK) return fail_with(rc);
+    for (int64_t k = 0; k < n_sub; ++k) {
+        if (k + 1 < n_sub && (rc = submit(k + 1)) != MS_OK) {
+            ms_polygons drop{xy.data(), cap_p, cs.data(), cap_c, ss.data(), 0, 0};
+            ms_wait_batch(d, (int)(k & 1), &drop);
+            return fail_with(rc);
+        }
+        const auto r = sub(k);
+        for (;;) {
+            ms_polygons pg{xy.data(), cap_p, cs.data(), cap_c, ss.data(), 0, 0};
+            rc = ms_wait_batch(d, (int)(k & 1), &pg);
+            if (rc == MS_ERR_CAPACITY && (pg.n_points > cap_p || pg.n_contours > cap_c)) {     // the slot stays collectable
+                cap_p = std::max(cap_p, pg.n_points + pg.n_points / 4 + 16);
+                cap_c = std::max(cap_c, pg.n_contours + pg.n_contours / 4 + 16);
+                cs.resize((size_t)cap_c + 1);
+                xy.resize((size_t)cap_p * 2);
+                continue;
+            }
+            if (rc != MS_OK) {
+                if (k + 1 < n_sub) {      // drain the sub-batch already in flight
+                    ms_polygons drop{xy.data(), cap_p, cs.data(), cap_c, ss.data(), 0, 0};
+                    ms_wait_batch(d, (int)((k + 1) & 1), &drop);
+                }
+                return fail_with(rc);
+            }
+            append(pg, (int)(r.second - r.first));
+            break;
+        }
+    }
+}
+
+}  // namespace
+
+int ms_process_volume_host(ms_handle* h, const uint16_t* h_src, int w, int hgt, int64_t n_slices, ms_polygons* out, uint8_t* h_norm_u8,
+                           uint8_t* h_mask_u8) {
+    if (!h) return MS_ERR_ARG;
+    return guarded(h, [&] {
+        MS_REQUIRE(h_src && w > 0 && hgt > 0 && n_slices > 0 && n_slices < ((int64_t)1 << 31), MS_ERR_ARG, "process_volume: bad argument");
+        MS_REQUIRE(out && out->slice_start && out->contour_start && (out->xy || out->cap_points == 0), MS_ERR_ARG,
+                   "ms_polygons: null buffer (slice_start needs n_slices + 1 entries)");
+        MS_REQUIRE(h->unet.loaded(), MS_ERR_STATE, "no weights loaded");
+        std::vector<ms_handle*> devs{h};
+        devs.insert(devs.end(), h->peers.begin(), h->peers.end());
+        const int G = (int)std::min<int64_t>((int64_t)devs.size(), n_slices);
+        std::vector<VolumePart> parts((size_t)G);
+        for (int g = 0; g < G; ++g) {
+            const auto r = block_of(n_slices, G, g);
+            parts[g].dev = devs[g];
+            parts[g].first = r.first;
+            parts[g].count = r.second - r.first;
+        }
+        std::vector<std::thread> th;
+        for (int g = 1; g < G; ++g) th.emplace_back(volume_worker, std::ref(parts[g]), h_src, w, hgt, h_norm_u8, h_mask_u8);
+        volume_worker(parts[0], h_src, w, hgt, h_norm_u8, h_mask_u8);
+        for (auto& t : th) t.join();
+        MS_CUDA(cudaSetDevice(h->device));
+        g_counter = &h->counter;
+        for (const auto& V : parts)
+            if (V.status != MS_OK) fail(V.status, "device " + std::to_string(V.dev->device) + ": " + V.error);
+        // concatenate in slice order
+        int64_t nc = 0, np = 0;
+        for (const auto& V : parts) {
+            nc += (int64_t)V.per_contour.size();
+            np += (int64_t)V.xy.size() / 2;
+        }
+        out->n_contours = nc;
+        out->n_points = np;
+        MS_REQUIRE(out->cap_contours >= nc && out->cap_points >= np, MS_ERR_CAPACITY,
+                   "polygon buffers too small: need " + std::to_string(nc) + " contours, " + std::to_string(np) + " points");
+        int64_t s = 0, c = 0, p = 0;
+        out->slice_start[0] = 0;
+        out->contour_start[0] = 0;
+        for (const auto& V : parts) {
+            for (int32_t k : V.per_slice) {
+                out->slice_start[s + 1] = out->slice_start[s] + k;
+                ++s;
+            }
+            for (int32_t k : V.per_contour) {
+                out->contour_start[c + 1] = out->contour_start[c] + k;
+                ++c;
+            }
+            if (!V.xy.empty()) std::memcpy(out->xy + 2 * p, V.xy.data(), V.xy.size() * 4);
+            p += (int64_t)V.xy.size() / 2;
+        }
+    });
+}
+
 // ---------------------------------------------------------------- instrumentation
-int64_t ms_launch_count(ms_handle* h) { return h ? h->counter.n : 0; }
+int64_t ms_launch_count(ms_handle* h) {
+    if (!h) return 0;
+    int64_t n = h->counter.n;
+    for (const ms_handle* c : h->peers) n += c->counter.n;
+    return n;
+}
+int ms_device_count(ms_handle* h) { return h ? 1 + (int)h->peers.size() : 0; }
 int ms_layer_count(ms_handle* h) { return h && h->unet.loaded() ? (int)h->unet.layers().size() : 0; }
 const char* ms_layer_name(ms_handle* h, int layer) {
     if (!h || !h->unet.loaded() || layer < 0 || layer >= (int)h->unet.layers().size()) return "";
