@@ -219,6 +219,16 @@ MS_API int ms_process_directory(ms_handle* h, const char* input_dir, int w, int 
 MS_API int64_t ms_polygons_to_json(const int32_t* xy, const int32_t* contour_start, int n_contours,
                                    const char* base_name, int orig_w, int orig_h, char* dst, int64_t cap);
 
+/* The same document for every slice of a polygon set at once, formatted by `n_threads` host threads (0 = all cores):
+ * the host stage that follows the GPU at > 10 k slices/s.  Texts are concatenated into `dst`
+ * (no NUL) in slice order, offsets[s] .. offsets[s + 1] delimiting slice s (offsets has n_slices + 1 entries, may be
+ * NULL); a slice without contours contributes nothing, as the reference writes no file for it
+ * (src/mask2polygon.cpp:183-186).  base_names[s] is the stem written into "imagePath".  Returns the total length; when
+ * it exceeds `cap` nothing is copied (call again with a larger buffer), negative ms_status on error. */
+MS_API int64_t ms_polygons_to_json_batch(const int32_t* xy, const int32_t* contour_start, const int32_t* slice_start, int n_slices,
+                                         const char* const* base_names, int orig_w, int orig_h, int n_threads, char* dst,
+                                         int64_t cap, int64_t* offsets);
+
 /* ---- instrumentation ------------------------------------------------------------------------- */
 
 /* Number of kernels this library launched on the handle since creation (bench.py `gpu_launches`). */

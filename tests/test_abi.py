@@ -97,3 +97,40 @@ def test_reference_main_links_unchanged(ms, tmp_path):
     assert out.returncode == 0
     assert "Error: Engine not initialized" in out.stderr
     assert "Exiting..." in out.stdout
+
+
+def test_json_batch_equals_per_slice_documents(ms):
+    """ms_polygons_to_json_batch (threaded, N2): per slice exactly the single-document formatter's bytes; slices without
+    contours contribute nothing (the reference writes no file for them, src/mask2polygon.cpp:183-186)."""
+    rng = np.random.default_rng(11)
+    per_slice = [[rng.integers(-5, 5000, (int(rng.integers(1, 300)), 2)).astype(np.int32) for _ in range(int(k))]
+                 for k in (2, 0, 1, 5, 0, 3, 1, 1, 0, 4)]
+    flat = [c for s in per_slice for c in s]
+    cs = np.zeros(len(flat) + 1, np.int32)
+    cs[1:] = np.cumsum([len(c) for c in flat])
+    ss = np.zeros(len(per_slice) + 1, np.int32)
+    ss[1:] = np.cumsum([len(s) for s in per_slice])
+    polys = ms.Polygons(np.concatenate(flat), cs, ss)
+    names = [f"vol.{i:03d}" for i in range(len(per_slice))]
+    for threads in (1, 3, 0):
+        buf, offs = ms.polygons_to_json_batch(polys, names, 1024, 768, n_threads=threads)
+        for i, s in enumerate(per_slice):
+            got = bytes(buf[offs[i]:offs[i + 1]]).decode()
+            assert got == (ms.polygons_to_json(s, names[i], 1024, 768) if s else ""), i
+    # too small a buffer: the needed size comes back and nothing is written
+    small = np.zeros(16, np.uint8)
+    buf, offs = ms.polygons_to_json_batch(polys, names, 1024, 768, buf=small)
+    assert buf.size == offs[-1] > 16 and (small == 0).all()
+
+
+def test_png_writer_and_simd_checksums(tmp_path):
+    """csrc/png_min.hpp on the host: PCLMULQDQ CRC-32 and SSSE3 Adler-32 == the table / scalar forms (random lengths and
+    alignments, known answers), and the row-streaming encoder round-trips through the decoder with valid chunk CRCs --
+    with the SIMD paths and with them switched off.  cv2 (libpng verifies CRC and Adler) reads its files."""
+    import cv2
+    exe = str(tmp_path / "png_check")
+    r = subprocess.run(["g++", "-O2", "-std=c++17", "-o", exe, os.path.join(ROOT, "tests", "hostsim", "png_check.cpp")], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-2000:]
+    for env in ({}, {"MEDSEG_SCALAR_CHECKSUMS": "1"}):
+        out = subprocess.run([exe], capture_output=True, text=True, env={**os.environ, **env}, timeout=120)
+        assert out.returncode == 0 and out.stdout.startswith("ok "), out.stdout

@@ -48,6 +48,20 @@ def main():
     rows["n_files"] = n
     rows["host_cores"] = os.cpu_count()
     rows["artefact_bytes_per_file"] = sum(os.path.getsize(os.path.join(out, f)) for f in os.listdir(out) if f.startswith("slice_0000"))
+    # every GPU of the box behind one handle ("devices"): the list is split into contiguous blocks, one pipeline per GPU
+    import torch
+    eng.cleanup()
+    g = torch.cuda.device_count()
+    if g > 1:
+        os.environ.pop("MEDSEG_WRITERS", None)
+        eng = ms.Engine({"weights": blob, "max_batch": 32, "devices": list(range(g))})
+        eng.process_directory(src, 512, 512, os.path.join(root, "warm_multi"))
+        out_m = os.path.join(root, "out_multi")
+        t0 = time.perf_counter()
+        found, good, bad = eng.process_directory(src, 512, 512, out_m)
+        dt = time.perf_counter() - t0
+        assert (found, good, bad) == (n, n, 0)
+        rows[f"directory_{g}_gpus_one_process"] = {"files_per_s": n / dt, "s": dt}
     print(json.dumps(rows))
     if len(sys.argv) > 2:
         json.dump(rows, open(sys.argv[2], "w"), indent=1)

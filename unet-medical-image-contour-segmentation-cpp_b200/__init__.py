@@ -80,6 +80,7 @@ ABI = {
     "ms_process_raw_files": (_I, [_P, C.POINTER(C.c_char_p), C.POINTER(C.c_char_p), _L, _I, _I, _P, C.POINTER(_L), C.POINTER(_L)]),
     "ms_process_directory": (_I, [_P, C.c_char_p, _I, _I, C.c_char_p, _I, _I, _I, C.POINTER(_L), C.POINTER(_L), C.POINTER(_L)]),
     "ms_polygons_to_json": (_L, [_P, _P, _I, C.c_char_p, _I, _I, _P, _L]),
+    "ms_polygons_to_json_batch": (_L, [_P, _P, _P, _I, C.POINTER(C.c_char_p), _I, _I, _I, _P, _L, _P]),
     "ms_launch_count": (_L, [_P]),
     "ms_time_layer": (_I, [_P, _I, _I, _I, C.POINTER(C.c_float), C.POINTER(C.c_double)]),
     "ms_layer_count": (_I, [_P]),
@@ -445,6 +446,28 @@ def polygons_to_json(contours: Sequence[np.ndarray], base_name: str, orig_w: int
     buf = C.create_string_buffer(n)
     l.ms_polygons_to_json(_ptr(xy), _ptr(cs), len(contours), base_name.encode(), orig_w, orig_h, C.addressof(buf), n)
     return buf.raw.decode()
+
+
+def polygons_to_json_batch(polys: "Polygons", base_names: Sequence[str], orig_w: int, orig_h: int, n_threads: int = 0,
+                           buf: Optional[np.ndarray] = None):
+    """LabelMe documents of every slice of a polygon set, formatted by a pool of host threads (ms_polygons_to_json_batch).
+    Returns (uint8 buffer, offsets[n_slices + 1]); slice s is buf[offsets[s]:offsets[s + 1]] (empty when it has no contour)."""
+    l = lib()
+    n = len(polys.slice_start) - 1
+    names = (C.c_char_p * max(n, 1))(*[b.encode() for b in base_names])
+    offs = np.zeros(n + 1, np.int64)
+    xy = np.ascontiguousarray(polys.xy, np.int32)
+    cs = np.ascontiguousarray(polys.contour_start, np.int32)
+    ss = np.ascontiguousarray(polys.slice_start, np.int32)
+    if buf is None:
+        buf = np.empty(max(1 << 16, int(polys.n_points) * 100 + n * 1024), np.uint8)
+    while True:
+        total = l.ms_polygons_to_json_batch(_ptr(xy), _ptr(cs), _ptr(ss), n, names, orig_w, orig_h, n_threads, _ptr(buf), buf.size, _ptr(offs))
+        if total < 0:
+            raise MedsegError(int(total), "ms_polygons_to_json_batch failed")
+        if total <= buf.size:
+            return buf[:total], offs
+        buf = np.empty(int(total) + 1024, np.uint8)
 
 
 def make_weight_blob(path: str, n_classes: int = 3, seed: int = 1234) -> str:

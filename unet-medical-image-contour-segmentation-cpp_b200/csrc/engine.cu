@@ -740,6 +740,48 @@ int64_t ms_polygons_to_json(const int32_t* xy, const int32_t* contour_start, int
     }
 }
 
+int64_t ms_polygons_to_json_batch(const int32_t* xy, const int32_t* contour_start, const int32_t* slice_start, int n_slices,
+                                  const char* const* base_names, int orig_w, int orig_h, int n_threads, char* dst, int64_t cap,
+                                  int64_t* offsets) {
+    if (n_slices < 0 || !contour_start || !slice_start || !base_names || (n_slices > 0 && slice_start[n_slices] > 0 && !xy)) return MS_ERR_ARG;
+    try {
+        const int T = std::max(1, std::min(n_threads > 0 ? n_threads : (int)std::thread::hardware_concurrency(), std::max(1, n_slices)));
+        std::vector<std::string> text((size_t)n_slices);
+        std::atomic<int> next{0};
+        auto work = [&] {
+            for (int s = next.fetch_add(1); s < n_slices; s = next.fetch_add(1)) {
+                const int c0 = slice_start[s], nc = slice_start[s + 1] - c0;
+                // the reference writes no document for a slice without contours (src/mask2polygon.cpp:183-186)
+                if (nc > 0) json::labelme_append(text[s], xy, contour_start + c0, nc, base_names[s] ? base_names[s] : "", orig_w, orig_h);
+            }
+        };
+        std::vector<std::thread> th;
+        for (int t = 1; t < T; ++t) th.emplace_back(work);
+        work();
+        for (auto& t : th) t.join();
+        int64_t total = 0;
+        for (const auto& t : text) total += (int64_t)t.size();
+        if (offsets) {
+            int64_t o = 0;
+            for (int s = 0; s < n_slices; ++s) {
+                offsets[s] = o;
+                o += (int64_t)text[s].size();
+            }
+            offsets[n_slices] = o;
+        }
+        if (dst && cap >= total) {
+            int64_t o = 0;
+            for (const auto& t : text) {
+                std::memcpy(dst + o, t.data(), t.size());
+                o += (int64_t)t.size();
+            }
+        }
+        return total;
+    } catch (...) {
+        return MS_ERR_INTERNAL;
+    }
+}
+
 // ---------------------------------------------------------------- file path (P0 + N1 + N3)
 namespace {
 
@@ -781,9 +823,14 @@ void write_artefacts(SliceJob& J, const BatchHost& B, int w, int hgt, int net_w,
         bool ok_norm = true, ok_mask = true;
         auto write_norm = [&] { ok_norm = png::write_file(png_path, norm, net_w, net_h, 1); };                  // src/preprocess.cpp:121-122
         auto write_mask = [&] {
-            std::vector<uint8_t> vis(npx);
-            for (size_t i = 0; i < npx; ++i) vis[i] = mask[i] == 1 ? 128 : (mask[i] == 2 ? 255 : (mask[i] == fg_value ? 255 : 0));  // src/process.cpp:178-185
-            ok_mask = png::write_file(mask_path, vis.data(), net_w, net_h, 1);                                  // :236-239
+            uint8_t lut[256] = {0};                                                                              // src/process.cpp:178-185
+            lut[fg_value & 255] = 255;
+            lut[1] = 128;
+            lut[2] = 255;
+            ok_mask = png::write_bytes(mask_path, png::encode_rows(net_w, net_h, 1, [&](int y, uint8_t* dst) {   // :236-239
+                const uint8_t* m = mask + (size_t)y * net_w;
+                for (int x = 0; x < net_w; ++x) dst[x] = lut[m[x]];
+            }));
         };
         if (spare_threads >= 2) {
             helper_norm = std::thread(write_norm);
@@ -804,12 +851,25 @@ void write_artefacts(SliceJob& J, const BatchHost& B, int w, int hgt, int net_w,
             out << "Warning: No Contours Detected\n";                                         // :184 (no JSON is written)
         } else {
             out << "Extracted " << nc << " Contours\n";                                       // :187
-            // overlay with unmapped (network-space) contours, red, 1 px (src/mask2polygon.cpp:114-129, 189-193)
-            std::vector<uint8_t> rgb(npx * 3);
-            for (size_t i = 0; i < npx; ++i) rgb[3 * i] = rgb[3 * i + 1] = rgb[3 * i + 2] = norm[i];
-            draw_contours_red(rgb, net_w, net_h, B.uxy.data(), cstart, nc);
+            // overlay with unmapped (network-space) contours, red, 1 px (src/mask2polygon.cpp:114-129, 189-193): rows are
+            // expanded grey -> RGB and painted from a 1-bit contour map while the PNG is written
+            const std::vector<uint32_t> red = contour_bitmap(net_w, net_h, B.uxy.data(), cstart, nc);
+            const int rp = (net_w + 31) / 32;
             const std::string overlay_path = J.dir + "/" + J.base + "_contour_overlay.png";  // :190
-            MS_REQUIRE(png::write_file(overlay_path, rgb.data(), net_w, net_h, 3), MS_ERR_IO, "Fail to Save Overlay PNG: " + overlay_path);
+            const bool ok_overlay = png::write_bytes(overlay_path, png::encode_rows(net_w, net_h, 3, [&](int y, uint8_t* dst) {
+                const uint8_t* g = norm + (size_t)y * net_w;
+                const uint32_t* rb = red.data() + (size_t)y * rp;
+                for (int x = 0; x < net_w; ++x) {
+                    const uint8_t v = g[x];
+                    dst[3 * x] = dst[3 * x + 1] = dst[3 * x + 2] = v;
+                }
+                for (int wq = 0; wq < rp; ++wq)
+                    for (uint32_t m = rb[wq]; m; m &= m - 1) {
+                        const int x = wq * 32 + __builtin_ctz(m);
+                        dst[3 * x] = 255; dst[3 * x + 1] = 0; dst[3 * x + 2] = 0;
+                    }
+            }));
+            MS_REQUIRE(ok_overlay, MS_ERR_IO, "Fail to Save Overlay PNG: " + overlay_path);
             out << "Overlay Image Saved to: " << overlay_path << "\n";                        // :193
             const std::string out_json = J.dir + "/" + J.base + ".json";                      // :206
             std::ofstream f(out_json, std::ios::binary);
@@ -832,10 +892,12 @@ void write_artefacts(SliceJob& J, const BatchHost& B, int w, int hgt, int net_w,
     }
 }
 
-int writer_threads() {
+// writer threads of one pipeline: MEDSEG_WRITERS, else every host core, shared evenly when several GPUs of one handle
+// run their pipelines side by side
+int writer_threads(int share = 1) {
     if (const char* e = std::getenv("MEDSEG_WRITERS")) return std::max(1, std::atoi(e));
-    const unsigned hc = std::thread::hardware_concurrency();
-    return (int)std::min<unsigned>(std::max(1u, hc), 16u);
+    const unsigned hc = std::max(1u, std::thread::hardware_concurrency());
+    return std::max(2, (int)hc / std::max(1, share));
 }
 
 // Reads batch `k` of the job list into B.in (good slices packed), assigning slots.  Runs on the prefetch thread.
@@ -866,7 +928,7 @@ void read_batch(SliceJob* jobs, size_t first, size_t last, BatchHost& B, int w, 
 // working on a different batch.  Per-file failures are recorded in the jobs; only CUDA / argument errors throw.
 // `console`: where the reference's std::cout / std::cerr lines go -- straight out (null), or into a string the caller prints
 // in job order (a GPU of a multi-device handle must not interleave its lines with the others')
-void process_jobs_on(ms_handle* h, SliceJob* jobs, size_t n, int w, int hgt, bool report_errors, std::string* console) {
+void process_jobs_on(ms_handle* h, SliceJob* jobs, size_t n, int w, int hgt, bool report_errors, std::string* console, int share = 1) {
     MS_REQUIRE(h->unet.loaded(), MS_ERR_STATE, "no weights loaded (handle was created without a weight blob)");
     MS_REQUIRE(w > 0 && hgt > 0, MS_ERR_ARG, "bad slice size");
     const size_t mb = (size_t)h->max_batch;
@@ -942,8 +1004,8 @@ void process_jobs_on(ms_handle* h, SliceJob* jobs, size_t n, int w, int hgt, boo
             join_writers();                                   // batch k - 1 is on disk
             if (k > 0) report(k - 1, infer_ms[(k - 1) & 1]);
             next_job = r.first;
-            const int nt = std::min<int>(writer_threads(), std::max(nb, 1));
-            const int spare = writer_threads() / std::max(nb, 1) - 1;   // helper threads each slice may use
+            const int nt = std::min<int>(writer_threads(share), std::max(nb, 1));
+            const int spare = writer_threads(share) / std::max(nb, 1) - 1;   // helper threads each slice may use
             for (int t = 0; t < nt; ++t)
                 writers.emplace_back([&, r, k, spare] {
                     for (size_t i = next_job.fetch_add(1); i < r.second; i = next_job.fetch_add(1))
@@ -982,7 +1044,7 @@ void process_jobs(ms_handle* h, std::vector<SliceJob>& jobs, int w, int hgt, boo
         try {
             MS_CUDA(cudaSetDevice(d->device));
             g_counter = &d->counter;
-            process_jobs_on(d, jobs.data() + r.first, (size_t)(r.second - r.first), w, hgt, report_errors, &parts[g].console);
+            process_jobs_on(d, jobs.data() + r.first, (size_t)(r.second - r.first), w, hgt, report_errors, &parts[g].console, G);
         } catch (const Error& e) {
             parts[g].status = e.code;
             parts[g].error = e.what;

@@ -13,6 +13,10 @@
 #include <cstring>
 #include <string>
 #include <vector>
+#if defined(__x86_64__) || defined(__i386__)
+#include <immintrin.h>
+#define MS_PNG_X86 1
+#endif
 
 namespace ms {
 namespace png {
@@ -31,7 +35,7 @@ struct CrcTables {
             for (int k = 1; k < 8; ++k) t[k][i] = t[0][t[k - 1][i] & 0xFF] ^ (t[k - 1][i] >> 8);
     }
 };
-inline uint32_t crc32_update(uint32_t crc, const uint8_t* p, size_t n) {
+inline uint32_t crc32_table(uint32_t crc, const uint8_t* p, size_t n) {
     static const CrcTables T;   // thread-safe initialisation (C++11 magic static)
     crc = ~crc;
     while (n >= 8) {
@@ -47,9 +51,114 @@ inline uint32_t crc32_update(uint32_t crc, const uint8_t* p, size_t n) {
     for (size_t i = 0; i < n; ++i) crc = T.t[0][(crc ^ p[i]) & 0xFF] ^ (crc >> 8);
     return ~crc;
 }
-// Adler-32 with the modulo deferred to once per 5552 bytes (the largest run that cannot overflow 32 bits)
-inline uint32_t adler32(const uint8_t* p, size_t n) {
+#ifdef MS_PNG_X86
+// Carry-less-multiply folding (Gopal et al., "Fast CRC Computation for Generic Polynomials Using PCLMULQDQ"): 64 bytes per
+// iteration in four 128-bit lanes.  `crc` is the running (already inverted) register; len >= 64 and a multiple of 16.
+__attribute__((target("pclmul,sse4.1"))) inline uint32_t crc32_clmul(uint32_t crc, const uint8_t* buf, size_t len) {
+    alignas(16) static const uint64_t k1k2[2] = {0x0154442bd4ull, 0x01c6e41596ull};
+    alignas(16) static const uint64_t k3k4[2] = {0x01751997d0ull, 0x00ccaa009eull};
+    alignas(16) static const uint64_t k5k0[2] = {0x0163cd6124ull, 0x0000000000ull};
+    alignas(16) static const uint64_t poly[2] = {0x01db710641ull, 0x01f7011641ull};
+    __m128i x0, x1, x2, x3, x4, x5, x6, x7, x8, y5, y6, y7, y8;
+    x1 = _mm_loadu_si128((const __m128i*)(buf + 0x00));
+    x2 = _mm_loadu_si128((const __m128i*)(buf + 0x10));
+    x3 = _mm_loadu_si128((const __m128i*)(buf + 0x20));
+    x4 = _mm_loadu_si128((const __m128i*)(buf + 0x30));
+    x1 = _mm_xor_si128(x1, _mm_cvtsi32_si128((int)crc));
+    x0 = _mm_load_si128((const __m128i*)k1k2);
+    buf += 64;
+    len -= 64;
+    while (len >= 64) {
+        x5 = _mm_clmulepi64_si128(x1, x0, 0x00);
+        x6 = _mm_clmulepi64_si128(x2, x0, 0x00);
+        x7 = _mm_clmulepi64_si128(x3, x0, 0x00);
+        x8 = _mm_clmulepi64_si128(x4, x0, 0x00);
+        x1 = _mm_clmulepi64_si128(x1, x0, 0x11);
+        x2 = _mm_clmulepi64_si128(x2, x0, 0x11);
+        x3 = _mm_clmulepi64_si128(x3, x0, 0x11);
+        x4 = _mm_clmulepi64_si128(x4, x0, 0x11);
+        y5 = _mm_loadu_si128((const __m128i*)(buf + 0x00));
+        y6 = _mm_loadu_si128((const __m128i*)(buf + 0x10));
+        y7 = _mm_loadu_si128((const __m128i*)(buf + 0x20));
+        y8 = _mm_loadu_si128((const __m128i*)(buf + 0x30));
+        x1 = _mm_xor_si128(_mm_xor_si128(x1, x5), y5);
+        x2 = _mm_xor_si128(_mm_xor_si128(x2, x6), y6);
+        x3 = _mm_xor_si128(_mm_xor_si128(x3, x7), y7);
+        x4 = _mm_xor_si128(_mm_xor_si128(x4, x8), y8);
+        buf += 64;
+        len -= 64;
+    }
+    x0 = _mm_load_si128((const __m128i*)k3k4);      // fold the four lanes into one
+    x5 = _mm_clmulepi64_si128(x1, x0, 0x00);
+    x1 = _mm_clmulepi64_si128(x1, x0, 0x11);
+    x1 = _mm_xor_si128(_mm_xor_si128(x1, x2), x5);
+    x5 = _mm_clmulepi64_si128(x1, x0, 0x00);
+    x1 = _mm_clmulepi64_si128(x1, x0, 0x11);
+    x1 = _mm_xor_si128(_mm_xor_si128(x1, x3), x5);
+    x5 = _mm_clmulepi64_si128(x1, x0, 0x00);
+    x1 = _mm_clmulepi64_si128(x1, x0, 0x11);
+    x1 = _mm_xor_si128(_mm_xor_si128(x1, x4), x5);
+    while (len >= 16) {
+        x2 = _mm_loadu_si128((const __m128i*)buf);
+        x5 = _mm_clmulepi64_si128(x1, x0, 0x00);
+        x1 = _mm_clmulepi64_si128(x1, x0, 0x11);
+        x1 = _mm_xor_si128(_mm_xor_si128(x1, x2), x5);
+        buf += 16;
+        len -= 16;
+    }
+    x2 = _mm_clmulepi64_si128(x1, x0, 0x10);         // 128 -> 64 bits
+    x3 = _mm_setr_epi32(~0, 0, ~0, 0);
+    x1 = _mm_srli_si128(x1, 8);
+    x1 = _mm_xor_si128(x1, x2);
+    x0 = _mm_loadl_epi64((const __m128i*)k5k0);
+    x2 = _mm_srli_si128(x1, 4);
+    x1 = _mm_and_si128(x1, x3);
+    x1 = _mm_clmulepi64_si128(x1, x0, 0x00);
+    x1 = _mm_xor_si128(x1, x2);
+    x0 = _mm_load_si128((const __m128i*)poly);       // Barrett reduction to 32 bits
+    x2 = _mm_and_si128(x1, x3);
+    x2 = _mm_clmulepi64_si128(x2, x0, 0x10);
+    x2 = _mm_and_si128(x2, x3);
+    x2 = _mm_clmulepi64_si128(x2, x0, 0x00);
+    x1 = _mm_xor_si128(x1, x2);
+    return (uint32_t)_mm_extract_epi32(x1, 1);
+}
+inline bool cpu_has_clmul() {
+    static const bool v = __builtin_cpu_supports("pclmul") && __builtin_cpu_supports("sse4.1");
+    return v;
+}
+inline bool cpu_has_ssse3() {
+    static const bool v = __builtin_cpu_supports("ssse3");
+    return v;
+}
+#endif
+
+// CRC-32 (IEEE) of p[0..n) continuing from `crc` (0 to start): PCLMULQDQ folding where the CPU has it, slicing-by-8
+// tables otherwise and for the tail.  MEDSEG_SCALAR_CHECKSUMS (read by the tests) forces the table form.
+inline bool& force_scalar_checksums() {
+    static bool v = std::getenv("MEDSEG_SCALAR_CHECKSUMS") != nullptr;
+    return v;
+}
+inline uint32_t crc32_update(uint32_t crc, const uint8_t* p, size_t n) {
+#ifdef MS_PNG_X86
+    if (n >= 64 && cpu_has_clmul() && !force_scalar_checksums()) {
+        const size_t body = n & ~(size_t)15;
+        crc = ~crc32_clmul(~crc, p, body);
+        p += body;
+        n -= body;
+    }
+#endif
+    return n ? crc32_table(crc, p, n) : crc;
+}
+
+// Adler-32 as two running sums, so scanlines can be fed one at a time: start from {1, 0}, finish with value().
+struct Adler {
     uint32_t a = 1, b = 0;
+    uint32_t value() const { return (b << 16) | a; }
+};
+// scalar form: the modulo deferred to once per 5552 bytes (the largest run that cannot overflow 32 bits)
+inline void adler_scalar(Adler& s, const uint8_t* p, size_t n) {
+    uint32_t a = s.a, b = s.b;
     while (n > 0) {
         const size_t k = n < 5552 ? n : 5552;
         for (size_t i = 0; i < k; ++i) {
@@ -61,7 +170,56 @@ inline uint32_t adler32(const uint8_t* p, size_t n) {
         p += k;
         n -= k;
     }
-    return (b << 16) | a;
+    s.a = a;
+    s.b = b;
+}
+#ifdef MS_PNG_X86
+// 32 bytes per step.  Over a block of m steps starting from (a0, b0):
+//   a = a0 + sum(bytes),   b = b0 + 32 m a0 + 32 * sum_j(bytes before step j) + sum_j sum_i (32 - i) * byte[j][i]
+// all three sums fit 32-bit lanes for blocks of <= 5536 bytes; the modulo once per block.
+__attribute__((target("ssse3"))) inline void adler_ssse3(Adler& s, const uint8_t* p, size_t n) {
+    uint64_t a = s.a, b = s.b;
+    const __m128i w_hi = _mm_setr_epi8(32, 31, 30, 29, 28, 27, 26, 25, 24, 23, 22, 21, 20, 19, 18, 17);
+    const __m128i w_lo = _mm_setr_epi8(16, 15, 14, 13, 12, 11, 10, 9, 8, 7, 6, 5, 4, 3, 2, 1);
+    const __m128i zero = _mm_setzero_si128(), ones = _mm_set1_epi16(1);
+    while (n >= 32) {
+        const size_t k = n < 5536 ? (n & ~(size_t)31) : 5536;      // 5536 = 173 * 32
+        const uint64_t m = k / 32;
+        __m128i va = zero, vs = zero, vb = zero;
+        for (size_t i = 0; i < k; i += 32) {
+            const __m128i d0 = _mm_loadu_si128((const __m128i*)(p + i)), d1 = _mm_loadu_si128((const __m128i*)(p + i + 16));
+            vs = _mm_add_epi32(vs, va);
+            va = _mm_add_epi32(va, _mm_add_epi32(_mm_sad_epu8(d0, zero), _mm_sad_epu8(d1, zero)));
+            vb = _mm_add_epi32(vb, _mm_madd_epi16(_mm_maddubs_epi16(d0, w_hi), ones));
+            vb = _mm_add_epi32(vb, _mm_madd_epi16(_mm_maddubs_epi16(d1, w_lo), ones));
+        }
+        alignas(16) uint32_t ta[4], ts[4], tb[4];
+        _mm_store_si128((__m128i*)ta, va);
+        _mm_store_si128((__m128i*)ts, vs);
+        _mm_store_si128((__m128i*)tb, vb);
+        const uint64_t sum = (uint64_t)ta[0] + ta[2];              // sad_epu8 leaves its sums in lanes 0 and 2
+        const uint64_t before = (uint64_t)ts[0] + ts[2];
+        const uint64_t weighted = (uint64_t)tb[0] + tb[1] + tb[2] + tb[3];
+        b = (b + 32 * m * a + 32 * before + weighted) % 65521u;
+        a = (a + sum) % 65521u;
+        p += k;
+        n -= k;
+    }
+    s.a = (uint32_t)a;
+    s.b = (uint32_t)b;
+    adler_scalar(s, p, n);
+}
+#endif
+inline void adler_update(Adler& s, const uint8_t* p, size_t n) {
+#ifdef MS_PNG_X86
+    if (n >= 64 && cpu_has_ssse3() && !force_scalar_checksums()) return adler_ssse3(s, p, n);
+#endif
+    adler_scalar(s, p, n);
+}
+inline uint32_t adler32(const uint8_t* p, size_t n) {
+    Adler s;
+    adler_update(s, p, n);
+    return s.value();
 }
 
 inline void put32(std::vector<uint8_t>& v, uint32_t x) {
@@ -79,59 +237,82 @@ inline void chunk(std::vector<uint8_t>& out, const char* type, const std::vector
     put32(out, crc32_update(0, out.data() + start, out.size() - start));
 }
 
-inline std::vector<uint8_t> encode(const uint8_t* pixels, int w, int h, int channels) {
-    std::vector<uint8_t> out = {0x89, 'P', 'N', 'G', 0x0D, 0x0A, 0x1A, 0x0A};
-    std::vector<uint8_t> ihdr;
-    put32(ihdr, (uint32_t)w);
-    put32(ihdr, (uint32_t)h);
-    ihdr.push_back(8);
-    ihdr.push_back(channels == 3 ? 2 : 0);
-    ihdr.push_back(0); ihdr.push_back(0); ihdr.push_back(0);
-    chunk(out, "IHDR", ihdr);
-    // raw scanlines, filter type 0
+// Encoder.  `fill_row(y, dst)` writes scanline y (w * channels bytes) -- the pixels never exist as a second image: the
+// normalised slice is copied, the mask goes through its LUT, the overlay is expanded grey -> RGB with the contour
+// pixels painted, all row by row, straight into the zlib stream of stored blocks (which is pure layout: the PNG row
+// filter byte 0, then the row; a 5-byte block header every 65,535 stream bytes).
+template <class FillRow>
+inline std::vector<uint8_t> encode_rows(int w, int h, int channels, FillRow&& fill_row) {
     const size_t row = (size_t)w * channels, raw_n = (row + 1) * (size_t)h;
-    std::vector<uint8_t> raw(raw_n);
-    for (int y = 0; y < h; ++y) {
-        uint8_t* dst = raw.data() + (size_t)y * (row + 1);
-        dst[0] = 0;
-        std::memcpy(dst + 1, pixels + (size_t)y * row, row);
-    }
-    // IDAT = zlib stream of stored blocks, written in place: length | "IDAT" | 78 01 | blocks | adler | crc
     const size_t n_blocks = raw_n == 0 ? 1 : (raw_n + 65534) / 65535;
     const size_t z_n = 2 + n_blocks * 5 + raw_n + 4;
-    const size_t idat_at = out.size();
-    out.resize(idat_at + 4 + 4 + z_n + 4);
-    uint8_t* q = out.data() + idat_at;
-    store32(q, (uint32_t)z_n);
-    std::memcpy(q + 4, "IDAT", 4);
-    uint8_t* z = q + 8;
+    std::vector<uint8_t> out(8 + 25 + 12 + z_n + 12);
+    uint8_t* o = out.data();
+    static const uint8_t sig[8] = {0x89, 'P', 'N', 'G', 0x0D, 0x0A, 0x1A, 0x0A};
+    std::memcpy(o, sig, 8);
+    o += 8;
+    store32(o, 13);                                      // IHDR
+    std::memcpy(o + 4, "IHDR", 4);
+    store32(o + 8, (uint32_t)w);
+    store32(o + 12, (uint32_t)h);
+    o[16] = 8; o[17] = channels == 3 ? 2 : 0; o[18] = 0; o[19] = 0; o[20] = 0;
+    store32(o + 21, crc32_update(0, o + 4, 17));
+    o += 25;
+    uint8_t* idat = o;                                   // IDAT = length | "IDAT" | 78 01 | blocks | adler | crc
+    store32(idat, (uint32_t)z_n);
+    std::memcpy(idat + 4, "IDAT", 4);
+    uint8_t* z = idat + 8;
     *z++ = 0x78;
     *z++ = 0x01;
-    size_t pos = 0;
-    for (size_t blk = 0; blk < n_blocks; ++blk) {
-        const size_t n = std::min<size_t>(65535, raw_n - pos);
-        *z++ = blk + 1 == n_blocks ? 1 : 0;
-        *z++ = (uint8_t)(n & 0xFF);
-        *z++ = (uint8_t)(n >> 8);
-        *z++ = (uint8_t)(~n & 0xFF);
-        *z++ = (uint8_t)((~n >> 8) & 0xFF);
-        std::memcpy(z, raw.data() + pos, n);
-        z += n;
-        pos += n;
+    std::vector<uint8_t> line(row + 1);
+    line[0] = 0;                                         // filter type 0
+    Adler ad;
+    size_t pos = 0, room = 0, blk = 0;                   // stream position, bytes left in the current stored block
+    for (int y = 0; y < h; ++y) {
+        fill_row(y, line.data() + 1);
+        adler_update(ad, line.data(), row + 1);
+        const uint8_t* src = line.data();
+        size_t left = row + 1;
+        while (left) {
+            if (room == 0) {
+                const size_t n = std::min<size_t>(65535, raw_n - pos);
+                *z++ = ++blk == n_blocks ? 1 : 0;
+                *z++ = (uint8_t)(n & 0xFF);
+                *z++ = (uint8_t)(n >> 8);
+                *z++ = (uint8_t)(~n & 0xFF);
+                *z++ = (uint8_t)((~n >> 8) & 0xFF);
+                room = n;
+            }
+            const size_t k = std::min(left, room);
+            std::memcpy(z, src, k);
+            z += k; src += k; left -= k; room -= k; pos += k;
+        }
     }
-    store32(z, adler32(raw.data(), raw_n));
+    if (raw_n == 0) { *z++ = 1; *z++ = 0; *z++ = 0; *z++ = 0xFF; *z++ = 0xFF; }
+    store32(z, ad.value());
     z += 4;
-    store32(z, crc32_update(0, q + 4, 4 + z_n));
-    chunk(out, "IEND", {});
+    store32(z, crc32_update(0, idat + 4, 4 + z_n));
+    z += 4;
+    store32(z, 0);                                       // IEND
+    std::memcpy(z + 4, "IEND", 4);
+    store32(z + 8, crc32_update(0, z + 4, 4));
     return out;
 }
 
-inline bool write_file(const std::string& path, const uint8_t* pixels, int w, int h, int channels) {
-    std::vector<uint8_t> bytes = encode(pixels, w, h, channels);
+inline std::vector<uint8_t> encode(const uint8_t* pixels, int w, int h, int channels) {
+    const size_t row = (size_t)w * channels;
+    return encode_rows(w, h, channels, [&](int y, uint8_t* dst) { std::memcpy(dst, pixels + (size_t)y * row, row); });
+}
+
+inline bool write_bytes(const std::string& path, const std::vector<uint8_t>& bytes) {
     FILE* f = std::fopen(path.c_str(), "wb");
     if (!f) return false;
+    std::setvbuf(f, nullptr, _IONBF, 0);                 // one write() of the whole file, no stdio copy
     const bool ok = std::fwrite(bytes.data(), 1, bytes.size(), f) == bytes.size();
     return std::fclose(f) == 0 && ok;
+}
+inline bool write_file(const std::string& path, const uint8_t* pixels, int w, int h, int channels) {
+    return write_bytes(path, encode(pixels, w, h, channels));
 }
 
 // ---------------------------------------------------------------- reader
