@@ -6,6 +6,8 @@
 #include <algorithm>
 #include <cstdint>
 #include <cstdio>
+#include <cstdlib>
+#include <utility>
 #include <mutex>
 #include <set>
 #include <string>
@@ -65,6 +67,39 @@ inline void set_max_dynamic_smem(Kernel kernel, int bytes) {
     if (done.count(key)) return;
     MS_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
     done.insert(key);
+}
+
+// Programmatic dependent launch (PDL).  Every layer kernel announces, right after its set-up, that its successor may be
+// scheduled (`launch_dependents`); the successor is launched with programmatic stream serialisation and runs ITS set-up
+// (tensor-map prefetch, barrier init, TMEM allocation, resident-weight TMA loads) on whatever SMs the predecessor's tail
+// leaves idle, then blocks in `wait` -- which returns once the predecessor grid has completed and its writes are visible --
+// before it touches an activation.  All of a kernel's global writes depend on loads issued after its wait, so no write can
+// overtake the predecessor either.  MEDSEG_PDL=0 falls back to plain stream order.
+#if defined(__CUDACC__)
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+#endif
+inline bool pdl_enabled() {
+    static const bool on = [] {
+        const char* e = std::getenv("MEDSEG_PDL");
+        return !(e && e[0] == '0');
+    }();
+    return on;
+}
+// kernel<<<grid, block, smem, st>>>(args...) with the PDL attribute when `dependent` (the kernel calls pdl_wait())
+template <class... KArgs, class... Args>
+inline void launch_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, bool dependent, Args&&... args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = (dependent && pdl_enabled()) ? 1 : 0;
+    MS_CUDA(cudaLaunchKernelEx(&cfg, kernel, KArgs(std::forward<Args>(args))...));
 }
 
 static inline int cdiv(int a, int b) { return (a + b - 1) / b; }

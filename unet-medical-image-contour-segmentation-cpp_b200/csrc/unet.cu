@@ -60,6 +60,8 @@ __global__ void __launch_bounds__(256) first_conv_kernel(const uint8_t* __restri
     const size_t img = (size_t)(blockIdx.x / blocks_per_img) * H * W;
     const int pitch = W + 2;
     for (int i = threadIdx.x; i < 64 * 9 + 64; i += 256) sw[i] = i < 576 ? w[i] : bias[i - 576];
+    pdl_launch_dependents();
+    pdl_wait();                   // `in` is the preprocess kernel's output
     if (VEC16) {
         // 16 pixels per load, all of a thread's loads in flight together (the scalar form below spends a fifth of the
         // kernel waiting on dependent byte loads: profiles/r1_ncu_full_forward_b32.json, enc1a)
@@ -251,7 +253,7 @@ void launch_tc(const UNetLayer& L, const tc::ConvArgs& a, int sm_count, cudaStre
     set_max_dynamic_smem(tc::conv_gemm_kernel<BN, EPI>, C::SMEM_BYTES);
     const int total = a.batch * (a.H / tc::TILE_H) * (a.W / tc::TILE_W) * (a.n_total / BN);
     const int grid = std::min(total, sm_count);
-    tc::conv_gemm_kernel<BN, EPI><<<grid, tc::NUM_THREADS, C::SMEM_BYTES, st>>>(L.map_a, L.map_b, L.map_out, a);
+    launch_kernel(tc::conv_gemm_kernel<BN, EPI>, dim3(grid), dim3(tc::NUM_THREADS), C::SMEM_BYTES, st, true, L.map_a, L.map_b, L.map_out, a);
     MS_LAUNCH_CHECK();
 }
 
@@ -261,7 +263,8 @@ void launch_halo_p(const UNetLayer& L, const tc::ConvArgs& a, int sm_count, cuda
     set_max_dynamic_smem(tc::conv_halo_kernel<BN, EPI, RKC, PITCH>, C::SMEM_BYTES);
     const int total = a.batch * (a.H / tc::HALO_TH) * (a.W / tc::HALO_TW);
     const int grid = std::min(total, sm_count);
-    tc::conv_halo_kernel<BN, EPI, RKC, PITCH><<<grid, tc::NUM_THREADS, C::SMEM_BYTES, st>>>(L.map_a_row, L.map_b, L.map_out, a);
+    launch_kernel(tc::conv_halo_kernel<BN, EPI, RKC, PITCH>, dim3(grid), dim3(tc::NUM_THREADS), C::SMEM_BYTES, st, true, L.map_a_row, L.map_b,
+                  L.map_out, a);
     MS_LAUNCH_CHECK();
 }
 template <int BN, int EPI, int RKC>
@@ -275,7 +278,8 @@ void launch_halo2(const UNetLayer& L, const tc::ConvArgs& a, int sm_count, cudaS
     set_max_dynamic_smem(tc::conv_halo2_kernel<BN, EPI, RKC>, C::SMEM_BYTES);
     const int pairs = a.batch * (a.H / tc::HALO_TH) * (a.W / tc::HALO_TW) / 2 * (a.n_total / BN);
     const int grid = 2 * std::min(pairs, sm_count / 2);
-    tc::conv_halo2_kernel<BN, EPI, RKC><<<grid, tc::HALO2_THREADS, C::SMEM_BYTES, st>>>(L.map_a_row, b_half ? *b_half : L.map_b_half, L.map_out, a);
+    launch_kernel(tc::conv_halo2_kernel<BN, EPI, RKC>, dim3(grid), dim3(tc::HALO2_THREADS), C::SMEM_BYTES, st, true, L.map_a_row,
+                  b_half ? *b_half : L.map_b_half, L.map_out, a);
     MS_LAUNCH_CHECK();
 }
 
@@ -557,10 +561,10 @@ void UNet::run_layer(int li, const uint8_t* d_in_u8, int batch, uint8_t* d_mask,
         MS_REQUIRE(smem <= 200 * 1024, MS_ERR_ARG, "network width too large for the first-conv row buffer");
         if (w % 16 == 0 && (reinterpret_cast<uintptr_t>(d_in_u8) & 15) == 0) {
             if (smem > 48 * 1024) set_max_dynamic_smem(first_conv_kernel<true>, 200 * 1024);   // nets wider than ~1200 px
-            first_conv_kernel<true><<<grid, 256, smem, st>>>(d_in_u8, h, w, L.w_f32, L.bias, bufs_[L.dst].p);
+            launch_kernel(first_conv_kernel<true>, dim3(grid), dim3(256), smem, st, true, d_in_u8, h, w, (const float*)L.w_f32, (const float*)L.bias, bufs_[L.dst].p);
         } else {
             if (smem > 48 * 1024) set_max_dynamic_smem(first_conv_kernel<false>, 200 * 1024);
-            first_conv_kernel<false><<<grid, 256, smem, st>>>(d_in_u8, h, w, L.w_f32, L.bias, bufs_[L.dst].p);
+            launch_kernel(first_conv_kernel<false>, dim3(grid), dim3(256), smem, st, true, d_in_u8, h, w, (const float*)L.w_f32, (const float*)L.bias, bufs_[L.dst].p);
         }
         MS_LAUNCH_CHECK();
         return;

@@ -478,12 +478,14 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
+    pdl_launch_dependents();
 
     if (warp == 0) {
         // ===================================================================== TMA producer
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
+            pdl_wait();            // the activations are the previous layer's output
             for (int t = blockIdx.x; t < total; t += gridDim.x) {
                 const TileCoord tc = decode_tile(t, n_tiles, tiles_x, tiles_y, BLOCK_N, TILE_W, TILE_H);
                 for (int tap = 0; tap < args.taps; ++tap) {
@@ -653,6 +655,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a_row, const __grid_con
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
+    pdl_launch_dependents();
 
     if (warp == 0) {
         // ===================================================================== TMA producer
@@ -664,6 +667,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a_row, const __grid_con
             }
             int sa = 0, sb = 0;
             uint32_t pa = 0, pb = 0;
+            pdl_wait();            // weights are in flight; the activations are the previous layer's output
             for (int t = blockIdx.x; t < total; t += gridDim.x) {
                 const TileCoord tc = decode_tile(t, 1, tiles_x, tiles_y, BLOCK_N, HALO_TW, HALO_TH);
                 for (int kc = 0; kc < kchunks; ++kc) {
@@ -894,6 +898,7 @@ conv_halo2_kernel(const __grid_constant__ CUtensorMap map_a_halo, const __grid_c
     cluster_sync_all();          // barrier inits of both CTAs are visible before any remote arrive / TMA signal
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
+    pdl_launch_dependents();
 
     if (warp == 0) {
         // ===================================================================== TMA producer (both CTAs)
@@ -906,6 +911,7 @@ conv_halo2_kernel(const __grid_constant__ CUtensorMap map_a_halo, const __grid_c
             }
             int sa = 0;
             uint32_t pa = 0;
+            pdl_wait();            // weights are in flight; the activations are the previous layer's output
             for (int p = pair_id; p < total_pairs; p += n_pairs) {
                 const TileCoord tc = decode_tile(2 * (p / n_tiles) + (int)rank, 1, tiles_x, tiles_y, BLOCK_N, HALO_TW, HALO_TH);
                 for (int kc = 0; kc < kchunks; ++kc) {
