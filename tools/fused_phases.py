@@ -35,7 +35,9 @@ def main():
         print(f"{n:28s} {int(t[i + 1] - t[i]):9d} cycles  {100.0 * (t[i + 1] - t[i]) / total:5.1f} %")
     print(f"{'total':28s} {int(total):9d} cycles  (~{total / 1.9e3:.1f} us at 1.9 GHz)")
     d = np.array(buf[20:25], dtype=np.int64)
-    print("holes label: scan+init %d | merge %d | compress %d | area %d cycles; runs %d" % (d[0] - t[1], d[1] - d[0], d[2] - d[1], d[3] - d[2], d[4]))
+    q = np.array(buf[20:32], dtype=np.int64)
+    print("holes label: scan+init %d | hook sweep %d | compress#1 %d (%d rounds) | leftover sweep %d | compress#2 %d (%d rounds) | head x %d | tails+flush %d cycles; runs %d"
+          % (q[0] - t[1], q[6] - q[0], q[1] - q[6], q[5] // 100, q[7] - q[1], q[2] - q[7], q[5] % 100, q[8] - q[2], q[3] - q[8], q[4]))
     e.cleanup()
 
 

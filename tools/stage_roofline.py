@@ -48,6 +48,8 @@ def main():
         t = timed(lambda: eng.preprocess_dev(d_src.data_ptr(), 512, 512, batch, d_u8.data_ptr(), d_bf.data_ptr(), st))
         by = batch * (2 * 512 * 512 + 2 * 512 * 512)
         rows.append({"stage": "K1 preprocess (u16 -> u8 + bf16)", "batch": batch, "ms": t, "alg_bytes": by, "GBps": by / t / 1e6})
+        t = timed(lambda: eng.preprocess_dev(d_src.data_ptr(), 512, 512, batch, d_u8.data_ptr(), 0, st))
+        rows.append({"stage": "K1 preprocess (u16 -> u8, as in the pipeline)", "batch": batch, "ms": t, "alg_bytes": by, "GBps": by / t / 1e6})
         # a realistic class mask: body ellipse = 2, organs = 1, speckle
         masks = []
         for i in range(8):

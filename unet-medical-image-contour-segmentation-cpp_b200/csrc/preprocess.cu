@@ -12,6 +12,7 @@
 //                     64-bit store.  The source rows it gathers were just streamed by minmax_kernel
 //                     and sit in L2 (a 32-slice batch of 512x512 is 16 MiB << 126 MB).
 #include "common.cuh"
+#include <cstdlib>
 
 namespace ms {
 
@@ -165,16 +166,128 @@ __global__ void __launch_bounds__(256) normalise_identity_kernel(const uint16_t*
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// One kernel for the identity geometry (BASELINE cfg1-3): a CLUSTER of 8 CTAs per slice.  Every thread loads its share of
+// the slice ONCE into registers (16 x 16 bytes, all loads in flight together), the slice's min / max is reduced through the
+// warps, the CTA and then the cluster's distributed shared memory, and the normalised pixels are written from the same
+// registers: the u16 slice crosses HBM exactly once (the two-kernel form reads it twice, the second time from L2, and pays
+// a memset + two launches).  Algorithmic bytes 2 w h + 2 * 512^2 per slice; actual traffic 2 w h + 512^2 (u8 out).
+constexpr int kK1Cluster = 8;     // 8 CTAs x THREADS x VEC x 8 px = 262,144 px
+__device__ __forceinline__ uint32_t k1_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void k1_cluster_sync() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t k1_ld_peer(uint32_t smem_addr, uint32_t rank) {
+    uint32_t a, v;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(a) : "r"(smem_addr), "r"(rank));
+    asm volatile("ld.shared::cluster.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
+    return v;
+}
+template <int kK1Threads, int kK1Vec>
+__global__ void __cluster_dims__(kK1Cluster, 1, 1) __launch_bounds__(kK1Threads)
+normalise_cluster_kernel(const uint16_t* __restrict__ src, int n_vec_per_slice /* uint4 per slice */, uint8_t* __restrict__ out_u8,
+                         __nv_bfloat16* __restrict__ out_bf16) {
+    __shared__ uint32_t s_warp[2][kK1Threads / 32];
+    __shared__ uint32_t s_mm[2];
+    const int b = blockIdx.x / kK1Cluster, rank = blockIdx.x % kK1Cluster;
+    const uint4* v = reinterpret_cast<const uint4*>(src) + (size_t)b * n_vec_per_slice;
+    // thread t of CTA r owns vectors r * 256 + t + k * 2048, k = 0 .. 15 (warp-contiguous 512-byte segments)
+    const int first = rank * kK1Threads + threadIdx.x;
+    uint4 q[kK1Vec];
+    uint32_t vmin = 0xFFFFFFFFu, vmax = 0u;
+#pragma unroll
+    for (int k = 0; k < kK1Vec; ++k) {
+        const int i = first + k * kK1Cluster * kK1Threads;
+        q[k] = i < n_vec_per_slice ? __ldg(v + i) : make_uint4(0xFFFF0000u, 0xFFFF0000u, 0xFFFF0000u, 0xFFFF0000u);   // neutral: {0, 65535}
+    }
+#pragma unroll
+    for (int k = 0; k < kK1Vec; ++k) {
+        const int i = first + k * kK1Cluster * kK1Threads;
+        if (i < n_vec_per_slice) {
+            vmin = __vminu2(vmin, __vminu2(__vminu2(q[k].x, q[k].y), __vminu2(q[k].z, q[k].w)));
+            vmax = __vmaxu2(vmax, __vmaxu2(__vmaxu2(q[k].x, q[k].y), __vmaxu2(q[k].z, q[k].w)));
+        }
+    }
+    uint32_t mn = min(vmin & 0xFFFFu, vmin >> 16), mx = max(vmax & 0xFFFFu, vmax >> 16);
+    mn = __reduce_min_sync(0xFFFFFFFFu, mn);
+    mx = __reduce_max_sync(0xFFFFFFFFu, mx);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (lane == 0) { s_warp[0][warp] = mn; s_warp[1][warp] = mx; }
+    __syncthreads();
+    if (warp == 0) {
+        mn = lane < kK1Threads / 32 ? s_warp[0][lane] : 0xFFFFu;
+        mx = lane < kK1Threads / 32 ? s_warp[1][lane] : 0u;
+        mn = __reduce_min_sync(0xFFFFFFFFu, mn);
+        mx = __reduce_max_sync(0xFFFFFFFFu, mx);
+        if (lane == 0) { s_mm[0] = mn; s_mm[1] = mx; }
+    }
+    k1_cluster_sync();                         // every CTA's {min, max} is published
+    {
+        const uint32_t a = k1_smem_u32(s_mm);
+        uint32_t m0 = 0xFFFFu, m1 = 0u;
+#pragma unroll
+        for (int r = 0; r < kK1Cluster; ++r) {
+            m0 = min(m0, k1_ld_peer(a, r));
+            m1 = max(m1, k1_ld_peer(a + 4, r));
+        }
+        mn = m0;
+        mx = m1;
+    }
+    k1_cluster_sync();                         // no CTA leaves (or reuses s_mm) while a peer may still read it
+    int imn = (int)mn, imx = (int)mx;
+    if (imn == imx) imx = imn + 1;                                  // preprocess.cpp:92
+    const double scale8 = __ddiv_rn(255.0, (double)(imx - imn));   // :93
+#pragma unroll
+    for (int k = 0; k < kK1Vec; ++k) {
+        const int i = first + k * kK1Cluster * kK1Threads;
+        if (i >= n_vec_per_slice) continue;
+        const uint32_t wds[4] = {q[k].x, q[k].y, q[k].z, q[k].w};
+        uint32_t lo = 0, hi = 0;
+        float f[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int px = (int)((wds[j >> 1] >> (16 * (j & 1))) & 0xFFFFu);
+            const double qd = __dadd_rn(__dmul_rn((double)(px - imn), scale8), 0.5);   // :116 with v == v00 (identity geometry)
+            const uint32_t r = (uint32_t)__double2int_rz(qd) & 0xFFu;
+            if (j < 4) lo |= r << (8 * j); else hi |= r << (8 * (j - 4));
+            f[j] = __fdiv_rn((float)r, 255.0f);                                        // process.cpp:38
+        }
+        const size_t o = ((size_t)b * n_vec_per_slice + i) * 8;
+        *reinterpret_cast<uint2*>(out_u8 + o) = make_uint2(lo, hi);
+        if (out_bf16) {
+            uint4 st;
+            __nv_bfloat162 t;
+            t = __floats2bfloat162_rn(f[0], f[1]); st.x = *reinterpret_cast<uint32_t*>(&t);
+            t = __floats2bfloat162_rn(f[2], f[3]); st.y = *reinterpret_cast<uint32_t*>(&t);
+            t = __floats2bfloat162_rn(f[4], f[5]); st.z = *reinterpret_cast<uint32_t*>(&t);
+            t = __floats2bfloat162_rn(f[6], f[7]); st.w = *reinterpret_cast<uint32_t*>(&t);
+            *reinterpret_cast<uint4*>(out_bf16 + o) = st;
+        }
+    }
+}
+
 }  // namespace
 
 void preprocess_launch(PreprocessWs& ws, const uint16_t* d_src, int w, int h, int batch, int out_w, int out_h,
                        uint8_t* d_out_u8, __nv_bfloat16* d_out_bf16, cudaStream_t st) {
     MS_REQUIRE(w > 0 && h > 0 && batch > 0 && out_w > 0 && out_h > 0, MS_ERR_ARG, "preprocess: bad shape");
     MS_REQUIRE((int64_t)w * h < (int64_t)1 << 31, MS_ERR_ARG, "preprocess: slice too large");
+    const size_t n = (size_t)w * h;
+    {
+        const bool aligned = (reinterpret_cast<uintptr_t>(d_src) & 15) == 0 && (reinterpret_cast<uintptr_t>(d_out_u8) & 7) == 0 &&
+                             (reinterpret_cast<uintptr_t>(d_out_bf16) & 15) == 0 && n % 8 == 0;
+        const char* e = std::getenv("MEDSEG_K1_CLUSTER");
+        if (w == out_w && h == out_h && aligned && n / 8 <= (size_t)kK1Cluster * 256 * 16 && !(e && e[0] == '0')) {
+            // 512 threads x 8 vectors: 3.98 TB/s of algorithmic bytes at batch 256 (256 x 16: 3.52; two kernels: 3.22)
+            normalise_cluster_kernel<512, 8><<<kK1Cluster * batch, 512, 0, st>>>(d_src, (int)(n / 8), d_out_u8, d_out_bf16);
+            MS_LAUNCH_CHECK();
+            return;
+        }
+    }
     ws.minmax.reserve((size_t)batch * 2 * sizeof(uint32_t));
     uint32_t* mm = ws.minmax.as<uint32_t>();
     MS_CUDA(cudaMemsetAsync(mm, 0, (size_t)batch * 2 * sizeof(uint32_t), st));
-    const size_t n = (size_t)w * h;
     // enough blocks per slice to fill 148 SMs across the batch, 16 B per thread per iteration
     int bx = (int)std::min<size_t>((n / 8 + 255) / 256, (size_t)std::max(1, (148 * 8 + batch - 1) / batch));
     bx = std::max(bx, 1);

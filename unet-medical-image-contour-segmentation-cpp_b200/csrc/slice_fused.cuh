@@ -285,8 +285,9 @@ __device__ __forceinline__ void for_each_link(const uint32_t* bits, const Geo& g
 }
 // pointer jumping until every run points at its root
 template <bool SMEM>
-__device__ __forceinline__ void compress(const Tab<SMEM>& lab, int n_runs) {
-    for (int round = 0; round < 40; ++round) {
+__device__ __forceinline__ int compress(const Tab<SMEM>& lab, int n_runs) {
+    int round = 0;
+    for (; round < 40; ++round) {
         int changed = 0;
         for (int i = threadIdx.x; i < n_runs; i += kT) {
             const int p = lab.ld(i);
@@ -300,6 +301,7 @@ __device__ __forceinline__ void compress(const Tab<SMEM>& lab, int n_runs) {
         }
         if (!__syncthreads_or(changed)) break;
     }
+    return round + 1;
 }
 
 template <int CONN, bool SMEM>
@@ -322,8 +324,9 @@ __device__ __forceinline__ void label_body(const uint32_t* bits, const Geo& g, c
     //    is a 512-deep list)
     for_each_link<CONN>(bits, g, roff, [&](int rc, int ru) { lab.amin(rc, ru); });
     __syncthreads();
+    MS_LABEL_MARK(6);
     // 2. flatten the forest
-    compress(lab, n_runs);
+    const int rounds1 = compress(lab, n_runs);
     MS_LABEL_MARK(1);
     // 3. links the hook did not use join different trees (U shapes): unite their roots -- paths are one step long now
     int joined = 0;
@@ -335,9 +338,14 @@ __device__ __forceinline__ void label_body(const uint32_t* bits, const Geo& g, c
         }
     });
     // 4. and flatten again where anything was joined
-    if (__syncthreads_or(joined)) compress(lab, n_runs);
+    const int any_joined = __syncthreads_or(joined);
+    MS_LABEL_MARK(7);
+    const int rounds2 = any_joined ? compress(lab, n_runs) : 0;
     MS_LABEL_MARK(2);
-    if (dbg && blockIdx.x == 0 && threadIdx.x == 0) dbg[4] = n_runs;
+    if (dbg && blockIdx.x == 0 && threadIdx.x == 0) {
+        dbg[4] = n_runs;
+        dbg[5] = rounds1 * 100 + rounds2;
+    }
     // 5. pixel counts and border flags per root.  A row run is contiguous, so its size is tail - head + 1: the thread that
     //    owns a head records its x, the thread that owns the tail adds the length -- only words with a run end do anything.
     //    Every thread accumulates for the root it saw last (a column of words mostly stays inside one component) and the
@@ -354,6 +362,7 @@ __device__ __forceinline__ void label_body(const uint32_t* bits, const Geo& g, c
         }
     }
     __syncthreads();
+    MS_LABEL_MARK(8);
     {
         int root = -1, acc = 0;
         bool edge = false;

@@ -225,10 +225,10 @@ void make_out_map(CUtensorMap* m, const __nv_bfloat16* base, int B, int H, int W
     make_act_map(m, base, B, H, W, C, tw, 32 / tw);
 }
 // destination of EPI_CONVT: the (2H x 2W) image viewed as (C, dx:2, W, dy:2, B*H); box {64, 1, 16, 1, 2}
-void make_convt_out_map(CUtensorMap* m, const __nv_bfloat16* base, int B, int H_in, int W_in, int C) {
+void make_convt_out_map(CUtensorMap* m, const __nv_bfloat16* base, int B, int H_in, int W_in, int C, int tw = tc::TILE_W) {
     cuuint64_t dims[5] = {(cuuint64_t)C, 2, (cuuint64_t)W_in, 2, (cuuint64_t)B * H_in};
     cuuint64_t strides[4] = {(cuuint64_t)C * 2, (cuuint64_t)2 * C * 2, (cuuint64_t)2 * W_in * C * 2, (cuuint64_t)4 * W_in * C * 2};
-    cuuint32_t box[5] = {(cuuint32_t)tc::BLOCK_K, 1, (cuuint32_t)tc::TILE_W, 1, (cuuint32_t)(32 / tc::TILE_W)};
+    cuuint32_t box[5] = {(cuuint32_t)tc::BLOCK_K, 1, (cuuint32_t)tw, 1, (cuuint32_t)(32 / tw)};
     cuuint32_t estr[5] = {1, 1, 1, 1, 1};
     CUresult r = encode_fn()(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<__nv_bfloat16*>(base), dims, strides, box, estr,
                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
@@ -270,6 +270,16 @@ void launch_halo_p(const UNetLayer& L, const tc::ConvArgs& a, int sm_count, cuda
 template <int BN, int EPI, int RKC>
 void launch_halo(const UNetLayer& L, const tc::ConvArgs& a, int sm_count, cudaStream_t st) {
     launch_halo_p<BN, EPI, RKC, 10>(L, a, sm_count, st);   // dense halo box (the 2048-byte pitch variant measured the same)
+}
+
+template <int BN>
+void launch_convt_pair(const UNetLayer& L, const tc::ConvArgs& a, int sm_count, cudaStream_t st) {
+    using C = tc::ConvT2Cfg<BN>;
+    set_max_dynamic_smem(tc::convt_pair_kernel<BN>, C::SMEM_BYTES);
+    const int pairs = a.batch * (a.H / tc::HALO_TH) * (a.W / tc::HALO_TW) / 2 * (a.n_total / BN);
+    const int grid = 2 * std::min(pairs, sm_count / 2);
+    launch_kernel(tc::convt_pair_kernel<BN>, dim3(grid), dim3(tc::NUM_THREADS), C::SMEM_BYTES, st, true, L.map_a_row, L.map_b_half, L.map_out, a);
+    MS_LAUNCH_CHECK();
 }
 
 template <int BN, int EPI, int RKC>
@@ -499,6 +509,19 @@ void UNet::load(const std::string& blob_path, int net_h, int net_w, int n_classe
         make_act_map(&L.map_a, bufs_[src].p, max_batch, h, wd, bufs_[src].C);
         make_wgt_map(&L.map_b, L.w, 4 * cout, cin, L.block_n);
         make_convt_out_map(&L.map_out, bufs_[dst].p, max_batch, h, wd, bufs_[dst].C);
+        // cta_group::2 GEMM: half the weight bytes per CTA.  Measured in-step at batch 32 (profiles/r2_ab_convt_pair.log):
+        // up4 (K = 1024) 0.115 -> 0.097 ms; up3 / up2 / up1 (K <= 512: one to four k-steps per tile, the epilogue and the
+        // 5-D scatter dominate and the pair's hand-offs are not amortised) lose 13 - 34 %, so they keep the per-tap kernel.
+        // MEDSEG_CONVT_PAIR=0 / =all force either form everywhere.
+        const char* cp = std::getenv("MEDSEG_CONVT_PAIR");
+        const bool pair_all = cp && cp[0] == 'a';
+        if (cta2_enabled_ && !(cp && cp[0] == '0') && (cin >= 1024 || pair_all) && L.block_n == 256 && h % tc::HALO_TH == 0 && wd % tc::HALO_TW == 0 &&
+            ((h / tc::HALO_TH) * (wd / tc::HALO_TW)) % 2 == 0) {
+            L.convt_pair = true;
+            make_act_map(&L.map_a_row, bufs_[src].p, max_batch, h, wd, bufs_[src].C, tc::HALO_TW, tc::HALO_TH);
+            make_wgt_map(&L.map_b_half, L.w, 4 * cout, cin, 128);
+            make_convt_out_map(&L.map_out, bufs_[dst].p, max_batch, h, wd, bufs_[dst].C, tc::HALO_TW);
+        }
         n_params_ += (int64_t)cin * cout * 4 + cout;
         flops_ += L.flops_per_slice;
         layers_.push_back(L);
@@ -620,7 +643,8 @@ void UNet::run_layer(int li, const uint8_t* d_in_u8, int batch, uint8_t* d_mask,
     } else if (L.kind == 3) {
         launch_tc<64, tc::EPI_HEAD>(L, a, sm_count_, st);
     } else if (L.kind == 2) {
-        if (L.block_n == 256) launch_tc<256, tc::EPI_CONVT>(L, a, sm_count_, st);
+        if (L.convt_pair) launch_convt_pair<256>(L, a, sm_count_, st);
+        else if (L.block_n == 256) launch_tc<256, tc::EPI_CONVT>(L, a, sm_count_, st);
         else if (L.block_n == 128) launch_tc<128, tc::EPI_CONVT>(L, a, sm_count_, st);
         else launch_tc<64, tc::EPI_CONVT>(L, a, sm_count_, st);
     } else {

@@ -26,6 +26,7 @@ struct UNetLayer {
     int block_n_alt = 0;         // 0 = none; 128 = deep layers switch to 128-wide N tiles when 256-wide ones cannot fill a wave
     CUtensorMap map_out;         // TMA store of the epilogue (one epilogue warp's 32-pixel x 64-channel slab)
     CUtensorMap map_a_row;       // halo kernel: box {64 ch, 10 px, 18 rows}
+    bool convt_pair = false;     // ConvT: cta_group::2 GEMM (convt_pair_kernel) with map_a_row = {64 ch, 8 px, 16 rows} tiles
     int halo = 0;                // 0 = per-tap streaming kernel, 1 = halo-stationary kernel, 2 = its cta_group::2 version
     int resident_kc = 0;         // halo kernel: > 0 when all weights stay in shared memory
     int halo_pitch = 16;         // halo kernel: shared-memory rows per halo image row (10 dense / 16 aligned)
@@ -34,6 +35,7 @@ struct UNetLayer {
     std::string kernel_name() const {
         const char* epi = kind == 3 ? "EPI_HEAD" : (kind == 2 ? "EPI_CONVT" : "EPI_STORE");
         if (kind == 0) return "first_conv_kernel";
+        if (convt_pair) return "tc::convt_pair_kernel<" + std::to_string(block_n) + ">";
         if (halo == 2) return "tc::conv_halo2_kernel<" + std::to_string(block_n) + ", " + epi + ", " + std::to_string(resident_kc) + ">";
         if (halo == 1) return "tc::conv_halo_kernel<" + std::to_string(block_n) + ", " + epi + ", " + std::to_string(resident_kc) + ", 10>";
         return "tc::conv_gemm_kernel<" + std::to_string(block_n) + ", " + epi + ">";

@@ -1047,5 +1047,151 @@ conv_halo2_kernel(const __grid_constant__ CUtensorMap map_a_halo, const __grid_c
     }
 }
 
+// ==================================================================================== kernel 4
+// Transposed conv 2x2 s2 as a cta_group::2 GEMM (M = pixels, N = 4 * Cout, K = Cin, one tap).  The per-tap kernel 1 runs
+// the up-sampling layers L2 -> SM bound: every CTA re-fetches the whole 256-row weight tile for each of its pixel tiles
+// (48 KiB of operands per k-step for 128 x 256 x 64 MACs).  Here a CTA pair works on two adjacent 8 x 16-pixel tiles as ONE
+// UMMA of M = 256: each CTA stages its own 128 pixel rows (16 KiB) and only HALF of the weight tile (BLOCK_N / 2 rows,
+// 16 KiB), so a k-step moves 32 KiB per CTA for twice the MACs per byte of weights.  Pipeline, barriers and epilogue are
+// those of kernel 3 (both CTAs' TMA loads signal the leader's barriers, tcgen05.commit multicasts to both CTAs, epilogues
+// report back over DSMEM); the epilogue scatters through the 5-D tensor map of the (2H x 2W) destination.
+template <int BLOCK_N>
+struct ConvT2Cfg {
+    static constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;                  // this CTA's 128 pixel rows of one K chunk
+    static constexpr int B_BYTES = (BLOCK_N / 2) * BLOCK_K * 2;            // this CTA's half of the weight tile
+    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+    static constexpr int STG_BYTES = 4 * 4096;
+    static constexpr int STAGES_RAW = (227 * 1024 - 4096 - 1024 - STG_BYTES) / STAGE_BYTES;
+    static constexpr int STAGES = STAGES_RAW > 6 ? 6 : STAGES_RAW;
+    static constexpr int TMEM_COLS = 2 * BLOCK_N;
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STG_BYTES + 4096 + 1024;
+};
+
+template <int BLOCK_N>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
+convt_pair_kernel(const __grid_constant__ CUtensorMap map_a_tile, const __grid_constant__ CUtensorMap map_b_half,
+                  const __grid_constant__ CUtensorMap map_out, const ConvArgs args) {
+    using C = ConvT2Cfg<BLOCK_N>;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* s_stg = smem + C::STAGES * C::STAGE_BYTES;
+    uint8_t* aux = s_stg + C::STG_BYTES;
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(aux);
+    uint64_t* empty_bar = full_bar + 8;
+    uint64_t* tmem_full = empty_bar + 8;
+    uint64_t* tmem_empty = tmem_full + 2;
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const bool leader = rank == 0;
+    const int pair_id = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
+    const int tiles_x = args.W / HALO_TW, tiles_y = args.H / HALO_TH;
+    const int n_tiles = args.n_total / BLOCK_N;
+    const int total_pairs = ((args.batch * tiles_y * tiles_x) >> 1) * n_tiles;   // work items: (tile pair, n tile)
+    const int kchunks = args.Cin / BLOCK_K;
+
+    if (threadIdx.x == 0) {
+        prefetch_tmap(&map_a_tile);
+        prefetch_tmap(&map_b_half);
+        prefetch_tmap(&map_out);
+        for (int i = 0; i < C::STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 256); }
+        fence_barrier_init();
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)), "r"((uint32_t)C::TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
+    pdl_launch_dependents();
+
+    if (warp == 0) {
+        // ===================================================================== TMA producer (both CTAs)
+        if (lane == 0 && pair_id < total_pairs) {
+            int stage = 0;
+            uint32_t phase = 0;
+            pdl_wait();            // the activations are the previous layer's output
+            for (int p = pair_id; p < total_pairs; p += n_pairs) {
+                const TileCoord tc = decode_tile(2 * (p / n_tiles) + (int)rank, 1, tiles_x, tiles_y, BLOCK_N, HALO_TW, HALO_TH);
+                const int n_row0 = (p % n_tiles) * BLOCK_N + (int)rank * (BLOCK_N / 2);
+                for (int kc = 0; kc < kchunks; ++kc) {
+                    mbar_wait(&empty_bar[stage], phase ^ 1);
+                    uint8_t* sa = smem + stage * C::STAGE_BYTES;
+                    if (leader) mbar_expect_tx(&full_bar[stage], 2 * C::STAGE_BYTES);
+                    tma2_load_4d(sa, &map_a_tile, &full_bar[stage], kc * BLOCK_K, tc.x0, tc.y0, tc.b);
+                    tma2_load_2d(sa + C::A_BYTES, &map_b_half, &full_bar[stage], kc * BLOCK_K, n_row0);
+                    if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================================================================== MMA issuer (leader CTA only)
+        if (leader && pair_id < total_pairs) {
+            constexpr uint32_t idesc = make_idesc_m256(BLOCK_N);
+            int stage = 0, acc = 0;
+            uint32_t phase = 0, acc_phase = 0;
+            for (int p = pair_id; p < total_pairs; p += n_pairs) {
+                mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BLOCK_N);
+                for (int kc = 0; kc < kchunks; ++kc) {
+                    mbar_wait(&full_bar[stage], phase);
+                    tc_fence_after();
+                    if (elect_one()) {
+                        const uint32_t sa = smem_u32(smem + stage * C::STAGE_BYTES);
+                        const uint64_t adesc = make_smem_desc(sa);
+                        const uint64_t bdesc = make_smem_desc(sa + C::A_BYTES);
+#pragma unroll
+                        for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
+                            umma2_f16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kc | k) != 0 ? 1u : 0u);
+                        umma2_commit_mc(&empty_bar[stage]);
+                        if (kc == kchunks - 1) umma2_commit_mc(&tmem_full[acc]);
+                    }
+                    __syncwarp();
+                    if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+                }
+                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            }
+        }
+    } else {
+        // ===================================================================== epilogue (both CTAs, own 128 rows)
+        const int quarter = warp & 3;
+        const int row = quarter * 32 + lane;
+        const int ly = row / HALO_TW, lx = row % HALO_TW;
+        EpiCtx e;
+        e.map_out = &map_out;
+        e.slab = smem_u32(s_stg + quarter * 4096);
+        e.slab_y = quarter * (32 / HALO_TW);
+        e.lane = lane;
+        const uint32_t empty0 = mapa_rank(smem_u32(&tmem_empty[0]), 0), empty1 = mapa_rank(smem_u32(&tmem_empty[1]), 0);
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        for (int p = pair_id; p < total_pairs; p += n_pairs) {
+            const TileCoord tcd = decode_tile(2 * (p / n_tiles) + (int)rank, 1, tiles_x, tiles_y, BLOCK_N, HALO_TW, HALO_TH);
+            e.b = tcd.b; e.y0 = tcd.y0; e.x0 = tcd.x0; e.y = tcd.y0 + ly; e.x = tcd.x0 + lx;
+            e.n0 = (p % n_tiles) * BLOCK_N;
+            mbar_wait(&tmem_full[acc], acc_phase);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BLOCK_N);
+            epilogue_tile<BLOCK_N, EPI_CONVT, HALO_TW, true>(args, nullptr, taddr, e, nullptr, acc ? empty1 : empty0);
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+        if (lane == 0) tma_store_wait_read();
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    if (warp == 1) {
+        __syncwarp();
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)C::TMEM_COLS) : "memory");
+    }
+}
+
 }  // namespace tc
 }  // namespace ms
