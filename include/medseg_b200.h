@@ -229,6 +229,15 @@ MS_API int64_t ms_polygons_to_json_batch(const int32_t* xy, const int32_t* conto
                                          const char* const* base_names, int orig_w, int orig_h, int n_threads, char* dst,
                                          int64_t cap, int64_t* offsets);
 
+/* ---- opt-in polygon simplification -------------------------------------------------------------
+ * NOT part of the reference (src/mask2polygon.cpp:34 stops at CHAIN_APPROX_SIMPLE; SURVEY.md finding 4).  With
+ * eps > 0 every polygon-producing call runs each contour through closed-curve Douglas-Peucker in network space,
+ * vertex for vertex what cv2.approxPolyDP(contour, eps, true) of OpenCV 4.13 returns, before the coordinate mapping
+ * of src/mask2polygon.cpp:41-63.  Config key "dp_epsilon" sets the initial value; 0 (the default) = off = the
+ * reference's output.  Applies to the handle and its per-GPU peers; not to be called while a batch is in flight. */
+MS_API int ms_set_dp_epsilon(ms_handle* h, double eps);
+MS_API double ms_dp_epsilon(ms_handle* h);
+
 /* ---- instrumentation ------------------------------------------------------------------------- */
 
 /* Number of kernels this library launched on the handle since creation (bench.py `gpu_launches`). */

@@ -3,10 +3,15 @@
 Every function cites the reference lines it restates (paths relative to /root/reference).
 The integer/byte stages call the *same OpenCV functions* the reference calls, through
 cv2 (opencv-python-headless 4.13.0; the reference's own OpenCV version is unpinned -- it has
-no build file).  The reference has no tests, fixtures or golden vectors, so
-PARITY IS UNPINNED by the reference itself; it is pinned instead by
+no build file).  The reference has no tests, fixtures or golden vectors; this
+module is pinned by
+  * oracle/_ref/libref_pipeline.so -- the reference's OWN preprocess.cpp / postprocess.cpp /
+    mask2polygon.cpp compiled unmodified against an OpenCV stub (oracle/ref_build, binding
+    oracle/ref.py; tests/test_ref_pin.py, tests/golden/ref_*),
   * tests/golden/*  generated from this module by tests/golden/make_golden.py, and
   * oracle/c/medseg_oracle.c, an OpenCV-free restatement checked against this module.
+What stays pinned to cv2 4.13 only (no reference object code can exist for it) is the arithmetic the
+reference delegates to OpenCV itself: findContours, connectedComponentsWithStats, morphologyEx.
 
 Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
 import this module; the product never does.
@@ -134,6 +139,104 @@ def mask_to_image(mask: np.ndarray) -> np.ndarray:
     lut[1], lut[2] = 128, 255
     return lut[mask]
 
+
+
+# --------------------------------------------------------------------------- Douglas-Peucker (opt-in, not in the reference)
+def approx_poly_dp(contour, eps: float) -> np.ndarray:
+    """Closed-curve Douglas-Peucker as cv2.approxPolyDP(contour, eps, True) of OpenCV 4.13 computes it (the reference never
+    simplifies: src/mask2polygon.cpp:34 stops at CHAIN_APPROX_SIMPLE; BASELINE.json north_star (3) names D-P as an extra, so it
+    is opt-in, "dp_epsilon" = 0 = off).  Restated from the library's behaviour and pinned by fuzzing against cv2 itself
+    (tests/test_oracle.py::test_approx_poly_dp_restatement_vs_cv2):
+      1. three sweeps "farthest point from the current start" fix the two initial split points (the output starts at the second);
+      2. a slice (s0, s1) is split at the interior point farthest FROM THE SEGMENT (not the line: points that project outside
+         the segment count with their distance to the nearer end), first maximum in walk order, while that distance > eps;
+      3. the start points of the leaf slices, in walk order, go through one clean-up pass that drops a vertex when it lies
+         within eps / sqrt(2) of the chord of its neighbours, the chord is not axis-parallel and the path does not turn back.
+    Distances are compared exactly (integers on the common scale |s1 - s0|^2); the eps test is `double(num) <= eps^2 * double(den)`.
+    `contour`: (n, 2) integer points.  Returns (m, 2) int32."""
+    pts = [(int(x), int(y)) for x, y in np.asarray(contour).reshape(-1, 2)]
+    count = len(pts)
+    if count == 0:
+        return np.zeros((0, 2), np.int32)
+    eps2 = float(eps) * float(eps)
+    nxt = lambda p: p + 1 if p + 1 < count else 0
+    out, stack = [], []
+    pos, right_start, le_eps, start = 0, 0, False, pts[0]
+    for _ in range(3):
+        max_d = 0
+        pos = (pos + right_start) % count
+        start, pos = pts[pos], nxt(pos)
+        for j in range(1, count):
+            pt, pos = pts[pos], nxt(pos)
+            d = (pt[0] - start[0]) ** 2 + (pt[1] - start[1]) ** 2
+            if d > max_d:
+                max_d, right_start = d, j
+        le_eps = float(max_d) <= eps2
+    if le_eps:
+        out.append(start)
+    else:
+        s0 = pos % count
+        s1 = (right_start + s0) % count
+        stack += [(s1, s0), (s0, s1)]
+    while stack:
+        s0, s1 = stack.pop()
+        a, b = pts[s0], pts[s1]
+        pos = nxt(s0)
+        if pos == s1:
+            out.append(a)
+            continue
+        dx, dy = b[0] - a[0], b[1] - a[1]
+        L = dx * dx + dy * dy
+        best, split = 0, s0
+        while pos != s1:
+            pt = pts[pos]
+            px, py = pt[0] - a[0], pt[1] - a[1]
+            dot = px * dx + py * dy
+            if L == 0 or dot < 0:
+                v = (px * px + py * py) * max(L, 1)
+            elif dot > L:
+                v = ((pt[0] - b[0]) ** 2 + (pt[1] - b[1]) ** 2) * L
+            else:
+                v = (py * dx - px * dy) ** 2
+            if v > best:
+                best, split = v, pos
+            pos = nxt(pos)
+        if float(best) <= eps2 * float(max(L, 1)):
+            out.append(a)
+        else:
+            stack += [(split, s1), (s0, split)]
+    # clean-up pass, in place with wrap-around exactly as the library does it
+    count = new_count = len(out)
+    dst = list(out)
+    rd = lambda p: (dst[p], p + 1 if p + 1 < count else 0)
+    start, pos = rd(count - 1)
+    wpos = pos
+    pt, pos = rd(pos)
+    i = 0
+    while i < count and new_count > 2:
+        end, pos = rd(pos)
+        dx, dy = float(end[0] - start[0]), float(end[1] - start[1])
+        dist = abs((pt[0] - start[0]) * dy - (pt[1] - start[1]) * dx)
+        sip = (pt[0] - start[0]) * (end[0] - pt[0]) + (pt[1] - start[1]) * (end[1] - pt[1])
+        if dist * dist <= 0.5 * eps2 * (dx * dx + dy * dy) and dx != 0 and dy != 0 and sip >= 0:
+            new_count -= 1
+            dst[wpos] = start = end
+            wpos = wpos + 1 if wpos + 1 < count else 0
+            pt, pos = rd(pos)
+            i += 2
+            continue
+        dst[wpos] = start = pt
+        wpos = wpos + 1 if wpos + 1 < count else 0
+        pt = end
+        i += 1
+    return np.array(dst[:new_count], dtype=np.int32).reshape(-1, 2)
+
+
+def simplify_contours(contours, eps: float):
+    """The opt-in step between extract_contours and map_contour_points: every contour through approx_poly_dp (eps <= 0: off)."""
+    if eps <= 0:
+        return list(contours)
+    return [approx_poly_dp(c, eps) for c in contours]
 
 # --------------------------------------------------------------------------- mask2polygon
 def extract_contours(mask_img: np.ndarray):

@@ -190,3 +190,49 @@ def test_as_shipped_file_path_equals_in_memory(tmp_path):
     assert (cv2.imread(str(tmp_path / "out" / "a_mask.png"), cv2.IMREAD_UNCHANGED) == m["vis"]).all()
     assert open(tmp_path / "out" / "a.json").read() == op.generate_json(m["mapped"], "a", 600, 400)
     assert open(tmp_path / "out" / "a_original_sizes.json").read() == op.sidecar_json_text("a.raw", 600, 400)
+
+
+# ----------------------------------------------------------------------------- Douglas-Peucker (opt-in extra)
+DP_EPS = (0.5, 1.0, 1.5, 2.0, 3.7, 10.0)
+
+
+def dp_fuzz_contours(n_masks, seed):
+    """Contours for the D-P pins: speckle / nested / smooth masks (spikes, revisited pixels, long smooth borders) and the
+    CT-like body outline."""
+    import cv2
+    rng = np.random.default_rng(seed)
+    for t in range(n_masks):
+        h, w = (int(v) for v in rng.integers(8, 160, 2))
+        k = t % 3
+        if k == 0:
+            m = (rng.random((h, w)) < rng.uniform(0.3, 0.7)).astype(np.uint8) * 255
+        elif k == 1:
+            m = np.zeros((h, w), np.uint8)
+            for _ in range(int(rng.integers(1, 6))):
+                cv2.ellipse(m, (int(rng.integers(0, w)), int(rng.integers(0, h))), (int(rng.integers(2, w)), int(rng.integers(2, h))),
+                            float(rng.uniform(0, 180)), 0, 360, 255, -1)
+        else:
+            m = cv2.GaussianBlur((rng.random((h, w)) * 255).astype(np.uint8), (0, 0), float(rng.uniform(1, 4)))
+            m = (m > 127).astype(np.uint8) * 255
+        for c in op.extract_contours(m):
+            yield c, float(rng.uniform(0.01, 6.0))
+
+
+def test_approx_poly_dp_restatement_vs_cv2():
+    """The oracle's closed-curve Douglas-Peucker against cv2.approxPolyDP (4.13) itself: same vertices, same start, same
+    order -- on tie-prone epsilons (multiples of 0.5) and random ones."""
+    import cv2
+    n = 0
+    for c, eps_r in dp_fuzz_contours(240, 5):
+        for eps in DP_EPS + (eps_r,):
+            want = cv2.approxPolyDP(c.reshape(-1, 1, 2), eps, True).reshape(-1, 2)
+            got = op.approx_poly_dp(c, eps)
+            assert got.shape == want.shape and (got == want).all(), (eps, c.tolist())
+            n += 1
+    assert n > 5000
+    # degenerate inputs: one point, two points, all points within eps of each other
+    for pts in ([[3, 4]], [[3, 4], [9, 4]], [[0, 0], [1, 0], [1, 1], [0, 1]]):
+        c = np.array(pts, np.int32)
+        for eps in (0.5, 1.0, 5.0):
+            want = cv2.approxPolyDP(c.reshape(-1, 1, 2), eps, True).reshape(-1, 2)
+            assert np.array_equal(op.approx_poly_dp(c, eps), want), (pts, eps)

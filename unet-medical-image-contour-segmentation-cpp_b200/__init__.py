@@ -82,6 +82,8 @@ ABI = {
     "ms_polygons_to_json": (_L, [_P, _P, _I, C.c_char_p, _I, _I, _P, _L]),
     "ms_polygons_to_json_batch": (_L, [_P, _P, _P, _I, C.POINTER(C.c_char_p), _I, _I, _I, _P, _L, _P]),
     "ms_launch_count": (_L, [_P]),
+    "ms_set_dp_epsilon": (_I, [_P, C.c_double]),
+    "ms_dp_epsilon": (C.c_double, [_P]),
     "ms_time_layer": (_I, [_P, _I, _I, _I, C.POINTER(C.c_float), C.POINTER(C.c_double)]),
     "ms_layer_count": (_I, [_P]),
     "ms_profile_layers_begin": (_I, [_P, _I]),
@@ -385,6 +387,14 @@ class Engine:
     def mask2polygon_dev(self, d_mask: int, h: int, w: int, batch: int, threshold: int = 127, stream: int = 0) -> Polygons:
         return self._poly_call(
             lambda pg: self._l.ms_mask2polygon_dev(self._h, d_mask, h, w, batch, threshold, w, h, pg, stream or None), batch)
+
+    def set_dp_epsilon(self, eps: float) -> None:
+        """Opt-in Douglas-Peucker (cv2.approxPolyDP, closed) on every contour before the coordinate mapping; 0 = off = the
+        reference's CHAIN_APPROX_SIMPLE output."""
+        self._check(self._l.ms_set_dp_epsilon(self._h, float(eps)))
+
+    def dp_epsilon(self) -> float:
+        return float(self._l.ms_dp_epsilon(self._h))
 
     # ------------------------------------------------------------------ instrumentation
     def launch_count(self) -> int:

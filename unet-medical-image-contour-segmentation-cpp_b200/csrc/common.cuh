@@ -213,9 +213,15 @@ struct PolyDev {              // device-resident polygon set + counters
     DevBuf rec;               // int2 [cap_contours]
     DevBuf vstore;            // u32  [cap_points]  x | y << 16
     bool fused = false;       // phase A ran on the fused path (phase B must finalize accordingly)
+    // opt-in Douglas-Peucker (dp_simplify.cuh), reserved only when "dp_epsilon" > 0
+    DevBuf dp_tmp;            // int2 [cap_points]: simplified vertices of contour c at its old offset
+    DevBuf dp_list;           // uint2 [cap_points]: work lists of contours too long for shared memory
+    DevBuf dp_keep;           // u32 bitmaps of those contours
+    DevBuf dp_cnt, dp_old;    // int32 [cap_contours (+ 1)]: simplified counts, offsets before simplification
     int64_t cap_contours = 0, cap_points = 0;
     void release() {
-        for (DevBuf* b : {&starts, &start_slice, &npts, &slice_start, &block_counts, &xy, &header, &chunks, &chunk_meta, &slice_info, &rec, &vstore})
+        for (DevBuf* b : {&starts, &start_slice, &npts, &slice_start, &block_counts, &xy, &header, &chunks, &chunk_meta, &slice_info, &rec, &vstore,
+                          &dp_tmp, &dp_list, &dp_keep, &dp_cnt, &dp_old})
             b->release();
     }
 };
@@ -231,6 +237,7 @@ struct M2pWs {
     DevBuf crack_contour;     // int32 [2 * (cap_contours + 1)]: position base per contour, rotation
     DevBuf crack_meta;        // int64 total positions, int32 round flags
     FusedWs fused;
+    double dp_eps = 0.0;      // > 0: phase B simplifies every contour (cv2.approxPolyDP, closed) before the coordinate mapping
     void release_crack() {
         for (DevBuf* b : {&crack_pair, &crack_pos, &crack_blocks, &crack_contour, &crack_meta}) b->release();
     }

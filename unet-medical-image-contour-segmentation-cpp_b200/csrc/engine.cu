@@ -269,6 +269,10 @@ void apply_config(ms_handle* h, const json::Value& cfg, const std::string& base_
     h->fg_value = (int)cfg.integer("foreground_value", 2);
     h->threshold = (int)cfg.integer("threshold", 127);
     h->min_area_ratio = (float)cfg.number("min_area_ratio", 0.06f);
+    // opt-in extra, never on the reference's path (src/mask2polygon.cpp:34 keeps CHAIN_APPROX_SIMPLE): > 0 = every contour goes
+    // through approxPolyDP(eps, closed) in network space before map_contour_points
+    h->m2p.dp_eps = cfg.number("dp_epsilon", 0.0);
+    MS_REQUIRE(h->m2p.dp_eps >= 0.0 && h->m2p.dp_eps < 1e9, MS_ERR_ARG, "dp_epsilon must be a finite number >= 0");
     h->device = (int)cfg.integer("device", 0);
     // "devices": [0, 1, ...] or "all" (MEDSEG_DEVICES=all|0,1,.. supplies it when the config names neither, so the
     // reference's `init <path>` needs no new argument): one process, one handle per listed GPU
@@ -460,6 +464,7 @@ static int init_common(ms_handle* h, const char* log_dir, ms_handle** out) {
         c->device = h->devices[i];
         c->net_h = h->net_h; c->net_w = h->net_w; c->n_classes_cfg = h->n_classes_cfg; c->max_batch = h->max_batch;
         c->fg_value = h->fg_value; c->threshold = h->threshold; c->min_area_ratio = h->min_area_ratio;
+        c->m2p.dp_eps = h->m2p.dp_eps;
         c->weights_path = h->weights_path;
         c->quiet_console = true;
         rc = guarded(nullptr, [&] { finish_init(c, nullptr); });
@@ -1500,6 +1505,16 @@ int ms_process_volume_host(ms_handle* h, const uint16_t* h_src, int w, int hgt, 
         }
     });
 }
+
+int ms_set_dp_epsilon(ms_handle* h, double eps) {
+    if (!h || !(eps >= 0.0 && eps < 1e9)) return MS_ERR_ARG;
+    h->m2p.dp_eps = eps;
+    for (ms_handle* c : h->peers) c->m2p.dp_eps = eps;
+    ++g_alloc_epoch;        // captured per-slot graphs hold the old launch sequence: capture again
+    return MS_OK;
+}
+
+double ms_dp_epsilon(ms_handle* h) { return h ? h->m2p.dp_eps : 0.0; }
 
 // ---------------------------------------------------------------- instrumentation
 int64_t ms_launch_count(ms_handle* h) {

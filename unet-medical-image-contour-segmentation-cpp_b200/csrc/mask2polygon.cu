@@ -914,6 +914,7 @@ __global__ void __launch_bounds__(1024) scan_points_kernel(int* __restrict__ npt
 }
 
 #include "slice_fused.cuh"
+#include "dp_simplify.cuh"
 
 enum TraceMode { kTraceSmem = 0, kTraceWindow = 1, kTraceCrack = 2, kTraceRank = 3 };
 
@@ -1169,20 +1170,52 @@ void m2p_phase_a(M2pWs& ws, PolyDev& P, const uint8_t* d_mask, int h, int w, int
     MS_LAUNCH_CHECK();
 }
 
+// Opt-in simplification of the polygon set phase B just wrote in NETWORK space: approxPolyDP per contour, new contour
+// offsets, then the coordinate mapping.  Three launches, all sizes on the device.
+static void dp_launch(PolyDev& P, int h, int w, double eps, double sx, double sy, cudaStream_t st) {
+    // exact integer distances: |cross|^2 and d^2 * L stay below 2^62
+    MS_REQUIRE((int64_t)w * w + (int64_t)h * h < ((int64_t)1 << 31), MS_ERR_ARG, "dp_epsilon: slice too large for exact simplification");
+    const int cap_c = (int)std::min<int64_t>(P.cap_contours, 0x7FFFFFF0);
+    P.dp_tmp.reserve((size_t)P.cap_points * 8);
+    P.dp_list.reserve((size_t)P.cap_points * 8);
+    P.dp_keep.reserve(((size_t)P.cap_points / 32 + (size_t)P.cap_contours + 2) * 4);
+    P.dp_cnt.reserve((size_t)P.cap_contours * 4);
+    P.dp_old.reserve(((size_t)P.cap_contours + 1) * 4);
+    dp::Args a{};
+    a.xy = P.xy.as<int2>(); a.cstart = P.npts.as<int>(); a.header = P.header.as<long long>();
+    a.cap_contours = cap_c; a.cap_points = (long long)P.cap_points;
+    a.eps2 = eps * eps;                                 // the library squares eps once, in double
+    a.g_list = P.dp_list.as<uint2>(); a.g_keep = P.dp_keep.as<uint32_t>(); a.tmp = P.dp_tmp.as<int2>(); a.cnt = P.dp_cnt.as<int>();
+    set_max_dynamic_smem(dp::simplify_kernel, (int)dp::kSmemBytes);
+    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(P.cap_contours, 148 * 3));
+    dp::simplify_kernel<<<grid, dp::kT, dp::kSmemBytes, st>>>(a);
+    MS_LAUNCH_CHECK();
+    dp::rescan_kernel<<<1, 1024, 0, st>>>(P.npts.as<int>(), P.dp_old.as<int>(), P.dp_cnt.as<int>(), P.header.as<long long>(), cap_c,
+                                          (long long)P.cap_points);
+    MS_LAUNCH_CHECK();
+    dp::compact_kernel<<<grid, 256, 0, st>>>(P.dp_tmp.as<int2>(), P.dp_old.as<int>(), P.npts.as<int>(), P.dp_cnt.as<int>(),
+                                             P.header.as<long long>(), sx, sy, P.xy.as<int2>());
+    MS_LAUNCH_CHECK();
+}
+
 void m2p_phase_b(M2pWs& ws, PolyDev& P, int h, int w, int batch, int orig_w, int orig_h, cudaStream_t st) {
     // src/mask2polygon.cpp:199-200
     const double sx = static_cast<double>(orig_w) / w;
     const double sy = static_cast<double>(orig_h) / h;
+    // with simplification on, the vertices are first emitted unmapped ((int)(x * 1.0) == x) and mapped after it
+    const bool simplify = ws.dp_eps > 0.0;
+    const double ex = simplify ? 1.0 : sx, ey = simplify ? 1.0 : sy;
     if (P.fused) {
         fused::finalize_kernel<<<batch, 256, 0, st>>>(P.slice_info.as<int4>(), P.rec.as<int2>(), P.vstore.as<uint32_t>(), batch,
-                                                     (int)std::min<int64_t>(P.cap_contours, 0x7FFFFFF0), (long long)P.cap_points, sx, sy,
+                                                     (int)std::min<int64_t>(P.cap_contours, 0x7FFFFFF0), (long long)P.cap_points, ex, ey,
                                                      P.slice_start.as<int>(), P.npts.as<int>(), P.xy.as<int2>(), P.header.as<long long>());
         MS_LAUNCH_CHECK();
-        return;
+    } else {
+        const TraceMode mode = pick_trace_mode(h, w, batch);
+        if (mode == kTraceCrack) crack_emit(ws, P, h, w, batch, ex, ey, st);
+        else launch_gather(P, ex, ey, st);
     }
-    const TraceMode mode = pick_trace_mode(h, w, batch);
-    if (mode == kTraceCrack) crack_emit(ws, P, h, w, batch, sx, sy, st);
-    else launch_gather(P, sx, sy, st);
+    if (simplify) dp_launch(P, h, w, ws.dp_eps, sx, sy, st);
 }
 
 }  // namespace ms
