@@ -75,3 +75,52 @@ def test_convt_pair_kernel_matches_per_tap_kernel(ms, blob3, torch_unet3):
         want = torch_unet3(x, taps).numpy()[0]
     err = np.abs(out["all"]["logits"][0] - want)
     assert np.quantile(err, 0.999) < 2e-2 and err.max() < 8e-2
+
+
+@pytest.mark.parametrize("n_classes", [3, 1])
+def test_rowpair_kernel_matches_halo_kernel_and_fp32_oracle(ms, tmp_path_factory, n_classes):
+    """The Cout = 64 layers (enc1b with its fused 2x2 max-pool, dec1b + head) through the row-pair kernel (two output rows per
+    GEMM row, N = 128 accumulators) and through the halo kernel (MEDSEG_ROWPAIR=0): both within the bf16 tolerance of the
+    fp32 oracle's skip map x1, its pooled map and the logits; masks of the two kernels agree to >= 99.99 %."""
+    import torch
+    import torch.nn.functional as F
+    from medseg_b200 import synth, weights as W
+    from oracle.unet_torch import load_unet
+    blob = ms.make_weight_blob(str(tmp_path_factory.mktemp("rp") / "u.msegw"), n_classes=n_classes, seed=77)
+    arch, w = W.load_blob(blob)
+    net = load_unet(w, n_classes)
+    B = 3
+    vol = synth.ct_volume(B, 512, 512, first_seed=40)
+    out = {}
+    for mode in ("0", "1"):
+        with _Env(MEDSEG_ROWPAIR=mode):
+            cfg = {"weights": blob, "max_batch": B}
+            if n_classes == 1:
+                cfg["head"] = "binary"
+            eng = ms.Engine(cfg)
+        kern = dict(zip(eng.layer_names(), eng.layer_kernels()))
+        for name in ("enc1b", "dec1b_head"):
+            assert ("rowpair" in kern[name]) == (mode == "1"), (mode, kern[name])
+        norm = eng.preprocess(vol)
+        mask, logits = eng.process(norm, want_logits=True)
+        out[mode] = {"mask": mask, "logits": logits, "cat1": eng.read_activation("cat1", B).reshape(B, 128, 512, 512)[:, :64],
+                     "p1": eng.read_activation("p1", B).reshape(B, 64, 256, 256)}
+        eng.cleanup()
+    assert (out["0"]["mask"] == out["1"]["mask"]).mean() >= 0.9999
+    for i in (0, B - 1):
+        taps = {}
+        with torch.no_grad():
+            x = torch.from_numpy(norm[i:i + 1].astype(np.float32) / np.float32(255.0))[:, None]
+            want = net(x, taps).numpy()[0]
+            x1 = taps["x1"]
+            p1 = F.max_pool2d(x1, 2).numpy()[0]
+            x1 = x1.numpy()[0]
+        for mode in ("0", "1"):
+            o = out[mode]
+            assert np.abs(o["cat1"][i] - x1).max() / np.abs(x1).max() < 2e-2, mode
+            assert np.abs(o["p1"][i] - p1).max() / np.abs(p1).max() < 2e-2, mode
+            err = np.abs(o["logits"][i] - want)
+            assert np.quantile(err, 0.999) < 2e-2 and err.max() < 8e-2, (mode, err.max())
+        # the pooled map is exactly the max of the stored skip map (both come from the same bf16 values)
+        c1 = torch.from_numpy(out["1"]["cat1"][i:i + 1])
+        assert np.array_equal(F.max_pool2d(c1, 2).numpy()[0], out["1"]["p1"][i])

@@ -272,6 +272,16 @@ void launch_halo(const UNetLayer& L, const tc::ConvArgs& a, int sm_count, cudaSt
     launch_halo_p<BN, EPI, RKC, 10>(L, a, sm_count, st);   // dense halo box (the 2048-byte pitch variant measured the same)
 }
 
+template <int EPI, int RKC>
+void launch_rowpair(const UNetLayer& L, const tc::ConvArgs& a, int sm_count, cudaStream_t st) {
+    using C = tc::RowPairCfg<RKC>;
+    set_max_dynamic_smem(tc::conv_rowpair_kernel<EPI, RKC>, C::SMEM_BYTES);
+    const int total = a.batch * (a.H / tc::RP_TH) * (a.W / tc::RP_TW);
+    const int grid = std::min(total, sm_count);
+    launch_kernel(tc::conv_rowpair_kernel<EPI, RKC>, dim3(grid), dim3(tc::NUM_THREADS), C::SMEM_BYTES, st, true, L.map_a_row, L.map_b, L.map_out, a);
+    MS_LAUNCH_CHECK();
+}
+
 template <int BN>
 void launch_convt_pair(const UNetLayer& L, const tc::ConvArgs& a, int sm_count, cudaStream_t st) {
     using C = tc::ConvT2Cfg<BN>;
@@ -366,7 +376,9 @@ void UNet::load(const std::string& blob_path, int net_h, int net_w, int n_classe
     const char* rb = std::getenv("MEDSEG_RES_BIG");
     res_big_ = !(rb && rb[0] == '0');
     const char* sv = std::getenv("MEDSEG_STREAM2");
-    stream2_enabled_ = !(sv && sv[0] == '0');   // MEDSEG_CTA2=2: prefer the pair kernel wherever it applies (A/B measurements)
+    stream2_enabled_ = !(sv && sv[0] == '0');
+    const char* rp = std::getenv("MEDSEG_ROWPAIR");
+    rowpair_enabled_ = !(rp && rp[0] == '0');   // MEDSEG_CTA2=2: prefer the pair kernel wherever it applies (A/B measurements)
     const char* pv = std::getenv("MEDSEG_HALO_PITCH");
     halo_pitch_ = 10;
     (void)pv;
@@ -472,6 +484,14 @@ void UNet::load(const std::string& blob_path, int net_h, int net_w, int n_classe
                 make_wgt_map(&L.map_b_half, L.w, cout, 9 * cin, L.block_n / 2);
             }
             if (L.halo) make_act_map(&L.map_a_row, bufs_[src].p, max_batch, h, w, bufs_[src].C, tc::HALO_TW + 2, tc::HALO_TH + 2);
+            // Cout = 64 with one 64-channel chunk (enc1b, dec1b + head): the row-pair kernel packs two output rows into one
+            // N = 128 accumulator, 4 MMA issue slots per 256 pixels and filter column instead of 6 (the N = 64 layers sit on
+            // the ~72-cycle issue floor of an M = 128 instruction)
+            if (rowpair_enabled_ && L.halo && L.block_n == 64 && kc == 1 && h % tc::RP_TH == 0 && w % tc::RP_TW == 0) {
+                L.halo = 3;
+                L.resident_kc = 1;
+                make_act_map(&L.map_a_row, bufs_[src].p, max_batch, h, w, bufs_[src].C, tc::RP_TW + 2, tc::RP_TH + 2);
+            }
         }
         // deep layers (N tile = 256): streaming pair kernel -- each CTA fetches the halo once per chunk and half of every
         // weight tile, ~2.6x less L2 -> SM traffic than the per-tap kernel
@@ -486,7 +506,8 @@ void UNet::load(const std::string& blob_path, int net_h, int net_w, int n_classe
             L.block_n_alt = 128;
             make_wgt_map(&L.map_b_half_alt, L.w, cout, 9 * cin, 64);
         }
-        if (dst >= 0) make_out_map(&L.map_out, bufs_[dst].p, max_batch, h, w, bufs_[dst].C, L.halo ? tc::HALO_TW : tc::TILE_W);
+        if (dst >= 0 && L.halo == 3) make_act_map(&L.map_out, bufs_[dst].p, max_batch, h, w, bufs_[dst].C, tc::RP_TW, 8);   // a warp's 8 rows
+        else if (dst >= 0) make_out_map(&L.map_out, bufs_[dst].p, max_batch, h, w, bufs_[dst].C, L.halo ? tc::HALO_TW : tc::TILE_W);
         else L.map_out = L.map_b;  // head layer: no bf16 output
         flops_ += L.flops_per_slice;
         layers_.push_back(L);
@@ -624,7 +645,10 @@ void UNet::run_layer(int li, const uint8_t* d_in_u8, int batch, uint8_t* d_mask,
         launch_halo2<128, tc::EPI_STORE, 0>(L, a, sm_count_, st, &L.map_b_half_alt);   // less than one wave of pairs at N = 256
         return;
     }
-    if (L.halo == 2) {
+    if (L.halo == 3) {
+        if (L.kind == 3) launch_rowpair<tc::EPI_HEAD, 1>(L, a, sm_count_, st);
+        else launch_rowpair<tc::EPI_STORE, 1>(L, a, sm_count_, st);
+    } else if (L.halo == 2) {
         const int rk = L.resident_kc;
         if (L.kind == 3 && rk == 1) launch_halo2<64, tc::EPI_HEAD, 1>(L, a, sm_count_, st);
         else if (L.kind != 3 && L.block_n == 64 && rk == 1) launch_halo2<64, tc::EPI_STORE, 1>(L, a, sm_count_, st);

@@ -1193,5 +1193,281 @@ convt_pair_kernel(const __grid_constant__ CUtensorMap map_a_tile, const __grid_c
     }
 }
 
+
+// ==================================================================================== kernel 5
+// Row-pair halo kernel for the Cout = 64 layers (enc1b, dec1b + head), which kernels 2 / 3 leave on the tcgen05 issue floor:
+// an M = 128 UMMA costs ~72 cycles whether N is 64 or 128 (profiles/r1_mma_rate_microbench.log), so at N = 64 half of every
+// instruction slot is empty and those layers cannot exceed ~45 % of the tensor peak.  Here ONE GEMM row carries TWO output
+// pixels, (y, x) and (y + 1, x): accumulator columns [0, 64) are the 64 channels of the even output row, [64, 128) those of
+// the odd row below it.  An A operand read at input-row shift a (relative to the even row) feeds tap dy = a of the even row
+// and tap dy = a - 1 of the odd row, so with the weight tiles of one filter column laid out as [W(dy=+1) | W(0) | W(-1)]
+// (64 rows each, contiguous) the twelve (dy, row) products of a filter column become FOUR instructions:
+//     a =  0 : N = 128, B = [W(0) ; W(-1)]     a = +1 : N = 128, B = [W(+1) ; W(0)]
+//     a = -1 : N =  64, B = W(-1) -> cols [0, 64)      a = +2 : N = 64, B = W(+1) -> cols [64, 128)
+// i.e. 4 issue slots per 256 pixels instead of 6: 1.5x the MMA-bound rate of kernel 2.  The tile is 8 px x 32 rows; GEMM row
+// group g (8 px) is output rows y0 + 2g, y0 + 2g + 1, so consecutive row groups are TWO halo rows apart: the A descriptors
+// are those of kernel 2 with SBO = 2 * 1280 B.  One TMA box {64 ch, 10 px, 34 rows} per 64-channel chunk; weights resident.
+// Epilogue: lane = (row group, px) holds both pixels of a column pair, so the 2 x 2 max-pool is one in-lane max plus one
+// exchange with lane ^ 1; an epilogue warp stages its 8 rows x 8 px x 64 ch (8 KiB) and writes them with ONE TMA store.
+constexpr int RP_TW = 8, RP_TH = 32;
+constexpr int RP_HALO_ROWS = RP_TH + 2;
+constexpr int RP_HALO_BOX_BYTES = RP_HALO_ROWS * (RP_TW + 2) * 128;     // 43,520 B per 64-channel chunk
+template <int RESIDENT_KC>
+struct RowPairCfg {
+    static constexpr int HALO_STAGE_BYTES = (RP_HALO_BOX_BYTES + 1023) / 1024 * 1024;
+    static constexpr int W_TILE_BYTES = 64 * BLOCK_K * 2;                // 64 output channels x 64 k
+    static constexpr int RES_BYTES = 9 * RESIDENT_KC * W_TILE_BYTES;
+    static constexpr int STG_BYTES = 4 * 8192;                           // one 8 KiB staging slab per epilogue warp
+    static constexpr int A_STAGES = 2;
+    static constexpr int TMEM_COLS = 256;                                // two accumulators of 128 columns
+    static constexpr int SMEM_BYTES = RES_BYTES + A_STAGES * HALO_STAGE_BYTES + STG_BYTES + 4096 + 1024;
+    static_assert(SMEM_BYTES <= 227 * 1024, "row-pair kernel: weights do not fit beside two halo stages");
+};
+
+// 64 -> n_classes head of one pixel on its fp32 features (bias + ReLU applied here), src/process.cpp:158-170
+__device__ __forceinline__ void head_pixel(const ConvArgs& args, const float* s_head, const uint32_t (&r0)[32], const uint32_t (&r1)[32],
+                                           int b, int y, int x) {
+    float f[64];
+    const float4* b4 = reinterpret_cast<const float4*>(args.bias);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const float4 lo = __ldg(b4 + j), hi = __ldg(b4 + 8 + j);
+        f[4 * j + 0] = fmaxf(__uint_as_float(r0[4 * j + 0]) + lo.x, 0.0f);
+        f[4 * j + 1] = fmaxf(__uint_as_float(r0[4 * j + 1]) + lo.y, 0.0f);
+        f[4 * j + 2] = fmaxf(__uint_as_float(r0[4 * j + 2]) + lo.z, 0.0f);
+        f[4 * j + 3] = fmaxf(__uint_as_float(r0[4 * j + 3]) + lo.w, 0.0f);
+        f[32 + 4 * j + 0] = fmaxf(__uint_as_float(r1[4 * j + 0]) + hi.x, 0.0f);
+        f[32 + 4 * j + 1] = fmaxf(__uint_as_float(r1[4 * j + 1]) + hi.y, 0.0f);
+        f[32 + 4 * j + 2] = fmaxf(__uint_as_float(r1[4 * j + 2]) + hi.z, 0.0f);
+        f[32 + 4 * j + 3] = fmaxf(__uint_as_float(r1[4 * j + 3]) + hi.w, 0.0f);
+    }
+    const size_t plane = (size_t)args.H * args.W;
+    const size_t pix = (size_t)b * plane + (size_t)y * args.W + x;
+    float best = -3.402823466e+38f;  // -FLT_MAX, src/process.cpp:159
+    int best_c = 0;
+    for (int c = 0; c < args.n_classes; ++c) {
+        float s = s_head[args.n_classes * 64 + c];
+        const float4* w4 = reinterpret_cast<const float4*>(s_head + c * 64);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            const float4 w = w4[j];
+            s = fmaf(f[4 * j + 0], w.x, s);
+            s = fmaf(f[4 * j + 1], w.y, s);
+            s = fmaf(f[4 * j + 2], w.z, s);
+            s = fmaf(f[4 * j + 3], w.w, s);
+        }
+        if (args.logits) args.logits[((size_t)b * args.n_classes + c) * plane + (size_t)y * args.W + x] = s;
+        if (s > best) { best = s; best_c = c; }   // strict >: first max wins, NaN never wins
+    }
+    args.mask[pix] = args.n_classes == 1 ? (uint8_t)(best > 0.0f ? args.fg_value : 0) : (uint8_t)best_c;
+}
+
+template <int EPI, int RESIDENT_KC>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+conv_rowpair_kernel(const __grid_constant__ CUtensorMap map_a_halo, const __grid_constant__ CUtensorMap map_b,
+                    const __grid_constant__ CUtensorMap map_out, const ConvArgs args) {
+    using C = RowPairCfg<RESIDENT_KC>;
+    static_assert(EPI == EPI_STORE || EPI == EPI_HEAD, "row-pair kernel: conv3x3 layers only");
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* s_res = smem;                                            // [filter column][chunk][dy = +1, 0, -1] weight tiles
+    uint8_t* s_a = smem + C::RES_BYTES;                               // halo ring
+    uint8_t* s_stg = s_a + C::A_STAGES * C::HALO_STAGE_BYTES;         // output staging slabs
+    uint8_t* aux = s_stg + C::STG_BYTES;
+    uint64_t* a_full = reinterpret_cast<uint64_t*>(aux);
+    uint64_t* a_empty = a_full + 4;
+    uint64_t* res_full = a_empty + 4;
+    uint64_t* tmem_full = res_full + 1;
+    uint64_t* tmem_empty = tmem_full + 2;
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+    float* s_head = reinterpret_cast<float*>(aux + 512);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int tiles_x = args.W / RP_TW, tiles_y = args.H / RP_TH;
+    const int total = args.batch * tiles_y * tiles_x;
+    const int kchunks = args.Cin / BLOCK_K;                           // == RESIDENT_KC
+
+    if (threadIdx.x == 0) {
+        prefetch_tmap(&map_a_halo);
+        prefetch_tmap(&map_b);
+        if (EPI != EPI_HEAD) prefetch_tmap(&map_out);
+        for (int i = 0; i < C::A_STAGES; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
+        mbar_init(res_full, 1);
+        for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 128); }
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc_warp(tmem_ptr, C::TMEM_COLS);
+    if (EPI == EPI_HEAD) {
+        for (int i = threadIdx.x; i < args.n_classes * 64 + args.n_classes; i += NUM_THREADS)
+            s_head[i] = i < args.n_classes * 64 ? args.head_w[i] : args.head_b[i - args.n_classes * 64];
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
+    pdl_launch_dependents();
+
+    if (warp == 0) {
+        // ===================================================================== TMA producer
+        if (lane == 0 && blockIdx.x < total) {
+            mbar_expect_tx(res_full, C::RES_BYTES);
+            for (int i = 0; i < 9 * RESIDENT_KC; ++i) {               // slot i = (dx, chunk, j): j = 0, 1, 2 <-> dy = +1, 0, -1
+                const int dxi = i / (3 * RESIDENT_KC), kc = (i / 3) % RESIDENT_KC, j = i % 3;
+                const int tap = (2 - j) * 3 + dxi;
+                tma_load_2d(s_res + i * C::W_TILE_BYTES, &map_b, res_full, tap * args.Cin + kc * BLOCK_K, 0);
+            }
+            int sa = 0;
+            uint32_t pa = 0;
+            pdl_wait();            // weights are in flight; the activations are the previous layer's output
+            for (int t = blockIdx.x; t < total; t += gridDim.x) {
+                const TileCoord tc = decode_tile(t, 1, tiles_x, tiles_y, 64, RP_TW, RP_TH);
+                for (int kc = 0; kc < kchunks; ++kc) {
+                    mbar_wait(&a_empty[sa], pa ^ 1);
+                    mbar_expect_tx(&a_full[sa], RP_HALO_BOX_BYTES);
+                    tma_load_4d(s_a + sa * C::HALO_STAGE_BYTES, &map_a_halo, &a_full[sa], kc * BLOCK_K, tc.x0 - 1, tc.y0 - 1, tc.b);
+                    if (++sa == C::A_STAGES) { sa = 0; pa ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================================================================== MMA issuer
+        if (blockIdx.x < total) {
+            constexpr uint32_t idesc128 = make_idesc(128), idesc64 = make_idesc(64);
+            constexpr int kPitch = RP_TW + 2;                           // halo row = 10 rows of 128 B
+            constexpr int kAUnit = 128 / 16;                            // one 128-byte row in descriptor units
+            constexpr int kWUnit = C::W_TILE_BYTES / 16;
+            int sa = 0, acc = 0;
+            uint32_t pa = 0, acc_phase = 0;
+            mbar_wait(res_full, 0);
+            tc_fence_after();
+            for (int t = blockIdx.x; t < total; t += gridDim.x) {
+                mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * 128);
+                for (int kc = 0; kc < kchunks; ++kc) {
+                    mbar_wait(&a_full[sa], pa);
+                    tc_fence_after();
+                    if (elect_one()) {
+                        // row group g of the A operand = halo rows 2g + (a + 1): SBO = two halo rows
+                        const uint64_t a0 = make_smem_desc_sbo(smem_u32(s_a + sa * C::HALO_STAGE_BYTES), 2 * kPitch * 128);
+#pragma unroll
+                        for (int dxi = 0; dxi < 3; ++dxi) {
+                            const uint64_t w0 = make_smem_desc(smem_u32(s_res + (dxi * RESIDENT_KC + kc) * 3 * C::W_TILE_BYTES));
+#pragma unroll
+                            for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+                                const uint64_t ar = a0 + (uint64_t)(dxi * kAUnit + 2 * k);      // + (a + 1) halo rows below
+                                const uint64_t wk = w0 + (uint64_t)(2 * k);
+                                // a = 0 first: the N = 128 instruction initialises both halves of a fresh accumulator
+                                umma_f16(d_tmem, ar + (uint64_t)(1 * kPitch * kAUnit), wk + (uint64_t)kWUnit, idesc128,
+                                         (dxi | k) != 0 ? 1u : (kc != 0 ? 1u : 0u));
+                                umma_f16(d_tmem, ar + (uint64_t)(2 * kPitch * kAUnit), wk, idesc128, 1u);
+                                umma_f16(d_tmem, ar, wk + (uint64_t)(2 * kWUnit), idesc64, 1u);
+                                umma_f16(d_tmem + 64u, ar + (uint64_t)(3 * kPitch * kAUnit), wk, idesc64, 1u);
+                            }
+                        }
+                        umma_commit(&a_empty[sa]);
+                        if (kc == kchunks - 1) umma_commit(&tmem_full[acc]);
+                    }
+                    __syncwarp();
+                    if (++sa == C::A_STAGES) { sa = 0; pa ^= 1; }
+                }
+                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            }
+        }
+    } else {
+        // ===================================================================== epilogue (warps 2..5): lane = (row group, px)
+        const int quarter = warp & 3;
+        const int gl = lane >> 3, px = lane & 7;
+        const uint32_t slab = smem_u32(s_stg + quarter * 8192);
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        for (int t = blockIdx.x; t < total; t += gridDim.x) {
+            const TileCoord tcd = decode_tile(t, 1, tiles_x, tiles_y, 64, RP_TW, RP_TH);
+            const int yw = tcd.y0 + quarter * 8;                       // first of this warp's 8 output rows
+            mbar_wait(&tmem_full[acc], acc_phase);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * 128);
+            if (EPI == EPI_HEAD) {
+#pragma unroll 1
+                for (int half = 0; half < 2; ++half) {
+                    uint32_t r0[32], r1[32];
+                    tmem_ld32(taddr + half * 64, r0);
+                    tmem_ld32(taddr + half * 64 + 32, r1);
+                    tmem_ld_wait();
+                    if (half == 1) {
+                        tc_fence_before();
+                        mbar_arrive(&tmem_empty[acc]);
+                    }
+                    head_pixel(args, s_head, r0, r1, tcd.b, yw + 2 * gl + half, tcd.x0 + px);
+                }
+            } else {
+                uint32_t pk[2][32];
+                const float4* b4 = reinterpret_cast<const float4*>(args.bias);
+#pragma unroll
+                for (int half = 0; half < 2; ++half) {
+                    uint32_t r0[32], r1[32];
+                    tmem_ld32(taddr + half * 64, r0);
+                    tmem_ld32(taddr + half * 64 + 32, r1);
+                    tmem_ld_wait();
+                    if (half == 1) {
+                        tc_fence_before();
+                        mbar_arrive(&tmem_empty[acc]);
+                    }
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const float4 lo = __ldg(b4 + j), hi = __ldg(b4 + 8 + j);
+                        pk[half][2 * j] = pack_bf16(fmaxf(__uint_as_float(r0[4 * j + 0]) + lo.x, 0.0f), fmaxf(__uint_as_float(r0[4 * j + 1]) + lo.y, 0.0f));
+                        pk[half][2 * j + 1] = pack_bf16(fmaxf(__uint_as_float(r0[4 * j + 2]) + lo.z, 0.0f), fmaxf(__uint_as_float(r0[4 * j + 3]) + lo.w, 0.0f));
+                        pk[half][16 + 2 * j] = pack_bf16(fmaxf(__uint_as_float(r1[4 * j + 0]) + hi.x, 0.0f), fmaxf(__uint_as_float(r1[4 * j + 1]) + hi.y, 0.0f));
+                        pk[half][16 + 2 * j + 1] = pack_bf16(fmaxf(__uint_as_float(r1[4 * j + 2]) + hi.z, 0.0f), fmaxf(__uint_as_float(r1[4 * j + 3]) + hi.w, 0.0f));
+                    }
+                }
+                // the previous TMA store must have finished reading the slab before it is overwritten
+                if (lane == 0) tma_store_wait_read();
+                __syncwarp();
+#pragma unroll
+                for (int half = 0; half < 2; ++half) {
+                    // slab row = (output row inside the warp's 8) * 8 + px; 16-byte chunk j of a row lives at j ^ (row & 7)
+                    const uint32_t row_addr = slab + (uint32_t)(((2 * gl + half) * 8 + px) * 128);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j)
+                        st_shared_v4(row_addr + (uint32_t)((j ^ px) << 4), pk[half][4 * j], pk[half][4 * j + 1], pk[half][4 * j + 2], pk[half][4 * j + 3]);
+                }
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0) {
+                    tma_store_4d(&map_out, slab, args.out_coff, tcd.x0, yw, tcd.b);       // box {64 ch, 8 px, 8 rows, 1 image}
+                    tma_store_commit();
+                }
+                if (args.pool) {
+                    // 2 x 2 max-pool: rows (2 gl, 2 gl + 1) are this lane's two halves, the column partner is lane ^ 1.  The even
+                    // lane finishes channels [0, 32), the odd lane [32, 64): each sends the half the other one needs.
+                    const bool odd = lane & 1;
+                    uint32_t res[16];
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        const uint32_t lo = max_bf16x2(pk[0][i], pk[1][i]), hi = max_bf16x2(pk[0][16 + i], pk[1][16 + i]);
+                        const uint32_t got = __shfl_xor_sync(0xFFFFFFFFu, odd ? lo : hi, 1);
+                        res[i] = max_bf16x2(odd ? hi : lo, got);
+                    }
+                    uint4* dst = reinterpret_cast<uint4*>(args.pool + (((size_t)tcd.b * (args.H / 2) + ((yw >> 1) + gl)) * (args.W / 2) +
+                                                                       ((tcd.x0 + px) >> 1)) * args.pool_cstride + (odd ? 32 : 0));
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) dst[i] = make_uint4(res[4 * i], res[4 * i + 1], res[4 * i + 2], res[4 * i + 3]);
+                }
+            }
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+        if (EPI != EPI_HEAD && lane == 0) tma_store_wait_read();
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        __syncwarp();
+        tmem_dealloc_warp(tmem_base, C::TMEM_COLS);
+    }
+}
+
 }  // namespace tc
 }  // namespace ms
