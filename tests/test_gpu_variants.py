@@ -92,21 +92,28 @@ def test_rowpair_kernel_matches_halo_kernel_and_fp32_oracle(ms, tmp_path_factory
     B = 3
     vol = synth.ct_volume(B, 512, 512, first_seed=40)
     out = {}
-    for mode in ("0", "1"):
-        with _Env(MEDSEG_ROWPAIR=mode):
+    # halo kernels | pair row-pair kernel where the weights stay resident | + dec1a (streamed weights) | single-CTA row-pair kernel
+    modes = {"0": dict(MEDSEG_ROWPAIR="0"), "1": dict(MEDSEG_ROWPAIR="1"), "2": dict(MEDSEG_ROWPAIR="2"),
+             "s": dict(MEDSEG_ROWPAIR="2", MEDSEG_ROWPAIR2="0")}
+    for mode, env in modes.items():
+        with _Env(**env):
             cfg = {"weights": blob, "max_batch": B}
             if n_classes == 1:
                 cfg["head"] = "binary"
             eng = ms.Engine(cfg)
         kern = dict(zip(eng.layer_names(), eng.layer_kernels()))
+        want_kernel = "conv_rowpair_kernel" if mode == "s" else "conv_rowpair2_kernel"
         for name in ("enc1b", "dec1b_head"):
-            assert ("rowpair" in kern[name]) == (mode == "1"), (mode, kern[name])
+            assert (want_kernel in kern[name]) == (mode != "0"), (mode, kern[name])
+        assert (want_kernel in kern["dec1a"]) == (mode in ("2", "s")), (mode, kern["dec1a"])
         norm = eng.preprocess(vol)
         mask, logits = eng.process(norm, want_logits=True)
         out[mode] = {"mask": mask, "logits": logits, "cat1": eng.read_activation("cat1", B).reshape(B, 128, 512, 512)[:, :64],
-                     "p1": eng.read_activation("p1", B).reshape(B, 64, 256, 256)}
+                     "p1": eng.read_activation("p1", B).reshape(B, 64, 256, 256), "d1a": eng.read_activation("d1a", B)}
         eng.cleanup()
-    assert (out["0"]["mask"] == out["1"]["mask"]).mean() >= 0.9999
+    for mode in ("1", "2", "s"):
+        assert (out["0"]["mask"] == out[mode]["mask"]).mean() >= 0.9999
+        assert np.abs(out["0"]["d1a"] - out[mode]["d1a"]).max() <= 1e-2 * np.abs(out["0"]["d1a"]).max(), mode
     for i in (0, B - 1):
         taps = {}
         with torch.no_grad():
@@ -115,12 +122,13 @@ def test_rowpair_kernel_matches_halo_kernel_and_fp32_oracle(ms, tmp_path_factory
             x1 = taps["x1"]
             p1 = F.max_pool2d(x1, 2).numpy()[0]
             x1 = x1.numpy()[0]
-        for mode in ("0", "1"):
+        for mode in modes:
             o = out[mode]
             assert np.abs(o["cat1"][i] - x1).max() / np.abs(x1).max() < 2e-2, mode
             assert np.abs(o["p1"][i] - p1).max() / np.abs(p1).max() < 2e-2, mode
             err = np.abs(o["logits"][i] - want)
             assert np.quantile(err, 0.999) < 2e-2 and err.max() < 8e-2, (mode, err.max())
         # the pooled map is exactly the max of the stored skip map (both come from the same bf16 values)
-        c1 = torch.from_numpy(out["1"]["cat1"][i:i + 1])
-        assert np.array_equal(F.max_pool2d(c1, 2).numpy()[0], out["1"]["p1"][i])
+        for mode in ("2", "s"):
+            c1 = torch.from_numpy(out[mode]["cat1"][i:i + 1])
+            assert np.array_equal(F.max_pool2d(c1, 2).numpy()[0], out[mode]["p1"][i])

@@ -235,6 +235,18 @@ void make_convt_out_map(CUtensorMap* m, const __nv_bfloat16* base, int B, int H_
                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     MS_REQUIRE(r == CUDA_SUCCESS, MS_ERR_CUDA, "cuTensorMapEncodeTiled(convT output) failed: " + std::to_string((int)r));
 }
+// destination of the row-pair kernel: [B][H][W][C] viewed as (C, W, row parity, H / 2, B); box {64 ch, 8 px, 1, 4, 1} = the four
+// rows of one parity of an epilogue warp's eight
+void make_rowpair_out_map(CUtensorMap* m, const __nv_bfloat16* base, int B, int H, int W, int C) {
+    cuuint64_t dims[5] = {(cuuint64_t)C, (cuuint64_t)W, 2, (cuuint64_t)H / 2, (cuuint64_t)B};
+    cuuint64_t strides[4] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)2 * W * C * 2, (cuuint64_t)H * W * C * 2};
+    cuuint32_t box[5] = {(cuuint32_t)tc::BLOCK_K, (cuuint32_t)tc::RP_TW, 1, 4, 1};
+    cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    CUresult r = encode_fn()(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<__nv_bfloat16*>(base), dims, strides, box, estr,
+                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    MS_REQUIRE(r == CUDA_SUCCESS, MS_ERR_CUDA, "cuTensorMapEncodeTiled(row-pair output) failed: " + std::to_string((int)r));
+}
 // weights [N][K] bf16, box {64, block_n}
 void make_wgt_map(CUtensorMap* m, const __nv_bfloat16* base, int N, int K, int block_n) {
     cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)N};
@@ -274,11 +286,22 @@ void launch_halo(const UNetLayer& L, const tc::ConvArgs& a, int sm_count, cudaSt
 
 template <int EPI, int RKC>
 void launch_rowpair(const UNetLayer& L, const tc::ConvArgs& a, int sm_count, cudaStream_t st) {
-    using C = tc::RowPairCfg<RKC>;
+    using C = tc::RowPairCfg<EPI, RKC>;
     set_max_dynamic_smem(tc::conv_rowpair_kernel<EPI, RKC>, C::SMEM_BYTES);
     const int total = a.batch * (a.H / tc::RP_TH) * (a.W / tc::RP_TW);
     const int grid = std::min(total, sm_count);
-    launch_kernel(tc::conv_rowpair_kernel<EPI, RKC>, dim3(grid), dim3(tc::NUM_THREADS), C::SMEM_BYTES, st, true, L.map_a_row, L.map_b, L.map_out, a);
+    launch_kernel(tc::conv_rowpair_kernel<EPI, RKC>, dim3(grid), dim3(C::THREADS), C::SMEM_BYTES, st, true, L.map_a_row, L.map_b, L.map_out, a);
+    MS_LAUNCH_CHECK();
+}
+
+template <int EPI, int RKC>
+void launch_rowpair2(const UNetLayer& L, const tc::ConvArgs& a, int sm_count, cudaStream_t st) {
+    using C = tc::RowPair2Cfg<EPI, RKC>;
+    set_max_dynamic_smem(tc::conv_rowpair2_kernel<EPI, RKC>, C::SMEM_BYTES);
+    const int pairs = a.batch * (a.H / tc::RP_TH) * (a.W / tc::RP_TW) / 2;
+    const int grid = 2 * std::min(pairs, sm_count / 2);
+    launch_kernel(tc::conv_rowpair2_kernel<EPI, RKC>, dim3(grid), dim3(tc::HALO2_THREADS), C::SMEM_BYTES, st, true, L.map_a_row, L.map_b,
+                  L.map_b_half, L.map_out, a);
     MS_LAUNCH_CHECK();
 }
 
@@ -378,7 +401,10 @@ void UNet::load(const std::string& blob_path, int net_h, int net_w, int n_classe
     const char* sv = std::getenv("MEDSEG_STREAM2");
     stream2_enabled_ = !(sv && sv[0] == '0');
     const char* rp = std::getenv("MEDSEG_ROWPAIR");
-    rowpair_enabled_ = !(rp && rp[0] == '0');   // MEDSEG_CTA2=2: prefer the pair kernel wherever it applies (A/B measurements)
+    rowpair_enabled_ = !(rp && rp[0] == '0');
+    rowpair_stream_ = !(rp && rp[0] == '1');
+    const char* rp2 = std::getenv("MEDSEG_ROWPAIR2");
+    rowpair2_enabled_ = !(rp2 && rp2[0] == '0');   // MEDSEG_CTA2=2: prefer the pair kernel wherever it applies (A/B measurements)
     const char* pv = std::getenv("MEDSEG_HALO_PITCH");
     halo_pitch_ = 10;
     (void)pv;
@@ -487,9 +513,17 @@ void UNet::load(const std::string& blob_path, int net_h, int net_w, int n_classe
             // Cout = 64 with one 64-channel chunk (enc1b, dec1b + head): the row-pair kernel packs two output rows into one
             // N = 128 accumulator, 4 MMA issue slots per 256 pixels and filter column instead of 6 (the N = 64 layers sit on
             // the ~72-cycle issue floor of an M = 128 instruction)
-            if (rowpair_enabled_ && L.halo && L.block_n == 64 && kc == 1 && h % tc::RP_TH == 0 && w % tc::RP_TW == 0) {
+            // (two chunks -- dec1a -- stream their weights: 144 KiB do not fit beside two 43 KiB halo stages; MEDSEG_ROWPAIR=1
+            // keeps that layer on the pair kernel)
+            if (rowpair_enabled_ && L.halo && L.block_n == 64 && (kc == 1 || (kc == 2 && rowpair_stream_ && !head)) && h % tc::RP_TH == 0 &&
+                w % tc::RP_TW == 0) {
                 L.halo = 3;
-                L.resident_kc = 1;
+                L.resident_kc = kc == 1 ? 1 : 0;
+                // its cta_group::2 form: every CTA reads half of each B operand (the kernel is shared-memory-bandwidth bound)
+                if (cta2_enabled_ && rowpair2_enabled_ && ((h / tc::RP_TH) * (w / tc::RP_TW)) % 2 == 0) {
+                    L.halo = 4;
+                    make_wgt_map(&L.map_b_half, L.w, cout, 9 * cin, 32);
+                }
                 make_act_map(&L.map_a_row, bufs_[src].p, max_batch, h, w, bufs_[src].C, tc::RP_TW + 2, tc::RP_TH + 2);
             }
         }
@@ -506,7 +540,7 @@ void UNet::load(const std::string& blob_path, int net_h, int net_w, int n_classe
             L.block_n_alt = 128;
             make_wgt_map(&L.map_b_half_alt, L.w, cout, 9 * cin, 64);
         }
-        if (dst >= 0 && L.halo == 3) make_act_map(&L.map_out, bufs_[dst].p, max_batch, h, w, bufs_[dst].C, tc::RP_TW, 8);   // a warp's 8 rows
+        if (dst >= 0 && L.halo >= 3) make_rowpair_out_map(&L.map_out, bufs_[dst].p, max_batch, h, w, bufs_[dst].C);
         else if (dst >= 0) make_out_map(&L.map_out, bufs_[dst].p, max_batch, h, w, bufs_[dst].C, L.halo ? tc::HALO_TW : tc::TILE_W);
         else L.map_out = L.map_b;  // head layer: no bf16 output
         flops_ += L.flops_per_slice;
@@ -645,9 +679,14 @@ void UNet::run_layer(int li, const uint8_t* d_in_u8, int batch, uint8_t* d_mask,
         launch_halo2<128, tc::EPI_STORE, 0>(L, a, sm_count_, st, &L.map_b_half_alt);   // less than one wave of pairs at N = 256
         return;
     }
-    if (L.halo == 3) {
+    if (L.halo == 4) {
+        if (L.kind == 3) launch_rowpair2<tc::EPI_HEAD, 1>(L, a, sm_count_, st);
+        else if (L.resident_kc == 1) launch_rowpair2<tc::EPI_STORE, 1>(L, a, sm_count_, st);
+        else launch_rowpair2<tc::EPI_STORE, 0>(L, a, sm_count_, st);
+    } else if (L.halo == 3) {
         if (L.kind == 3) launch_rowpair<tc::EPI_HEAD, 1>(L, a, sm_count_, st);
-        else launch_rowpair<tc::EPI_STORE, 1>(L, a, sm_count_, st);
+        else if (L.resident_kc == 1) launch_rowpair<tc::EPI_STORE, 1>(L, a, sm_count_, st);
+        else launch_rowpair<tc::EPI_STORE, 0>(L, a, sm_count_, st);
     } else if (L.halo == 2) {
         const int rk = L.resident_kc;
         if (L.kind == 3 && rk == 1) launch_halo2<64, tc::EPI_HEAD, 1>(L, a, sm_count_, st);

@@ -27,7 +27,7 @@ struct UNetLayer {
     CUtensorMap map_out;         // TMA store of the epilogue (one epilogue warp's 32-pixel x 64-channel slab)
     CUtensorMap map_a_row;       // halo kernel: box {64 ch, 10 px, 18 rows}
     bool convt_pair = false;     // ConvT: cta_group::2 GEMM (convt_pair_kernel) with map_a_row = {64 ch, 8 px, 16 rows} tiles
-    int halo = 0;                // 0 = per-tap streaming kernel, 1 = halo-stationary kernel, 2 = its cta_group::2 version, 3 = row-pair kernel
+    int halo = 0;                // 0 = per-tap streaming kernel, 1 = halo-stationary kernel, 2 = its cta_group::2 version, 3 = row-pair kernel, 4 = row-pair cta_group::2
     int resident_kc = 0;         // halo kernel: > 0 when all weights stay in shared memory
     int halo_pitch = 16;         // halo kernel: shared-memory rows per halo image row (10 dense / 16 aligned)
     double flops_per_slice = 0;  // 2 * MAC
@@ -36,6 +36,7 @@ struct UNetLayer {
         const char* epi = kind == 3 ? "EPI_HEAD" : (kind == 2 ? "EPI_CONVT" : "EPI_STORE");
         if (kind == 0) return "first_conv_kernel";
         if (convt_pair) return "tc::convt_pair_kernel<" + std::to_string(block_n) + ">";
+        if (halo == 4) return std::string("tc::conv_rowpair2_kernel<") + epi + ", " + std::to_string(resident_kc) + ">";
         if (halo == 3) return std::string("tc::conv_rowpair_kernel<") + epi + ", " + std::to_string(resident_kc) + ">";
         if (halo == 2) return "tc::conv_halo2_kernel<" + std::to_string(block_n) + ", " + epi + ", " + std::to_string(resident_kc) + ">";
         if (halo == 1) return "tc::conv_halo_kernel<" + std::to_string(block_n) + ", " + epi + ", " + std::to_string(resident_kc) + ", 10>";
@@ -83,6 +84,8 @@ class UNet {
     bool deep2_enabled_ = true;    // MEDSEG_DEEP2=0: per-tap kernel for the N = 256 layers
     bool res_big_ = true;          // MEDSEG_RES_BIG=0: 144 KiB half-weight sets stream instead of staying resident
     bool rowpair_enabled_ = true;  // MEDSEG_ROWPAIR=0: kernels 2 / 3 for the Cout = 64 layers
+    bool rowpair2_enabled_ = true; // MEDSEG_ROWPAIR2=0: single-CTA row-pair kernel instead of its cta_group::2 form
+    bool rowpair_stream_ = true;   // MEDSEG_ROWPAIR=1: row-pair kernel only where its weights stay resident (not dec1a)
     bool stream2_enabled_ = true;  // MEDSEG_STREAM2=0: per-tap kernel instead of the streaming pair kernel (dec2a)
     int halo_pitch_ = 16;       // MEDSEG_HALO_PITCH
     int desc_mode_ = 0;         // MEDSEG_DESC_MODE: UMMA descriptor base-offset convention of the halo kernel

@@ -167,6 +167,12 @@ __device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, u
         ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
         : "memory");
 }
+// L2 prefetch of a 4-D box (no shared-memory destination, no barrier): the later tma_load_4d of the same box hits L2
+__device__ __forceinline__ void tma_prefetch_4d(const CUtensorMap* map, int c0, int c1, int c2, int c3) {
+    asm volatile("cp.async.bulk.prefetch.tensor.4d.L2.global.tile [%0, {%1, %2, %3, %4}];"
+                 ::"l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+                 : "memory");
+}
 __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
     asm volatile(
         "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
@@ -787,8 +793,12 @@ __device__ __forceinline__ uint32_t mapa_rank(uint32_t smem_addr, uint32_t rank)
     asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_addr), "r"(rank));
     return r;
 }
+// Remote "accumulator drained" arrive.  The ordering that matters (this thread's tcgen05.ld before the leader's next MMA) is
+// carried by tcgen05.wait::ld + tcgen05.fence::before_thread_sync on this side and the fence::after_thread_sync behind the
+// leader's wait, so the arrive itself needs no cluster-scope release: `.release.cluster` compiled to MEMBAR.ALL + ERRBAR in
+// front of every arrive and was ~45 % of the epilogue warps' stall samples (profiles/r2_ncu_rowpair2_before.txt).
 __device__ __forceinline__ void mbar_arrive_cluster_fwd(uint32_t cluster_addr) {
-    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 constexpr int HALO2_THREADS = 224;   // warps 0/1 producer + MMA, 2..5 epilogue, 6 weight-tile producer (streaming mode)
 constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;   // clears the CTA-rank bit of a shared::cluster address -> CTA 0 of the pair
@@ -1212,15 +1222,23 @@ convt_pair_kernel(const __grid_constant__ CUtensorMap map_a_tile, const __grid_c
 constexpr int RP_TW = 8, RP_TH = 32;
 constexpr int RP_HALO_ROWS = RP_TH + 2;
 constexpr int RP_HALO_BOX_BYTES = RP_HALO_ROWS * (RP_TW + 2) * 128;     // 43,520 B per 64-channel chunk
-template <int RESIDENT_KC>
+template <int EPI, int RESIDENT_KC>
 struct RowPairCfg {
     static constexpr int HALO_STAGE_BYTES = (RP_HALO_BOX_BYTES + 1023) / 1024 * 1024;
     static constexpr int W_TILE_BYTES = 64 * BLOCK_K * 2;                // 64 output channels x 64 k
     static constexpr int RES_BYTES = 9 * RESIDENT_KC * W_TILE_BYTES;
-    static constexpr int STG_BYTES = 4 * 8192;                           // one 8 KiB staging slab per epilogue warp
-    static constexpr int A_STAGES = 2;
+    // RESIDENT_KC == 0 (Cin > 64: the weight set does not fit beside two halo stages): the three tiles of one filter column
+    // and chunk ([W(+1) | W(0) | W(-1)], 24 KiB = 16 MMAs) stream through their own ring, fed by their own producer warp
+    static constexpr int B_STAGE_BYTES = 3 * W_TILE_BYTES;
+    static constexpr int B_STAGES = RESIDENT_KC > 0 ? 0 : 3;
+    // one 4 KiB staging slab per epilogue warp (the four rows of one parity; none for the head, which stores no feature map)
+    // two 4 KiB staging slabs per epilogue warp (the four rows of each parity; none for the head, which stores no feature map)
+    static constexpr int STG_BYTES = EPI == EPI_HEAD ? 0 : 4 * 8192;
+    // halo stages: two where the slabs take 32 KiB (a third stage measured no faster: the loads are not the bound)
+    static constexpr int A_STAGES = EPI == EPI_HEAD ? 3 : 2;
     static constexpr int TMEM_COLS = 256;                                // two accumulators of 128 columns
-    static constexpr int SMEM_BYTES = RES_BYTES + A_STAGES * HALO_STAGE_BYTES + STG_BYTES + 4096 + 1024;
+    static constexpr int THREADS = RESIDENT_KC > 0 ? NUM_THREADS : NUM_THREADS + 32;
+    static constexpr int SMEM_BYTES = RES_BYTES + B_STAGES * B_STAGE_BYTES + A_STAGES * HALO_STAGE_BYTES + STG_BYTES + 4096 + 1024;
     static_assert(SMEM_BYTES <= 227 * 1024, "row-pair kernel: weights do not fit beside two halo stages");
 };
 
@@ -1262,65 +1280,209 @@ __device__ __forceinline__ void head_pixel(const ConvArgs& args, const float* s_
     args.mask[pix] = args.n_classes == 1 ? (uint8_t)(best > 0.0f ? args.fg_value : 0) : (uint8_t)best_c;
 }
 
+// 64 -> n_classes head of one pixel on its fp32 features (bias + ReLU already applied), src/process.cpp:158-170
+__device__ __forceinline__ void head_pixel_f(const ConvArgs& args, const float* s_head, const float (&f)[64], int b, int y, int x) {
+    const size_t plane = (size_t)args.H * args.W;
+    const size_t pix = (size_t)b * plane + (size_t)y * args.W + x;
+    float best = -3.402823466e+38f;  // -FLT_MAX, src/process.cpp:159
+    int best_c = 0;
+    for (int c = 0; c < args.n_classes; ++c) {
+        // four partial sums: the dot product is a 16-deep dependent chain instead of a 64-deep one
+        float s0 = s_head[args.n_classes * 64 + c], s1 = 0.0f, s2 = 0.0f, s3 = 0.0f;
+        const float4* w4 = reinterpret_cast<const float4*>(s_head + c * 64);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            const float4 w = w4[j];
+            s0 = fmaf(f[4 * j + 0], w.x, s0);
+            s1 = fmaf(f[4 * j + 1], w.y, s1);
+            s2 = fmaf(f[4 * j + 2], w.z, s2);
+            s3 = fmaf(f[4 * j + 3], w.w, s3);
+        }
+        const float sum = (s0 + s1) + (s2 + s3);
+        if (args.logits) args.logits[((size_t)b * args.n_classes + c) * plane + (size_t)y * args.W + x] = sum;
+        if (sum > best) { best = sum; best_c = c; }   // strict >: first max wins, NaN never wins
+    }
+    args.mask[pix] = args.n_classes == 1 ? (uint8_t)(best > 0.0f ? args.fg_value : 0) : (uint8_t)best_c;
+}
+
+// Epilogue of one row-pair tile for one epilogue warp: lane = (row group gl, px) owns output pixels (yw + 2 gl, x0 + px) in
+// accumulator columns [0, 64) and (yw + 2 gl + 1, x0 + px) in [64, 128).  The epilogue, not the MMA pipe, bounds these layers
+// (stripped of its math the kernel runs at ~1.6 PFLOP/s), and it is LATENCY bound -- one warp per scheduler, every TMEM load,
+// store-read wait and proxy fence exposed -- so the tile is handled in one pass: all four TMEM loads in flight together and
+// the accumulator handed back before any math, the bias from shared memory, one slab per row parity (the wait for the
+// previous tile's TMA stores is long satisfied), one proxy fence and both stores issued together.
+template <int EPI, bool REMOTE>
+__device__ __forceinline__ void rowpair_epilogue_tile(const ConvArgs& args, const CUtensorMap* map_out, const float* s_head, const float* s_bias,
+                                                      uint32_t taddr, uint32_t slab, const TileCoord& tcd, int yw, int lane,
+                                                      uint64_t* tmem_empty_bar, uint32_t remote_empty) {
+    const int gl = lane >> 3, px = lane & 7;
+    uint32_t r[4][32];
+    tmem_ld32(taddr, r[0]);
+    tmem_ld32(taddr + 32, r[1]);
+    tmem_ld32(taddr + 64, r[2]);
+    tmem_ld32(taddr + 96, r[3]);
+    tmem_ld_wait();
+    tc_fence_before();
+    if (REMOTE) mbar_arrive_cluster_fwd(remote_empty); else mbar_arrive(tmem_empty_bar);
+    const float4* b4 = reinterpret_cast<const float4*>(s_bias);     // broadcast 16-byte loads
+    if (EPI == EPI_HEAD) {
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+            float f[64];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                const float4 bb = b4[j];
+                const uint32_t* q = &r[2 * half + (j >> 3)][4 * (j & 7)];
+                f[4 * j + 0] = fmaxf(__uint_as_float(q[0]) + bb.x, 0.0f);
+                f[4 * j + 1] = fmaxf(__uint_as_float(q[1]) + bb.y, 0.0f);
+                f[4 * j + 2] = fmaxf(__uint_as_float(q[2]) + bb.z, 0.0f);
+                f[4 * j + 3] = fmaxf(__uint_as_float(q[3]) + bb.w, 0.0f);
+            }
+            head_pixel_f(args, s_head, f, tcd.b, yw + 2 * gl + half, tcd.x0 + px);
+        }
+        return;
+    }
+    uint32_t pk[2][32];                                              // pk[half][i] = channels 2 i, 2 i + 1
+#pragma unroll
+    for (int half = 0; half < 2; ++half)
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            const float4 bb = b4[j];
+            const uint32_t* q = &r[2 * half + (j >> 3)][4 * (j & 7)];
+            pk[half][2 * j] = pack_bf16(fmaxf(__uint_as_float(q[0]) + bb.x, 0.0f), fmaxf(__uint_as_float(q[1]) + bb.y, 0.0f));
+            pk[half][2 * j + 1] = pack_bf16(fmaxf(__uint_as_float(q[2]) + bb.z, 0.0f), fmaxf(__uint_as_float(q[3]) + bb.w, 0.0f));
+        }
+    // the previous tile's TMA stores must have finished reading the two slabs
+    if (lane == 0) tma_store_wait_read();
+    __syncwarp();
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+        // slab row = (row group) * 8 + px; 16-byte chunk j of a row lives at j ^ (row & 7)
+        const uint32_t row_addr = slab + (uint32_t)(half * 4096 + lane * 128);
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+            st_shared_v4(row_addr + (uint32_t)((j ^ px) << 4), pk[half][4 * j], pk[half][4 * j + 1], pk[half][4 * j + 2], pk[half][4 * j + 3]);
+    }
+    fence_proxy_async_smem();
+    __syncwarp();
+    if (lane == 0) {
+        // destination viewed as (C, W, row parity, H / 2, B): box {64 ch, 8 px, 1, 4 row pairs, 1} = rows yw + half + 2 g
+        tma_store_5d(map_out, slab, args.out_coff, tcd.x0, 0, yw >> 1, tcd.b);
+        tma_store_5d(map_out, slab + 4096u, args.out_coff, tcd.x0, 1, yw >> 1, tcd.b);
+        tma_store_commit();
+    }
+    if (args.pool) {
+        // 2 x 2 max-pool: rows (2 gl, 2 gl + 1) are this lane's two halves, the column partner is lane ^ 1.  The even
+        // lane finishes channels [0, 32), the odd lane [32, 64): each sends the half the other one needs.
+        const bool odd = lane & 1;
+        uint32_t res[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            const uint32_t lo = max_bf16x2(pk[0][i], pk[1][i]), hi = max_bf16x2(pk[0][16 + i], pk[1][16 + i]);
+            const uint32_t got = __shfl_xor_sync(0xFFFFFFFFu, odd ? lo : hi, 1);
+            res[i] = max_bf16x2(odd ? hi : lo, got);
+        }
+        uint4* dst = reinterpret_cast<uint4*>(args.pool + (((size_t)tcd.b * (args.H / 2) + ((yw >> 1) + gl)) * (args.W / 2) +
+                                                           ((tcd.x0 + px) >> 1)) * args.pool_cstride + (odd ? 32 : 0));
+#pragma unroll
+        for (int i = 0; i < 4; ++i) dst[i] = make_uint4(res[4 * i], res[4 * i + 1], res[4 * i + 2], res[4 * i + 3]);
+    }
+}
+
 template <int EPI, int RESIDENT_KC>
-__global__ void __launch_bounds__(NUM_THREADS, 1)
+__global__ void __launch_bounds__(RowPairCfg<EPI, RESIDENT_KC>::THREADS, 1)
 conv_rowpair_kernel(const __grid_constant__ CUtensorMap map_a_halo, const __grid_constant__ CUtensorMap map_b,
                     const __grid_constant__ CUtensorMap map_out, const ConvArgs args) {
-    using C = RowPairCfg<RESIDENT_KC>;
+    using C = RowPairCfg<EPI, RESIDENT_KC>;
     static_assert(EPI == EPI_STORE || EPI == EPI_HEAD, "row-pair kernel: conv3x3 layers only");
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* s_res = smem;                                            // [filter column][chunk][dy = +1, 0, -1] weight tiles
-    uint8_t* s_a = smem + C::RES_BYTES;                               // halo ring
+    uint8_t* s_b = smem + C::RES_BYTES;                               // streamed weight ring (RESIDENT_KC == 0)
+    uint8_t* s_a = s_b + C::B_STAGES * C::B_STAGE_BYTES;              // halo ring
     uint8_t* s_stg = s_a + C::A_STAGES * C::HALO_STAGE_BYTES;         // output staging slabs
     uint8_t* aux = s_stg + C::STG_BYTES;
     uint64_t* a_full = reinterpret_cast<uint64_t*>(aux);
     uint64_t* a_empty = a_full + 4;
-    uint64_t* res_full = a_empty + 4;
+    uint64_t* b_full = a_empty + 4;
+    uint64_t* b_empty = b_full + 4;
+    uint64_t* res_full = b_empty + 4;
     uint64_t* tmem_full = res_full + 1;
     uint64_t* tmem_empty = tmem_full + 2;
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
     float* s_head = reinterpret_cast<float*>(aux + 512);
+    float* s_bias = reinterpret_cast<float*>(aux + 3072);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int tiles_x = args.W / RP_TW, tiles_y = args.H / RP_TH;
     const int total = args.batch * tiles_y * tiles_x;
-    const int kchunks = args.Cin / BLOCK_K;                           // == RESIDENT_KC
+    const int kchunks = args.Cin / BLOCK_K;                           // == RESIDENT_KC when the weights are resident
 
     if (threadIdx.x == 0) {
         prefetch_tmap(&map_a_halo);
         prefetch_tmap(&map_b);
         if (EPI != EPI_HEAD) prefetch_tmap(&map_out);
         for (int i = 0; i < C::A_STAGES; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
+        for (int i = 0; i < 4; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
         mbar_init(res_full, 1);
         for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 128); }
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc_warp(tmem_ptr, C::TMEM_COLS);
     if (EPI == EPI_HEAD) {
-        for (int i = threadIdx.x; i < args.n_classes * 64 + args.n_classes; i += NUM_THREADS)
+        for (int i = threadIdx.x; i < args.n_classes * 64 + args.n_classes; i += C::THREADS)
             s_head[i] = i < args.n_classes * 64 ? args.head_w[i] : args.head_b[i - args.n_classes * 64];
     }
+    if (threadIdx.x < 64) s_bias[threadIdx.x] = args.bias[threadIdx.x];
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
     pdl_launch_dependents();
 
-    if (warp == 0) {
+    if (warp == 6) {
+        // ===================================================================== weight producer (streaming mode only)
+        if (RESIDENT_KC == 0 && lane == 0 && blockIdx.x < total) {
+            int sb = 0;
+            uint32_t pb = 0;
+            for (int t = blockIdx.x; t < total; t += gridDim.x)
+                for (int kc = 0; kc < kchunks; ++kc)
+                    for (int dxi = 0; dxi < 3; ++dxi) {
+                        mbar_wait(&b_empty[sb], pb ^ 1);
+                        mbar_expect_tx(&b_full[sb], C::B_STAGE_BYTES);
+                        for (int j = 0; j < 3; ++j)              // j = 0, 1, 2 <-> dy = +1, 0, -1
+                            tma_load_2d(s_b + sb * C::B_STAGE_BYTES + j * C::W_TILE_BYTES, &map_b, &b_full[sb],
+                                        ((2 - j) * 3 + dxi) * args.Cin + kc * BLOCK_K, 0);
+                        if (++sb == C::B_STAGES) { sb = 0; pb ^= 1; }
+                    }
+        }
+    } else if (warp == 0) {
         // ===================================================================== TMA producer
         if (lane == 0 && blockIdx.x < total) {
-            mbar_expect_tx(res_full, C::RES_BYTES);
-            for (int i = 0; i < 9 * RESIDENT_KC; ++i) {               // slot i = (dx, chunk, j): j = 0, 1, 2 <-> dy = +1, 0, -1
-                const int dxi = i / (3 * RESIDENT_KC), kc = (i / 3) % RESIDENT_KC, j = i % 3;
-                const int tap = (2 - j) * 3 + dxi;
-                tma_load_2d(s_res + i * C::W_TILE_BYTES, &map_b, res_full, tap * args.Cin + kc * BLOCK_K, 0);
+            if (RESIDENT_KC > 0) {
+                mbar_expect_tx(res_full, C::RES_BYTES);
+                for (int i = 0; i < 9 * RESIDENT_KC; ++i) {           // slot i = (dx, chunk, j): j = 0, 1, 2 <-> dy = +1, 0, -1
+                    const int dxi = i / (3 * RESIDENT_KC), kc = (i / 3) % RESIDENT_KC, j = i % 3;
+                    const int tap = (2 - j) * 3 + dxi;
+                    tma_load_2d(s_res + i * C::W_TILE_BYTES, &map_b, res_full, tap * args.Cin + kc * BLOCK_K, 0);
+                }
             }
             int sa = 0;
             uint32_t pa = 0;
             pdl_wait();            // weights are in flight; the activations are the previous layer's output
+            // Two 43 KiB halo stages hold one load in flight per SM while the other stage computes -- not enough to cover the
+            // HBM latency at this layer's rate (24 GB/s per SM).  The halos of the tiles kPrefetch rounds ahead are therefore
+            // pulled into L2 by TMA prefetches, so the load that fills a freed stage is an L2 hit.
+            const int pf = args.desc_mode >= 16 ? (args.desc_mode >> 4) : 0;
+            auto prefetch_tile = [&](int t2) {
+                if (t2 >= total) return;
+                const TileCoord p = decode_tile(t2, 1, tiles_x, tiles_y, 64, RP_TW, RP_TH);
+                for (int kc = 0; kc < kchunks; ++kc) tma_prefetch_4d(&map_a_halo, kc * BLOCK_K, p.x0 - 1, p.y0 - 1, p.b);
+            };
+            for (int i = 1; i < pf; ++i) prefetch_tile(blockIdx.x + i * gridDim.x);
             for (int t = blockIdx.x; t < total; t += gridDim.x) {
                 const TileCoord tc = decode_tile(t, 1, tiles_x, tiles_y, 64, RP_TW, RP_TH);
+                if (pf) prefetch_tile(t + pf * gridDim.x);
                 for (int kc = 0; kc < kchunks; ++kc) {
                     mbar_wait(&a_empty[sa], pa ^ 1);
                     mbar_expect_tx(&a_full[sa], RP_HALO_BOX_BYTES);
@@ -1336,10 +1498,25 @@ conv_rowpair_kernel(const __grid_constant__ CUtensorMap map_a_halo, const __grid
             constexpr int kPitch = RP_TW + 2;                           // halo row = 10 rows of 128 B
             constexpr int kAUnit = 128 / 16;                            // one 128-byte row in descriptor units
             constexpr int kWUnit = C::W_TILE_BYTES / 16;
-            int sa = 0, acc = 0;
-            uint32_t pa = 0, acc_phase = 0;
-            mbar_wait(res_full, 0);
-            tc_fence_after();
+            int sa = 0, sb = 0, acc = 0;
+            uint32_t pa = 0, pb = 0, acc_phase = 0;
+            if (RESIDENT_KC > 0) {
+                mbar_wait(res_full, 0);
+                tc_fence_after();
+            }
+            // the 16 instructions of one filter column and chunk; a = 0 first: its N = 128 form initialises both halves of a
+            // fresh accumulator
+            auto issue_column = [&](uint32_t d_tmem, uint64_t a_col, uint64_t w0, bool fresh) {
+#pragma unroll
+                for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+                    const uint64_t ar = a_col + (uint64_t)(2 * k);      // + (a + 1) halo rows below
+                    const uint64_t wk = w0 + (uint64_t)(2 * k);
+                    umma_f16(d_tmem, ar + (uint64_t)(1 * kPitch * kAUnit), wk + (uint64_t)kWUnit, idesc128, (k != 0 || !fresh) ? 1u : 0u);
+                    umma_f16(d_tmem, ar + (uint64_t)(2 * kPitch * kAUnit), wk, idesc128, 1u);
+                    umma_f16(d_tmem, ar, wk + (uint64_t)(2 * kWUnit), idesc64, 1u);
+                    umma_f16(d_tmem + 64u, ar + (uint64_t)(3 * kPitch * kAUnit), wk, idesc64, 1u);
+                }
+            };
             for (int t = blockIdx.x; t < total; t += gridDim.x) {
                 mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
                 tc_fence_after();
@@ -1347,28 +1524,36 @@ conv_rowpair_kernel(const __grid_constant__ CUtensorMap map_a_halo, const __grid
                 for (int kc = 0; kc < kchunks; ++kc) {
                     mbar_wait(&a_full[sa], pa);
                     tc_fence_after();
-                    if (elect_one()) {
-                        // row group g of the A operand = halo rows 2g + (a + 1): SBO = two halo rows
-                        const uint64_t a0 = make_smem_desc_sbo(smem_u32(s_a + sa * C::HALO_STAGE_BYTES), 2 * kPitch * 128);
+                    // row group g of the A operand = halo rows 2g + (a + 1): SBO = two halo rows
+                    const uint64_t a0 = make_smem_desc_sbo(smem_u32(s_a + sa * C::HALO_STAGE_BYTES), 2 * kPitch * 128);
+                    if (RESIDENT_KC > 0) {
+                        if (elect_one()) {
+#pragma unroll
+                            for (int dxi = 0; dxi < 3; ++dxi)
+                                issue_column(d_tmem, a0 + (uint64_t)(dxi * kAUnit),
+                                             make_smem_desc(smem_u32(s_res + (dxi * RESIDENT_KC + kc) * 3 * C::W_TILE_BYTES)), dxi == 0 && kc == 0);
+                            umma_commit(&a_empty[sa]);
+                            if (kc == kchunks - 1) umma_commit(&tmem_full[acc]);
+                        }
+                        __syncwarp();
+                    } else {
 #pragma unroll
                         for (int dxi = 0; dxi < 3; ++dxi) {
-                            const uint64_t w0 = make_smem_desc(smem_u32(s_res + (dxi * RESIDENT_KC + kc) * 3 * C::W_TILE_BYTES));
-#pragma unroll
-                            for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-                                const uint64_t ar = a0 + (uint64_t)(dxi * kAUnit + 2 * k);      // + (a + 1) halo rows below
-                                const uint64_t wk = w0 + (uint64_t)(2 * k);
-                                // a = 0 first: the N = 128 instruction initialises both halves of a fresh accumulator
-                                umma_f16(d_tmem, ar + (uint64_t)(1 * kPitch * kAUnit), wk + (uint64_t)kWUnit, idesc128,
-                                         (dxi | k) != 0 ? 1u : (kc != 0 ? 1u : 0u));
-                                umma_f16(d_tmem, ar + (uint64_t)(2 * kPitch * kAUnit), wk, idesc128, 1u);
-                                umma_f16(d_tmem, ar, wk + (uint64_t)(2 * kWUnit), idesc64, 1u);
-                                umma_f16(d_tmem + 64u, ar + (uint64_t)(3 * kPitch * kAUnit), wk, idesc64, 1u);
+                            mbar_wait(&b_full[sb], pb);
+                            tc_fence_after();
+                            if (elect_one()) {
+                                issue_column(d_tmem, a0 + (uint64_t)(dxi * kAUnit), make_smem_desc(smem_u32(s_b + sb * C::B_STAGE_BYTES)),
+                                             dxi == 0 && kc == 0);
+                                umma_commit(&b_empty[sb]);
+                                if (dxi == 2) {
+                                    umma_commit(&a_empty[sa]);
+                                    if (kc == kchunks - 1) umma_commit(&tmem_full[acc]);
+                                }
                             }
+                            __syncwarp();
+                            if (++sb == C::B_STAGES) { sb = 0; pb ^= 1; }
                         }
-                        umma_commit(&a_empty[sa]);
-                        if (kc == kchunks - 1) umma_commit(&tmem_full[acc]);
                     }
-                    __syncwarp();
                     if (++sa == C::A_STAGES) { sa = 0; pa ^= 1; }
                 }
                 if (++acc == 2) { acc = 0; acc_phase ^= 1; }
@@ -1377,7 +1562,6 @@ conv_rowpair_kernel(const __grid_constant__ CUtensorMap map_a_halo, const __grid
     } else {
         // ===================================================================== epilogue (warps 2..5): lane = (row group, px)
         const int quarter = warp & 3;
-        const int gl = lane >> 3, px = lane & 7;
         const uint32_t slab = smem_u32(s_stg + quarter * 8192);
         int acc = 0;
         uint32_t acc_phase = 0;
@@ -1387,75 +1571,7 @@ conv_rowpair_kernel(const __grid_constant__ CUtensorMap map_a_halo, const __grid
             mbar_wait(&tmem_full[acc], acc_phase);
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * 128);
-            if (EPI == EPI_HEAD) {
-#pragma unroll 1
-                for (int half = 0; half < 2; ++half) {
-                    uint32_t r0[32], r1[32];
-                    tmem_ld32(taddr + half * 64, r0);
-                    tmem_ld32(taddr + half * 64 + 32, r1);
-                    tmem_ld_wait();
-                    if (half == 1) {
-                        tc_fence_before();
-                        mbar_arrive(&tmem_empty[acc]);
-                    }
-                    head_pixel(args, s_head, r0, r1, tcd.b, yw + 2 * gl + half, tcd.x0 + px);
-                }
-            } else {
-                uint32_t pk[2][32];
-                const float4* b4 = reinterpret_cast<const float4*>(args.bias);
-#pragma unroll
-                for (int half = 0; half < 2; ++half) {
-                    uint32_t r0[32], r1[32];
-                    tmem_ld32(taddr + half * 64, r0);
-                    tmem_ld32(taddr + half * 64 + 32, r1);
-                    tmem_ld_wait();
-                    if (half == 1) {
-                        tc_fence_before();
-                        mbar_arrive(&tmem_empty[acc]);
-                    }
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        const float4 lo = __ldg(b4 + j), hi = __ldg(b4 + 8 + j);
-                        pk[half][2 * j] = pack_bf16(fmaxf(__uint_as_float(r0[4 * j + 0]) + lo.x, 0.0f), fmaxf(__uint_as_float(r0[4 * j + 1]) + lo.y, 0.0f));
-                        pk[half][2 * j + 1] = pack_bf16(fmaxf(__uint_as_float(r0[4 * j + 2]) + lo.z, 0.0f), fmaxf(__uint_as_float(r0[4 * j + 3]) + lo.w, 0.0f));
-                        pk[half][16 + 2 * j] = pack_bf16(fmaxf(__uint_as_float(r1[4 * j + 0]) + hi.x, 0.0f), fmaxf(__uint_as_float(r1[4 * j + 1]) + hi.y, 0.0f));
-                        pk[half][16 + 2 * j + 1] = pack_bf16(fmaxf(__uint_as_float(r1[4 * j + 2]) + hi.z, 0.0f), fmaxf(__uint_as_float(r1[4 * j + 3]) + hi.w, 0.0f));
-                    }
-                }
-                // the previous TMA store must have finished reading the slab before it is overwritten
-                if (lane == 0) tma_store_wait_read();
-                __syncwarp();
-#pragma unroll
-                for (int half = 0; half < 2; ++half) {
-                    // slab row = (output row inside the warp's 8) * 8 + px; 16-byte chunk j of a row lives at j ^ (row & 7)
-                    const uint32_t row_addr = slab + (uint32_t)(((2 * gl + half) * 8 + px) * 128);
-#pragma unroll
-                    for (int j = 0; j < 8; ++j)
-                        st_shared_v4(row_addr + (uint32_t)((j ^ px) << 4), pk[half][4 * j], pk[half][4 * j + 1], pk[half][4 * j + 2], pk[half][4 * j + 3]);
-                }
-                fence_proxy_async_smem();
-                __syncwarp();
-                if (lane == 0) {
-                    tma_store_4d(&map_out, slab, args.out_coff, tcd.x0, yw, tcd.b);       // box {64 ch, 8 px, 8 rows, 1 image}
-                    tma_store_commit();
-                }
-                if (args.pool) {
-                    // 2 x 2 max-pool: rows (2 gl, 2 gl + 1) are this lane's two halves, the column partner is lane ^ 1.  The even
-                    // lane finishes channels [0, 32), the odd lane [32, 64): each sends the half the other one needs.
-                    const bool odd = lane & 1;
-                    uint32_t res[16];
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) {
-                        const uint32_t lo = max_bf16x2(pk[0][i], pk[1][i]), hi = max_bf16x2(pk[0][16 + i], pk[1][16 + i]);
-                        const uint32_t got = __shfl_xor_sync(0xFFFFFFFFu, odd ? lo : hi, 1);
-                        res[i] = max_bf16x2(odd ? hi : lo, got);
-                    }
-                    uint4* dst = reinterpret_cast<uint4*>(args.pool + (((size_t)tcd.b * (args.H / 2) + ((yw >> 1) + gl)) * (args.W / 2) +
-                                                                       ((tcd.x0 + px) >> 1)) * args.pool_cstride + (odd ? 32 : 0));
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) dst[i] = make_uint4(res[4 * i], res[4 * i + 1], res[4 * i + 2], res[4 * i + 3]);
-                }
-            }
+            rowpair_epilogue_tile<EPI, false>(args, &map_out, s_head, s_bias, taddr, slab, tcd, yw, lane, &tmem_empty[acc], 0u);
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
         if (EPI != EPI_HEAD && lane == 0) tma_store_wait_read();
@@ -1466,6 +1582,229 @@ conv_rowpair_kernel(const __grid_constant__ CUtensorMap map_a_halo, const __grid
     if (warp == 1) {
         __syncwarp();
         tmem_dealloc_warp(tmem_base, C::TMEM_COLS);
+    }
+}
+
+
+// ==================================================================================== kernel 6
+// cta_group::2 form of the row-pair kernel.  Kernel 5 is not bound by the MMA rate but by SHARED-MEMORY BANDWIDTH: an M = 128
+// instruction reads 4 KiB of A and N x 32 B of B, so at N <= 128 the operand fetch (6 - 8 KiB per instruction against
+// ~128 B / cycle) takes as long as the math, and the halo writes and the epilogue's staging traffic come on top
+// (tools/microbench/mma_rowpair*.cu: 63 cycles per instruction of the mix with idle shared memory, ~95 inside the kernel).
+// As a CTA pair (M = 256: each CTA its own 8 x 32-pixel tile) every CTA supplies only HALF of each B operand: per filter
+// column and K-slice a CTA reads 4 x 4 KiB of A + (2 + 2 + 1 + 1) KiB of B = 22 KiB instead of 28.  The B halves fall out of
+// the column layout for free: for the N = 128 instructions CTA 0 holds the tile of the even output row and CTA 1 that of the
+// odd row ([W(0) ; W(-1)] and [W(+1) ; W(0)] are split exactly there); for the N = 64 instructions each CTA holds 32 of the
+// 64 output channels.  Per (filter column, chunk) a CTA stores S0 | S1 | S2 | S3 = 8 + 8 + 4 + 4 KiB:
+//     CTA 0: W(+1) | W(0)  | W(-1)[0:32]  | W(+1)[0:32]        CTA 1: W(0) | W(-1) | W(-1)[32:64] | W(+1)[32:64]
+//     a = +1 reads S0 (N = 128), a = 0 reads S1 (N = 128), a = -1 reads S2 (N = 64), a = +2 reads S3 (N = 64, columns [64, 128)).
+// Pipeline, barriers and the remote "accumulator drained" arrive are those of kernel 3.
+template <int EPI, int RESIDENT_KC>
+struct RowPair2Cfg {
+    static constexpr int HALO_STAGE_BYTES = (RP_HALO_BOX_BYTES + 1023) / 1024 * 1024;
+    static constexpr int COL_BYTES = 3 * 64 * BLOCK_K * 2;               // S0 | S1 | S2 | S3 of one filter column and chunk: 24 KiB
+    static constexpr int RES_BYTES = 3 * RESIDENT_KC * COL_BYTES;
+    static constexpr int B_STAGES = RESIDENT_KC > 0 ? 0 : 3;
+    static constexpr int STG_BYTES = EPI == EPI_HEAD ? 0 : 4 * 8192;
+    static constexpr int A_STAGES = EPI == EPI_HEAD ? 3 : 2;
+    static constexpr int TMEM_COLS = 256;
+    static constexpr int SMEM_BYTES = RES_BYTES + B_STAGES * COL_BYTES + A_STAGES * HALO_STAGE_BYTES + STG_BYTES + 4096 + 1024;
+    static_assert(SMEM_BYTES <= 227 * 1024, "row-pair pair kernel: shared memory");
+};
+
+template <int EPI, int RESIDENT_KC>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(HALO2_THREADS, 1)
+conv_rowpair2_kernel(const __grid_constant__ CUtensorMap map_a_halo, const __grid_constant__ CUtensorMap map_b64,
+                     const __grid_constant__ CUtensorMap map_b32, const __grid_constant__ CUtensorMap map_out, const ConvArgs args) {
+    using C = RowPair2Cfg<EPI, RESIDENT_KC>;
+    static_assert(EPI == EPI_STORE || EPI == EPI_HEAD, "row-pair kernel: conv3x3 layers only");
+    extern __shared__ uint8_t smem_raw[];
+    // identical carve-up in both CTAs: the UMMA descriptors and multicast barrier addresses are CTA-relative offsets
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* s_res = smem;
+    uint8_t* s_b = smem + C::RES_BYTES;
+    uint8_t* s_a = s_b + C::B_STAGES * C::COL_BYTES;
+    uint8_t* s_stg = s_a + C::A_STAGES * C::HALO_STAGE_BYTES;
+    uint8_t* aux = s_stg + C::STG_BYTES;
+    uint64_t* a_full = reinterpret_cast<uint64_t*>(aux);
+    uint64_t* a_empty = a_full + 4;
+    uint64_t* b_full = a_empty + 4;
+    uint64_t* b_empty = b_full + 4;
+    uint64_t* res_full = b_empty + 4;
+    uint64_t* tmem_full = res_full + 1;
+    uint64_t* tmem_empty = tmem_full + 2;
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+    float* s_head = reinterpret_cast<float*>(aux + 512);
+    float* s_bias = reinterpret_cast<float*>(aux + 3072);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const bool leader = rank == 0;
+    const int pair_id = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
+    const int tiles_x = args.W / RP_TW, tiles_y = args.H / RP_TH;
+    const int total_pairs = (args.batch * tiles_y * tiles_x) >> 1;    // tiles 2p, 2p + 1 are neighbours in x (even tile count)
+    const int kchunks = args.Cin / BLOCK_K;
+
+    if (threadIdx.x == 0) {
+        prefetch_tmap(&map_a_halo);
+        prefetch_tmap(&map_b64);
+        prefetch_tmap(&map_b32);
+        if (EPI != EPI_HEAD) prefetch_tmap(&map_out);
+        for (int i = 0; i < 4; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
+        mbar_init(res_full, 1);
+        for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 256); }
+        fence_barrier_init();
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)), "r"((uint32_t)C::TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    if (EPI == EPI_HEAD) {
+        for (int i = threadIdx.x; i < args.n_classes * 64 + args.n_classes; i += HALO2_THREADS)
+            s_head[i] = i < args.n_classes * 64 ? args.head_w[i] : args.head_b[i - args.n_classes * 64];
+    }
+    if (threadIdx.x < 64) s_bias[threadIdx.x] = args.bias[threadIdx.x];
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();          // barrier inits of both CTAs are visible before any remote arrive / TMA signal
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
+    pdl_launch_dependents();
+
+    // this CTA's share of one filter column's weights: S0 | S1 | S2 | S3 (dy index j: 0, 1, 2 <-> dy = +1, 0, -1; tap = (2 - j) * 3 + dxi)
+    auto load_column = [&](uint8_t* dst, uint64_t* bar, int dxi, int kc) {
+        const int r = (int)rank, k0 = kc * BLOCK_K;
+        tma2_load_2d(dst, &map_b64, bar, ((2 - r) * 3 + dxi) * args.Cin + k0, 0);                    // S0: j = r
+        tma2_load_2d(dst + 8192, &map_b64, bar, ((1 - r) * 3 + dxi) * args.Cin + k0, 0);             // S1: j = 1 + r
+        tma2_load_2d(dst + 16384, &map_b32, bar, (0 * 3 + dxi) * args.Cin + k0, 32 * r);             // S2: W(-1), channels 32 r ..
+        tma2_load_2d(dst + 20480, &map_b32, bar, (2 * 3 + dxi) * args.Cin + k0, 32 * r);             // S3: W(+1), channels 32 r ..
+    };
+
+    if (warp == 0) {
+        // ===================================================================== TMA producer (both CTAs)
+        if (lane == 0 && pair_id < total_pairs) {
+            if (RESIDENT_KC > 0) {
+                if (leader) mbar_expect_tx(res_full, 2 * C::RES_BYTES);
+                for (int i = 0; i < 3 * RESIDENT_KC; ++i) load_column(s_res + i * C::COL_BYTES, res_full, i / RESIDENT_KC, i % RESIDENT_KC);
+            }
+            int sa = 0;
+            uint32_t pa = 0;
+            pdl_wait();            // weights are in flight; the activations are the previous layer's output
+            for (int p = pair_id; p < total_pairs; p += n_pairs) {
+                const TileCoord tc = decode_tile(2 * p + (int)rank, 1, tiles_x, tiles_y, 64, RP_TW, RP_TH);
+                for (int kc = 0; kc < kchunks; ++kc) {
+                    mbar_wait(&a_empty[sa], pa ^ 1);
+                    if (leader) mbar_expect_tx(&a_full[sa], 2 * RP_HALO_BOX_BYTES);
+                    tma2_load_4d(s_a + sa * C::HALO_STAGE_BYTES, &map_a_halo, &a_full[sa], kc * BLOCK_K, tc.x0 - 1, tc.y0 - 1, tc.b);
+                    if (++sa == C::A_STAGES) { sa = 0; pa ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 6) {
+        // ===================================================================== weight producer (streaming mode, both CTAs)
+        if (RESIDENT_KC == 0 && lane == 0 && pair_id < total_pairs) {
+            int sb = 0;
+            uint32_t pb = 0;
+            for (int p = pair_id; p < total_pairs; p += n_pairs)
+                for (int kc = 0; kc < kchunks; ++kc)
+                    for (int dxi = 0; dxi < 3; ++dxi) {
+                        mbar_wait(&b_empty[sb], pb ^ 1);
+                        if (leader) mbar_expect_tx(&b_full[sb], 2 * C::COL_BYTES);
+                        load_column(s_b + sb * C::COL_BYTES, &b_full[sb], dxi, kc);
+                        if (++sb == C::B_STAGES) { sb = 0; pb ^= 1; }
+                    }
+        }
+    } else if (warp == 1) {
+        // ===================================================================== MMA issuer (leader CTA only)
+        if (leader && pair_id < total_pairs) {
+            constexpr uint32_t idesc128 = make_idesc_m256(128), idesc64 = make_idesc_m256(64);
+            constexpr int kPitch = RP_TW + 2;
+            constexpr int kAUnit = 128 / 16;
+            int sa = 0, sb = 0, acc = 0;
+            uint32_t pa = 0, pb = 0, acc_phase = 0;
+            if (RESIDENT_KC > 0) {
+                mbar_wait(res_full, 0);
+                tc_fence_after();
+            }
+            // the 16 instructions of one filter column and chunk; a = 0 first: its N = 128 form initialises both halves of a
+            // fresh accumulator
+            auto issue_column = [&](uint32_t d_tmem, uint64_t a_col, uint64_t w0, bool fresh) {
+#pragma unroll
+                for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+                    const uint64_t ar = a_col + (uint64_t)(2 * k);      // + (a + 1) halo rows below
+                    const uint64_t wk = w0 + (uint64_t)(2 * k);
+                    umma2_f16(d_tmem, ar + (uint64_t)(1 * kPitch * kAUnit), wk + (uint64_t)(8192 / 16), idesc128, (k != 0 || !fresh) ? 1u : 0u);
+                    umma2_f16(d_tmem, ar + (uint64_t)(2 * kPitch * kAUnit), wk, idesc128, 1u);
+                    umma2_f16(d_tmem, ar, wk + (uint64_t)(16384 / 16), idesc64, 1u);
+                    umma2_f16(d_tmem + 64u, ar + (uint64_t)(3 * kPitch * kAUnit), wk + (uint64_t)(20480 / 16), idesc64, 1u);
+                }
+            };
+            for (int p = pair_id; p < total_pairs; p += n_pairs) {
+                mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * 128);
+                for (int kc = 0; kc < kchunks; ++kc) {
+                    mbar_wait(&a_full[sa], pa);
+                    tc_fence_after();
+                    const uint64_t a0 = make_smem_desc_sbo(smem_u32(s_a + sa * C::HALO_STAGE_BYTES), 2 * kPitch * 128);
+                    if (RESIDENT_KC > 0) {
+                        if (elect_one()) {
+#pragma unroll
+                            for (int dxi = 0; dxi < 3; ++dxi)
+                                issue_column(d_tmem, a0 + (uint64_t)(dxi * kAUnit),
+                                             make_smem_desc(smem_u32(s_res + (dxi * RESIDENT_KC + kc) * C::COL_BYTES)), dxi == 0 && kc == 0);
+                            umma2_commit_mc(&a_empty[sa]);
+                            if (kc == kchunks - 1) umma2_commit_mc(&tmem_full[acc]);
+                        }
+                        __syncwarp();
+                    } else {
+#pragma unroll
+                        for (int dxi = 0; dxi < 3; ++dxi) {
+                            mbar_wait(&b_full[sb], pb);
+                            tc_fence_after();
+                            if (elect_one()) {
+                                issue_column(d_tmem, a0 + (uint64_t)(dxi * kAUnit), make_smem_desc(smem_u32(s_b + sb * C::COL_BYTES)),
+                                             dxi == 0 && kc == 0);
+                                umma2_commit_mc(&b_empty[sb]);
+                                if (dxi == 2) {
+                                    umma2_commit_mc(&a_empty[sa]);
+                                    if (kc == kchunks - 1) umma2_commit_mc(&tmem_full[acc]);
+                                }
+                            }
+                            __syncwarp();
+                            if (++sb == C::B_STAGES) { sb = 0; pb ^= 1; }
+                        }
+                    }
+                    if (++sa == C::A_STAGES) { sa = 0; pa ^= 1; }
+                }
+                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            }
+        }
+    } else {
+        // ===================================================================== epilogue (both CTAs, own tile)
+        const int quarter = warp & 3;
+        const uint32_t slab = smem_u32(s_stg + quarter * 8192);
+        const uint32_t empty0 = mapa_rank(smem_u32(&tmem_empty[0]), 0), empty1 = mapa_rank(smem_u32(&tmem_empty[1]), 0);
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        for (int p = pair_id; p < total_pairs; p += n_pairs) {
+            const TileCoord tcd = decode_tile(2 * p + (int)rank, 1, tiles_x, tiles_y, 64, RP_TW, RP_TH);
+            const int yw = tcd.y0 + quarter * 8;
+            mbar_wait(&tmem_full[acc], acc_phase);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * 128);
+            rowpair_epilogue_tile<EPI, true>(args, &map_out, s_head, s_bias, taddr, slab, tcd, yw, lane, nullptr, acc ? empty1 : empty0);
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+        if (EPI != EPI_HEAD && lane == 0) tma_store_wait_read();
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();          // neither CTA may free TMEM / exit while its partner can still touch it
+    if (warp == 1) {
+        __syncwarp();
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)C::TMEM_COLS) : "memory");
     }
 }
 
