@@ -290,7 +290,8 @@ void launch_rowpair(const UNetLayer& L, const tc::ConvArgs& a, int sm_count, cud
     set_max_dynamic_smem(tc::conv_rowpair_kernel<EPI, RKC>, C::SMEM_BYTES);
     const int total = a.batch * (a.H / tc::RP_TH) * (a.W / tc::RP_TW);
     const int grid = std::min(total, sm_count);
-    launch_kernel(tc::conv_rowpair_kernel<EPI, RKC>, dim3(grid), dim3(C::THREADS), C::SMEM_BYTES, st, true, L.map_a_row, L.map_b, L.map_out, a);
+    launch_kernel(tc::conv_rowpair_kernel<EPI, RKC>, dim3(grid), dim3(C::THREADS), C::SMEM_BYTES, st, true, L.map_a_row, L.map_b, L.map_out,
+                  L.map_pool, a);
     MS_LAUNCH_CHECK();
 }
 
@@ -301,7 +302,7 @@ void launch_rowpair2(const UNetLayer& L, const tc::ConvArgs& a, int sm_count, cu
     const int pairs = a.batch * (a.H / tc::RP_TH) * (a.W / tc::RP_TW) / 2;
     const int grid = 2 * std::min(pairs, sm_count / 2);
     launch_kernel(tc::conv_rowpair2_kernel<EPI, RKC>, dim3(grid), dim3(tc::HALO2_THREADS), C::SMEM_BYTES, st, true, L.map_a_row, L.map_b,
-                  L.map_b_half, L.map_out, a);
+                  L.map_b_half, L.map_out, L.map_pool, a);
     MS_LAUNCH_CHECK();
 }
 
@@ -543,6 +544,9 @@ void UNet::load(const std::string& blob_path, int net_h, int net_w, int n_classe
         if (dst >= 0 && L.halo >= 3) make_rowpair_out_map(&L.map_out, bufs_[dst].p, max_batch, h, w, bufs_[dst].C);
         else if (dst >= 0) make_out_map(&L.map_out, bufs_[dst].p, max_batch, h, w, bufs_[dst].C, L.halo ? tc::HALO_TW : tc::TILE_W);
         else L.map_out = L.map_b;  // head layer: no bf16 output
+        L.map_pool = L.map_out;
+        if (L.halo >= 3 && pool_dst >= 0)      // pooled map of the row-pair kernels: box {64 ch, 4 px, 4 rows} = one epilogue warp's share
+            make_act_map(&L.map_pool, bufs_[pool_dst].p, max_batch, h / 2, w / 2, bufs_[pool_dst].C, 4, 4);
         flops_ += L.flops_per_slice;
         layers_.push_back(L);
     };

@@ -25,6 +25,7 @@ struct UNetLayer {
     CUtensorMap map_b_half_alt;  // same for the small-batch tiling (block_n_alt / 2 rows)
     int block_n_alt = 0;         // 0 = none; 128 = deep layers switch to 128-wide N tiles when 256-wide ones cannot fill a wave
     CUtensorMap map_out;         // TMA store of the epilogue (one epilogue warp's 32-pixel x 64-channel slab)
+    CUtensorMap map_pool;        // row-pair kernels: TMA store of the fused 2x2 max-pool
     CUtensorMap map_a_row;       // halo kernel: box {64 ch, 10 px, 18 rows}
     bool convt_pair = false;     // ConvT: cta_group::2 GEMM (convt_pair_kernel) with map_a_row = {64 ch, 8 px, 16 rows} tiles
     int halo = 0;                // 0 = per-tap streaming kernel, 1 = halo-stationary kernel, 2 = its cta_group::2 version, 3 = row-pair kernel, 4 = row-pair cta_group::2

@@ -87,8 +87,12 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
+// "Accumulator drained" arrive of an epilogue thread.  Relaxed: what it orders (this thread's tcgen05.ld before the next MMA
+// into the accumulator) is carried by tcgen05.wait::ld + tcgen05.fence::before_thread_sync here and fence::after_thread_sync
+// behind the issuer's wait.  The default .release compiled to a MEMBAR.ALL.CTA in front of every arrive, which waits for the
+// thread's outstanding GLOBAL stores (previous tile's mask / pooled pixels) -- the top stall of the epilogue warps in ncu.
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+    asm volatile("mbarrier.arrive.relaxed.cta.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
     uint32_t ok;
@@ -798,7 +802,7 @@ __device__ __forceinline__ uint32_t mapa_rank(uint32_t smem_addr, uint32_t rank)
 // leader's wait, so the arrive itself needs no cluster-scope release: `.release.cluster` compiled to MEMBAR.ALL + ERRBAR in
 // front of every arrive and was ~45 % of the epilogue warps' stall samples (profiles/r2_ncu_rowpair2_before.txt).
 __device__ __forceinline__ void mbar_arrive_cluster_fwd(uint32_t cluster_addr) {
-    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+    asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 constexpr int HALO2_THREADS = 224;   // warps 0/1 producer + MMA, 2..5 epilogue, 6 weight-tile producer (streaming mode)
 constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;   // clears the CTA-rank bit of a shared::cluster address -> CTA 0 of the pair
@@ -1233,7 +1237,7 @@ struct RowPairCfg {
     static constexpr int B_STAGES = RESIDENT_KC > 0 ? 0 : 3;
     // one 4 KiB staging slab per epilogue warp (the four rows of one parity; none for the head, which stores no feature map)
     // two 4 KiB staging slabs per epilogue warp (the four rows of each parity; none for the head, which stores no feature map)
-    static constexpr int STG_BYTES = EPI == EPI_HEAD ? 0 : 4 * 8192;
+    static constexpr int STG_BYTES = EPI == EPI_HEAD ? 0 : 4 * 10240;   // per warp: two 4 KiB row slabs + a 2 KiB pooled slab
     // halo stages: two where the slabs take 32 KiB (a third stage measured no faster: the loads are not the bound)
     static constexpr int A_STAGES = EPI == EPI_HEAD ? 3 : 2;
     static constexpr int TMEM_COLS = 256;                                // two accumulators of 128 columns
@@ -1312,7 +1316,8 @@ __device__ __forceinline__ void head_pixel_f(const ConvArgs& args, const float* 
 // the accumulator handed back before any math, the bias from shared memory, one slab per row parity (the wait for the
 // previous tile's TMA stores is long satisfied), one proxy fence and both stores issued together.
 template <int EPI, bool REMOTE>
-__device__ __forceinline__ void rowpair_epilogue_tile(const ConvArgs& args, const CUtensorMap* map_out, const float* s_head, const float* s_bias,
+__device__ __forceinline__ void rowpair_epilogue_tile(const ConvArgs& args, const CUtensorMap* map_out, const CUtensorMap* map_pool,
+                                                      const float* s_head, const float* s_bias,
                                                       uint32_t taddr, uint32_t slab, const TileCoord& tcd, int yw, int lane,
                                                       uint64_t* tmem_empty_bar, uint32_t remote_empty) {
     const int gl = lane >> 3, px = lane & 7;
@@ -1352,7 +1357,19 @@ __device__ __forceinline__ void rowpair_epilogue_tile(const ConvArgs& args, cons
             pk[half][2 * j] = pack_bf16(fmaxf(__uint_as_float(q[0]) + bb.x, 0.0f), fmaxf(__uint_as_float(q[1]) + bb.y, 0.0f));
             pk[half][2 * j + 1] = pack_bf16(fmaxf(__uint_as_float(q[2]) + bb.z, 0.0f), fmaxf(__uint_as_float(q[3]) + bb.w, 0.0f));
         }
-    // the previous tile's TMA stores must have finished reading the two slabs
+    // 2 x 2 max-pool in registers: rows (2 gl, 2 gl + 1) are this lane's two halves, the column partner is lane ^ 1.  The even
+    // lane finishes channels [0, 32), the odd lane [32, 64): each sends the half the other one needs.
+    const bool odd = lane & 1;
+    uint32_t res[16];
+    if (args.pool) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            const uint32_t lo = max_bf16x2(pk[0][i], pk[1][i]), hi = max_bf16x2(pk[0][16 + i], pk[1][16 + i]);
+            const uint32_t got = __shfl_xor_sync(0xFFFFFFFFu, odd ? lo : hi, 1);
+            res[i] = max_bf16x2(odd ? hi : lo, got);
+        }
+    }
+    // the previous tile's TMA stores must have finished reading the slabs
     if (lane == 0) tma_store_wait_read();
     __syncwarp();
 #pragma unroll
@@ -1363,36 +1380,31 @@ __device__ __forceinline__ void rowpair_epilogue_tile(const ConvArgs& args, cons
         for (int j = 0; j < 8; ++j)
             st_shared_v4(row_addr + (uint32_t)((j ^ px) << 4), pk[half][4 * j], pk[half][4 * j + 1], pk[half][4 * j + 2], pk[half][4 * j + 3]);
     }
+    if (args.pool) {
+        // pooled slab (2 KiB behind the two row slabs): row = gl * 4 + px / 2, this lane's four 16-byte chunks.  The pooled map
+        // leaves through TMA like the rest: a generic st.global here would still be in flight at the NEXT tile's proxy fence
+        // (MEMBAR.ALL.CTA), which then waits out an HBM write latency per tile.
+        const int prow = gl * 4 + (px >> 1);
+        const uint32_t paddr = slab + 8192u + (uint32_t)(prow * 128);
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+            st_shared_v4(paddr + (uint32_t)((((odd ? 4 : 0) + i) ^ (prow & 7)) << 4), res[4 * i], res[4 * i + 1], res[4 * i + 2], res[4 * i + 3]);
+    }
     fence_proxy_async_smem();
     __syncwarp();
     if (lane == 0) {
         // destination viewed as (C, W, row parity, H / 2, B): box {64 ch, 8 px, 1, 4 row pairs, 1} = rows yw + half + 2 g
         tma_store_5d(map_out, slab, args.out_coff, tcd.x0, 0, yw >> 1, tcd.b);
         tma_store_5d(map_out, slab + 4096u, args.out_coff, tcd.x0, 1, yw >> 1, tcd.b);
+        if (args.pool) tma_store_4d(map_pool, slab + 8192u, 0, tcd.x0 >> 1, yw >> 1, tcd.b);   // box {64 ch, 4 px, 4 rows, 1}
         tma_store_commit();
-    }
-    if (args.pool) {
-        // 2 x 2 max-pool: rows (2 gl, 2 gl + 1) are this lane's two halves, the column partner is lane ^ 1.  The even
-        // lane finishes channels [0, 32), the odd lane [32, 64): each sends the half the other one needs.
-        const bool odd = lane & 1;
-        uint32_t res[16];
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-            const uint32_t lo = max_bf16x2(pk[0][i], pk[1][i]), hi = max_bf16x2(pk[0][16 + i], pk[1][16 + i]);
-            const uint32_t got = __shfl_xor_sync(0xFFFFFFFFu, odd ? lo : hi, 1);
-            res[i] = max_bf16x2(odd ? hi : lo, got);
-        }
-        uint4* dst = reinterpret_cast<uint4*>(args.pool + (((size_t)tcd.b * (args.H / 2) + ((yw >> 1) + gl)) * (args.W / 2) +
-                                                           ((tcd.x0 + px) >> 1)) * args.pool_cstride + (odd ? 32 : 0));
-#pragma unroll
-        for (int i = 0; i < 4; ++i) dst[i] = make_uint4(res[4 * i], res[4 * i + 1], res[4 * i + 2], res[4 * i + 3]);
     }
 }
 
 template <int EPI, int RESIDENT_KC>
 __global__ void __launch_bounds__(RowPairCfg<EPI, RESIDENT_KC>::THREADS, 1)
 conv_rowpair_kernel(const __grid_constant__ CUtensorMap map_a_halo, const __grid_constant__ CUtensorMap map_b,
-                    const __grid_constant__ CUtensorMap map_out, const ConvArgs args) {
+                    const __grid_constant__ CUtensorMap map_out, const __grid_constant__ CUtensorMap map_pool, const ConvArgs args) {
     using C = RowPairCfg<EPI, RESIDENT_KC>;
     static_assert(EPI == EPI_STORE || EPI == EPI_HEAD, "row-pair kernel: conv3x3 layers only");
     extern __shared__ uint8_t smem_raw[];
@@ -1421,7 +1433,7 @@ conv_rowpair_kernel(const __grid_constant__ CUtensorMap map_a_halo, const __grid
     if (threadIdx.x == 0) {
         prefetch_tmap(&map_a_halo);
         prefetch_tmap(&map_b);
-        if (EPI != EPI_HEAD) prefetch_tmap(&map_out);
+        if (EPI != EPI_HEAD) { prefetch_tmap(&map_out); prefetch_tmap(&map_pool); }
         for (int i = 0; i < C::A_STAGES; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
         for (int i = 0; i < 4; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
         mbar_init(res_full, 1);
@@ -1562,7 +1574,7 @@ conv_rowpair_kernel(const __grid_constant__ CUtensorMap map_a_halo, const __grid
     } else {
         // ===================================================================== epilogue (warps 2..5): lane = (row group, px)
         const int quarter = warp & 3;
-        const uint32_t slab = smem_u32(s_stg + quarter * 8192);
+        const uint32_t slab = smem_u32(s_stg + quarter * 10240);
         int acc = 0;
         uint32_t acc_phase = 0;
         for (int t = blockIdx.x; t < total; t += gridDim.x) {
@@ -1571,7 +1583,7 @@ conv_rowpair_kernel(const __grid_constant__ CUtensorMap map_a_halo, const __grid
             mbar_wait(&tmem_full[acc], acc_phase);
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * 128);
-            rowpair_epilogue_tile<EPI, false>(args, &map_out, s_head, s_bias, taddr, slab, tcd, yw, lane, &tmem_empty[acc], 0u);
+            rowpair_epilogue_tile<EPI, false>(args, &map_out, &map_pool, s_head, s_bias, taddr, slab, tcd, yw, lane, &tmem_empty[acc], 0u);
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
         if (EPI != EPI_HEAD && lane == 0) tma_store_wait_read();
@@ -1605,7 +1617,7 @@ struct RowPair2Cfg {
     static constexpr int COL_BYTES = 3 * 64 * BLOCK_K * 2;               // S0 | S1 | S2 | S3 of one filter column and chunk: 24 KiB
     static constexpr int RES_BYTES = 3 * RESIDENT_KC * COL_BYTES;
     static constexpr int B_STAGES = RESIDENT_KC > 0 ? 0 : 3;
-    static constexpr int STG_BYTES = EPI == EPI_HEAD ? 0 : 4 * 8192;
+    static constexpr int STG_BYTES = EPI == EPI_HEAD ? 0 : 4 * 10240;   // per warp: two 4 KiB row slabs + a 2 KiB pooled slab
     static constexpr int A_STAGES = EPI == EPI_HEAD ? 3 : 2;
     static constexpr int TMEM_COLS = 256;
     static constexpr int SMEM_BYTES = RES_BYTES + B_STAGES * COL_BYTES + A_STAGES * HALO_STAGE_BYTES + STG_BYTES + 4096 + 1024;
@@ -1615,7 +1627,8 @@ struct RowPair2Cfg {
 template <int EPI, int RESIDENT_KC>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(HALO2_THREADS, 1)
 conv_rowpair2_kernel(const __grid_constant__ CUtensorMap map_a_halo, const __grid_constant__ CUtensorMap map_b64,
-                     const __grid_constant__ CUtensorMap map_b32, const __grid_constant__ CUtensorMap map_out, const ConvArgs args) {
+                     const __grid_constant__ CUtensorMap map_b32, const __grid_constant__ CUtensorMap map_out,
+                     const __grid_constant__ CUtensorMap map_pool, const ConvArgs args) {
     using C = RowPair2Cfg<EPI, RESIDENT_KC>;
     static_assert(EPI == EPI_STORE || EPI == EPI_HEAD, "row-pair kernel: conv3x3 layers only");
     extern __shared__ uint8_t smem_raw[];
@@ -1649,7 +1662,7 @@ conv_rowpair2_kernel(const __grid_constant__ CUtensorMap map_a_halo, const __gri
         prefetch_tmap(&map_a_halo);
         prefetch_tmap(&map_b64);
         prefetch_tmap(&map_b32);
-        if (EPI != EPI_HEAD) prefetch_tmap(&map_out);
+        if (EPI != EPI_HEAD) { prefetch_tmap(&map_out); prefetch_tmap(&map_pool); }
         for (int i = 0; i < 4; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
         mbar_init(res_full, 1);
         for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 256); }
@@ -1783,7 +1796,7 @@ conv_rowpair2_kernel(const __grid_constant__ CUtensorMap map_a_halo, const __gri
     } else {
         // ===================================================================== epilogue (both CTAs, own tile)
         const int quarter = warp & 3;
-        const uint32_t slab = smem_u32(s_stg + quarter * 8192);
+        const uint32_t slab = smem_u32(s_stg + quarter * 10240);
         const uint32_t empty0 = mapa_rank(smem_u32(&tmem_empty[0]), 0), empty1 = mapa_rank(smem_u32(&tmem_empty[1]), 0);
         int acc = 0;
         uint32_t acc_phase = 0;
@@ -1793,7 +1806,7 @@ conv_rowpair2_kernel(const __grid_constant__ CUtensorMap map_a_halo, const __gri
             mbar_wait(&tmem_full[acc], acc_phase);
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * 128);
-            rowpair_epilogue_tile<EPI, true>(args, &map_out, s_head, s_bias, taddr, slab, tcd, yw, lane, nullptr, acc ? empty1 : empty0);
+            rowpair_epilogue_tile<EPI, true>(args, &map_out, &map_pool, s_head, s_bias, taddr, slab, tcd, yw, lane, nullptr, acc ? empty1 : empty0);
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
         if (EPI != EPI_HEAD && lane == 0) tma_store_wait_read();
