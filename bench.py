@@ -396,7 +396,7 @@ def run_ours(args, rank, world, local):
     fwd_tflops = eng.info.flops_per_slice * B / (fwd_ms / 1e3) / 1e12
     # DRAM bytes from the committed `ncu --set full` capture of one forward pass at this batch (tools/forward_once.py)
     traffic, traffic_all, traffic_src = None, None, None
-    prof = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r1_ncu_full_forward_b32.json")
+    prof = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r2_ncu_full_forward_b32.json")
     if os.path.exists(prof):
         with open(prof) as f:
             pj = json.load(f)
@@ -404,7 +404,7 @@ def run_ours(args, rank, world, local):
             per_layer = [l["dram_read_bytes"] + l["dram_write_bytes"] for l in pj["layers"]]
             traffic = sum(b for b, k in zip(per_layer, kernels) if k == dominant["kernel"])
             traffic_all = pj["tcgen05_dram_bytes"]
-            traffic_src = "profiles/r1_ncu_full_forward_b32.json: dram__bytes_read.sum + dram__bytes_write.sum per launch, summed over this kernel's launches of one step"
+            traffic_src = "profiles/r2_ncu_full_forward_b32.json: dram__bytes_read.sum + dram__bytes_write.sum per launch, summed over this kernel's launches of one step"
     roofline = {"bound": "tensor", "kernel": dominant["kernel"], "launches_per_step": dominant["launches"],
                 "achieved": dominant["achieved"], "peak": sustained, "unit": "TFLOP/s", "frac": dominant["achieved"] / sustained,
                 "traffic": traffic, "traffic_source": traffic_src,
