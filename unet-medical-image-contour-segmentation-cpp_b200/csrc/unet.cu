@@ -47,9 +47,9 @@ __device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
     return d;
 }
 
-constexpr int kFirstRows = 8;   // image rows per block: the weights-to-registers prologue and the halo rows are amortised
-
-template <bool VEC16>
+// kFirstRows = image rows per block: 8 amortises the weights-to-registers prologue and the halo rows (batch >= ~5); 2 gives a
+// single slice 256 blocks instead of 64 (batch-1 latency: 29 -> ~12 us)
+template <bool VEC16, int kFirstRows>
 __global__ void __launch_bounds__(256) first_conv_kernel(const uint8_t* __restrict__ in, int H, int W,
                                                           const float* __restrict__ w /*[64][9]*/, const float* __restrict__ bias,
                                                           __nv_bfloat16* __restrict__ out /*NHWC 64*/) {
@@ -638,16 +638,17 @@ void UNet::run_layer(int li, const uint8_t* d_in_u8, int batch, uint8_t* d_mask,
     const UNetLayer& L = layers_[li];
     const int h = H_ >> L.level, w = W_ >> L.level;
     if (L.kind == 0) {
-        const unsigned grid = (unsigned)(batch * h / kFirstRows);
-        const size_t smem = (kFirstRows + 2) * (w + 2) * sizeof(float);
+        const bool small = batch * (h / 8) < 2 * sm_count_ && h % 2 == 0;     // fewer than two waves of 8-row blocks
+        const int rows = small ? 2 : 8;
+        const unsigned grid = (unsigned)(batch * h / rows);
+        const size_t smem = (size_t)(rows + 2) * (w + 2) * sizeof(float);
         MS_REQUIRE(smem <= 200 * 1024, MS_ERR_ARG, "network width too large for the first-conv row buffer");
-        if (w % 16 == 0 && (reinterpret_cast<uintptr_t>(d_in_u8) & 15) == 0) {
-            if (smem > 48 * 1024) set_max_dynamic_smem(first_conv_kernel<true>, 200 * 1024);   // nets wider than ~1200 px
-            launch_kernel(first_conv_kernel<true>, dim3(grid), dim3(256), smem, st, true, d_in_u8, h, w, (const float*)L.w_f32, (const float*)L.bias, bufs_[L.dst].p);
-        } else {
-            if (smem > 48 * 1024) set_max_dynamic_smem(first_conv_kernel<false>, 200 * 1024);
-            launch_kernel(first_conv_kernel<false>, dim3(grid), dim3(256), smem, st, true, d_in_u8, h, w, (const float*)L.w_f32, (const float*)L.bias, bufs_[L.dst].p);
-        }
+        auto go = [&](auto kernel) {
+            if (smem > 48 * 1024) set_max_dynamic_smem(kernel, 200 * 1024);   // nets wider than ~1200 px
+            launch_kernel(kernel, dim3(grid), dim3(256), smem, st, true, d_in_u8, h, w, (const float*)L.w_f32, (const float*)L.bias, bufs_[L.dst].p);
+        };
+        if (w % 16 == 0 && (reinterpret_cast<uintptr_t>(d_in_u8) & 15) == 0) { if (small) go(first_conv_kernel<true, 2>); else go(first_conv_kernel<true, 8>); }
+        else { if (small) go(first_conv_kernel<false, 2>); else go(first_conv_kernel<false, 8>); }
         MS_LAUNCH_CHECK();
         return;
     }

@@ -171,12 +171,6 @@ __device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, u
         ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
         : "memory");
 }
-// L2 prefetch of a 4-D box (no shared-memory destination, no barrier): the later tma_load_4d of the same box hits L2
-__device__ __forceinline__ void tma_prefetch_4d(const CUtensorMap* map, int c0, int c1, int c2, int c3) {
-    asm volatile("cp.async.bulk.prefetch.tensor.4d.L2.global.tile [%0, {%1, %2, %3, %4}];"
-                 ::"l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
-                 : "memory");
-}
 __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
     asm volatile(
         "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
@@ -1246,44 +1240,6 @@ struct RowPairCfg {
     static_assert(SMEM_BYTES <= 227 * 1024, "row-pair kernel: weights do not fit beside two halo stages");
 };
 
-// 64 -> n_classes head of one pixel on its fp32 features (bias + ReLU applied here), src/process.cpp:158-170
-__device__ __forceinline__ void head_pixel(const ConvArgs& args, const float* s_head, const uint32_t (&r0)[32], const uint32_t (&r1)[32],
-                                           int b, int y, int x) {
-    float f[64];
-    const float4* b4 = reinterpret_cast<const float4*>(args.bias);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-        const float4 lo = __ldg(b4 + j), hi = __ldg(b4 + 8 + j);
-        f[4 * j + 0] = fmaxf(__uint_as_float(r0[4 * j + 0]) + lo.x, 0.0f);
-        f[4 * j + 1] = fmaxf(__uint_as_float(r0[4 * j + 1]) + lo.y, 0.0f);
-        f[4 * j + 2] = fmaxf(__uint_as_float(r0[4 * j + 2]) + lo.z, 0.0f);
-        f[4 * j + 3] = fmaxf(__uint_as_float(r0[4 * j + 3]) + lo.w, 0.0f);
-        f[32 + 4 * j + 0] = fmaxf(__uint_as_float(r1[4 * j + 0]) + hi.x, 0.0f);
-        f[32 + 4 * j + 1] = fmaxf(__uint_as_float(r1[4 * j + 1]) + hi.y, 0.0f);
-        f[32 + 4 * j + 2] = fmaxf(__uint_as_float(r1[4 * j + 2]) + hi.z, 0.0f);
-        f[32 + 4 * j + 3] = fmaxf(__uint_as_float(r1[4 * j + 3]) + hi.w, 0.0f);
-    }
-    const size_t plane = (size_t)args.H * args.W;
-    const size_t pix = (size_t)b * plane + (size_t)y * args.W + x;
-    float best = -3.402823466e+38f;  // -FLT_MAX, src/process.cpp:159
-    int best_c = 0;
-    for (int c = 0; c < args.n_classes; ++c) {
-        float s = s_head[args.n_classes * 64 + c];
-        const float4* w4 = reinterpret_cast<const float4*>(s_head + c * 64);
-#pragma unroll
-        for (int j = 0; j < 16; ++j) {
-            const float4 w = w4[j];
-            s = fmaf(f[4 * j + 0], w.x, s);
-            s = fmaf(f[4 * j + 1], w.y, s);
-            s = fmaf(f[4 * j + 2], w.z, s);
-            s = fmaf(f[4 * j + 3], w.w, s);
-        }
-        if (args.logits) args.logits[((size_t)b * args.n_classes + c) * plane + (size_t)y * args.W + x] = s;
-        if (s > best) { best = s; best_c = c; }   // strict >: first max wins, NaN never wins
-    }
-    args.mask[pix] = args.n_classes == 1 ? (uint8_t)(best > 0.0f ? args.fg_value : 0) : (uint8_t)best_c;
-}
-
 // 64 -> n_classes head of one pixel on its fp32 features (bias + ReLU already applied), src/process.cpp:158-170
 __device__ __forceinline__ void head_pixel_f(const ConvArgs& args, const float* s_head, const float (&f)[64], int b, int y, int x) {
     const size_t plane = (size_t)args.H * args.W;
@@ -1482,19 +1438,8 @@ conv_rowpair_kernel(const __grid_constant__ CUtensorMap map_a_halo, const __grid
             int sa = 0;
             uint32_t pa = 0;
             pdl_wait();            // weights are in flight; the activations are the previous layer's output
-            // Two 43 KiB halo stages hold one load in flight per SM while the other stage computes -- not enough to cover the
-            // HBM latency at this layer's rate (24 GB/s per SM).  The halos of the tiles kPrefetch rounds ahead are therefore
-            // pulled into L2 by TMA prefetches, so the load that fills a freed stage is an L2 hit.
-            const int pf = args.desc_mode >= 16 ? (args.desc_mode >> 4) : 0;
-            auto prefetch_tile = [&](int t2) {
-                if (t2 >= total) return;
-                const TileCoord p = decode_tile(t2, 1, tiles_x, tiles_y, 64, RP_TW, RP_TH);
-                for (int kc = 0; kc < kchunks; ++kc) tma_prefetch_4d(&map_a_halo, kc * BLOCK_K, p.x0 - 1, p.y0 - 1, p.b);
-            };
-            for (int i = 1; i < pf; ++i) prefetch_tile(blockIdx.x + i * gridDim.x);
             for (int t = blockIdx.x; t < total; t += gridDim.x) {
                 const TileCoord tc = decode_tile(t, 1, tiles_x, tiles_y, 64, RP_TW, RP_TH);
-                if (pf) prefetch_tile(t + pf * gridDim.x);
                 for (int kc = 0; kc < kchunks; ++kc) {
                     mbar_wait(&a_empty[sa], pa ^ 1);
                     mbar_expect_tx(&a_full[sa], RP_HALO_BOX_BYTES);
