@@ -261,11 +261,11 @@ void make_wgt_map(CUtensorMap* m, const __nv_bfloat16* base, int N, int K, int b
 
 template <int BN, int EPI>
 void launch_tc(const UNetLayer& L, const tc::ConvArgs& a, int sm_count, cudaStream_t st) {
-    using C = tc::Cfg<BN>;
+    using C = tc::Cfg<BN, EPI>;
     set_max_dynamic_smem(tc::conv_gemm_kernel<BN, EPI>, C::SMEM_BYTES);
     const int total = a.batch * (a.H / tc::TILE_H) * (a.W / tc::TILE_W) * (a.n_total / BN);
     const int grid = std::min(total, sm_count);
-    launch_kernel(tc::conv_gemm_kernel<BN, EPI>, dim3(grid), dim3(tc::NUM_THREADS), C::SMEM_BYTES, st, true, L.map_a, L.map_b, L.map_out, a);
+    launch_kernel(tc::conv_gemm_kernel<BN, EPI>, dim3(grid), dim3(C::THREADS), C::SMEM_BYTES, st, true, L.map_a, L.map_b, L.map_out, a);
     MS_LAUNCH_CHECK();
 }
 

@@ -67,15 +67,21 @@ struct ConvArgs {
     int desc_mode;          // halo kernel: 0 = base_offset 0, 1 = base_offset (addr >> 7) & 7 (bring-up switch)
 };
 
-template <int BLOCK_N>
+template <int BLOCK_N, int EPI = 0>
 struct Cfg {
+    // The transposed convs (K = Cin only: 2 - 16 chunks per tile, N = 256) are bound by their EPILOGUE -- four 64-column
+    // blocks of TMEM load / pack / stage / TMA scatter per warp against 8 - 64 MMAs -- so they get two epilogue warps per
+    // TMEM lane quarter, each taking half of the columns.
+    static constexpr int EPI_GROUPS = (EPI == 1 /* EPI_CONVT */ && BLOCK_N == 256) ? 2 : 1;
+    static constexpr int THREADS = 64 + 128 * EPI_GROUPS;
     static constexpr int B_STAGE_BYTES = BLOCK_N * BLOCK_K * 2;
     static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
-    static constexpr int STAGES = (BLOCK_N == 256) ? 4 : (BLOCK_N == 128 ? 6 : 8);
+    static constexpr int STAGES = (BLOCK_N == 256) ? (EPI_GROUPS == 2 ? 3 : 4) : (BLOCK_N == 128 ? 6 : 8);
     static constexpr int TMEM_COLS = 2 * BLOCK_N < 32 ? 32 : 2 * BLOCK_N;  // 128 / 256 / 512: powers of two
     static constexpr int AUX_BYTES = 4096;  // barriers, tmem pointer, head weights
-    static constexpr int STG_BYTES = 4 * 4096;  // one 4 KiB output staging slab per epilogue warp
+    static constexpr int STG_BYTES = EPI_GROUPS * 4 * 4096;  // one 4 KiB output staging slab per epilogue warp
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STG_BYTES + AUX_BYTES + 1024;  // + alignment slack
+    static_assert(SMEM_BYTES <= 227 * 1024, "conv_gemm_kernel: shared memory");
 };
 
 // ------------------------------------------------------------------------------------ PTX wrappers
@@ -282,7 +288,7 @@ __device__ __forceinline__ void mbar_arrive_cluster_fwd(uint32_t cluster_addr);
 
 template <int BLOCK_N, int EPI, int TW, bool REMOTE = false>
 __device__ __forceinline__ void epilogue_tile(const ConvArgs& args, const float* s_head, uint32_t taddr, const EpiCtx& e,
-                                              uint64_t* tmem_empty_bar, uint32_t remote_empty = 0) {
+                                              uint64_t* tmem_empty_bar, uint32_t remote_empty = 0, int c_begin = 0, int c_end = BLOCK_N) {
     if (EPI == EPI_HEAD) {
         // BLOCK_N == 64: the whole feature vector of this pixel
         uint32_t r0[32], r1[32];
@@ -326,12 +332,12 @@ __device__ __forceinline__ void epilogue_tile(const ConvArgs& args, const float*
         args.mask[pix] = args.n_classes == 1 ? (uint8_t)(best > 0.0f ? args.fg_value : 0) : (uint8_t)best_c;
     } else {
 #pragma unroll 1
-        for (int c0 = 0; c0 < BLOCK_N; c0 += 64) {
+        for (int c0 = c_begin; c0 < c_end; c0 += 64) {
             uint32_t r0[32], r1[32];
             tmem_ld32(taddr + c0, r0);
             tmem_ld32(taddr + c0 + 32, r1);
             tmem_ld_wait();
-            if (c0 + 64 >= BLOCK_N) {  // last block read: hand the accumulator back to the MMA warp
+            if (c0 + 64 >= c_end) {  // last block read: hand the accumulator back to the MMA warp
                 tc_fence_before();
                 if (REMOTE) mbar_arrive_cluster_fwd(remote_empty); else mbar_arrive(tmem_empty_bar);
             }
@@ -437,10 +443,10 @@ __device__ __forceinline__ void tmem_dealloc_warp(uint32_t base, uint32_t cols) 
 // Per-tap operand streaming: every k-step loads one shifted 16x8-pixel A box and one B box.  Used where
 // N >= 256 keeps the tensor pipe busy per byte fetched (deep layers) and for the ConvT GEMMs (one tap).
 template <int BLOCK_N, int EPI>
-__global__ void __launch_bounds__(NUM_THREADS, 1)
+__global__ void __launch_bounds__(Cfg<BLOCK_N, EPI>::THREADS, 1)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                  const __grid_constant__ CUtensorMap map_out, const ConvArgs args) {
-    using C = Cfg<BLOCK_N>;
+    using C = Cfg<BLOCK_N, EPI>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* s_stg = smem + C::STAGES * C::STAGE_BYTES;
@@ -469,13 +475,13 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(&tmem_full[i], 1);
-            mbar_init(&tmem_empty[i], 128);
+            mbar_init(&tmem_empty[i], 128 * C::EPI_GROUPS);
         }
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc_warp(tmem_ptr, C::TMEM_COLS);
     if (EPI == EPI_HEAD) {
-        for (int i = threadIdx.x; i < args.n_classes * 64 + args.n_classes; i += NUM_THREADS)
+        for (int i = threadIdx.x; i < args.n_classes * 64 + args.n_classes; i += C::THREADS)
             s_head[i] = i < args.n_classes * 64 ? args.head_w[i] : args.head_b[i - args.n_classes * 64];
     }
     tc_fence_before();
@@ -543,11 +549,13 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     } else {
         // ===================================================================== epilogue (warps 2..5)
         const int quarter = warp & 3;           // TMEM lane quarter this warp may access
+        const int egroup = (warp - 2) >> 2;     // which share of the columns (two warps per quarter for the transposed convs)
+        constexpr int kColsPerGroup = BLOCK_N / C::EPI_GROUPS;
         const int row = quarter * 32 + lane;    // GEMM row inside the tile = pixel
         const int ly = row / TILE_W, lx = row % TILE_W;
         EpiCtx e;
         e.map_out = &map_out;
-        e.slab = smem_u32(s_stg + quarter * 4096);
+        e.slab = smem_u32(s_stg + (egroup * 4 + quarter) * 4096);
         e.slab_y = quarter * (32 / TILE_W);
         e.lane = lane;
         int acc = 0;
@@ -558,7 +566,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             mbar_wait(&tmem_full[acc], acc_phase);
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BLOCK_N);
-            epilogue_tile<BLOCK_N, EPI, TILE_W>(args, s_head, taddr, e, &tmem_empty[acc]);
+            epilogue_tile<BLOCK_N, EPI, TILE_W>(args, s_head, taddr, e, &tmem_empty[acc], 0u, egroup * kColsPerGroup, (egroup + 1) * kColsPerGroup);
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
         if (EPI != EPI_HEAD && lane == 0) tma_store_wait_read();   // the slab must outlive the last store's read
