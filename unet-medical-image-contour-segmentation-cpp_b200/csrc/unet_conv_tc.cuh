@@ -1248,29 +1248,40 @@ struct RowPairCfg {
     static_assert(SMEM_BYTES <= 227 * 1024, "row-pair kernel: weights do not fit beside two halo stages");
 };
 
-// 64 -> n_classes head of one pixel on its fp32 features (bias + ReLU already applied), src/process.cpp:158-170
-__device__ __forceinline__ void head_pixel_f(const ConvArgs& args, const float* s_head, const float (&f)[64], int b, int y, int x) {
+// 64 -> n_classes head (src/process.cpp:158-170) of the TWO pixels of a row-pair lane, (y, x) and (y + 1, x), on their fp32
+// features (bias + ReLU already applied).  Both pixels share every broadcast weight load and run eight independent FMA chains
+// (four partial sums per pixel): with one pixel at a time the multi-class head waited on its shared-memory weight loads
+// (ncu: long-scoreboard stalls on the FFMAs) and ran the layer at half the rate of the binary head.
+__device__ __forceinline__ void head_pixel_pair(const ConvArgs& args, const float* s_head, const float (&f0)[64], const float (&f1)[64],
+                                                int b, int y, int x) {
     const size_t plane = (size_t)args.H * args.W;
     const size_t pix = (size_t)b * plane + (size_t)y * args.W + x;
-    float best = -3.402823466e+38f;  // -FLT_MAX, src/process.cpp:159
-    int best_c = 0;
+    float best0 = -3.402823466e+38f, best1 = -3.402823466e+38f;  // -FLT_MAX, src/process.cpp:159
+    int c0 = 0, c1 = 0;
     for (int c = 0; c < args.n_classes; ++c) {
-        // four partial sums: the dot product is a 16-deep dependent chain instead of a 64-deep one
-        float s0 = s_head[args.n_classes * 64 + c], s1 = 0.0f, s2 = 0.0f, s3 = 0.0f;
+        const float hb = s_head[args.n_classes * 64 + c];
+        float p0 = hb, p1 = 0.0f, p2 = 0.0f, p3 = 0.0f, q0 = hb, q1 = 0.0f, q2 = 0.0f, q3 = 0.0f;
         const float4* w4 = reinterpret_cast<const float4*>(s_head + c * 64);
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
             const float4 w = w4[j];
-            s0 = fmaf(f[4 * j + 0], w.x, s0);
-            s1 = fmaf(f[4 * j + 1], w.y, s1);
-            s2 = fmaf(f[4 * j + 2], w.z, s2);
-            s3 = fmaf(f[4 * j + 3], w.w, s3);
+            p0 = fmaf(f0[4 * j + 0], w.x, p0); q0 = fmaf(f1[4 * j + 0], w.x, q0);
+            p1 = fmaf(f0[4 * j + 1], w.y, p1); q1 = fmaf(f1[4 * j + 1], w.y, q1);
+            p2 = fmaf(f0[4 * j + 2], w.z, p2); q2 = fmaf(f1[4 * j + 2], w.z, q2);
+            p3 = fmaf(f0[4 * j + 3], w.w, p3); q3 = fmaf(f1[4 * j + 3], w.w, q3);
         }
-        const float sum = (s0 + s1) + (s2 + s3);
-        if (args.logits) args.logits[((size_t)b * args.n_classes + c) * plane + (size_t)y * args.W + x] = sum;
-        if (sum > best) { best = sum; best_c = c; }   // strict >: first max wins, NaN never wins
+        const float s0 = (p0 + p1) + (p2 + p3), s1 = (q0 + q1) + (q2 + q3);
+        if (args.logits) {
+            float* lg = args.logits + ((size_t)b * args.n_classes + c) * plane + (size_t)y * args.W + x;
+            lg[0] = s0;
+            lg[args.W] = s1;
+        }
+        if (s0 > best0) { best0 = s0; c0 = c; }   // strict >: first max wins, NaN never wins
+        if (s1 > best1) { best1 = s1; c1 = c; }
     }
-    args.mask[pix] = args.n_classes == 1 ? (uint8_t)(best > 0.0f ? args.fg_value : 0) : (uint8_t)best_c;
+    const bool binary = args.n_classes == 1;
+    args.mask[pix] = binary ? (uint8_t)(best0 > 0.0f ? args.fg_value : 0) : (uint8_t)c0;
+    args.mask[pix + args.W] = binary ? (uint8_t)(best1 > 0.0f ? args.fg_value : 0) : (uint8_t)c1;
 }
 
 // Epilogue of one row-pair tile for one epilogue warp: lane = (row group gl, px) owns output pixels (yw + 2 gl, x0 + px) in
@@ -1295,20 +1306,19 @@ __device__ __forceinline__ void rowpair_epilogue_tile(const ConvArgs& args, cons
     if (REMOTE) mbar_arrive_cluster_fwd(remote_empty); else mbar_arrive(tmem_empty_bar);
     const float4* b4 = reinterpret_cast<const float4*>(s_bias);     // broadcast 16-byte loads
     if (EPI == EPI_HEAD) {
+        float f[2][64];
 #pragma unroll
-        for (int half = 0; half < 2; ++half) {
-            float f[64];
+        for (int half = 0; half < 2; ++half)
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
                 const float4 bb = b4[j];
                 const uint32_t* q = &r[2 * half + (j >> 3)][4 * (j & 7)];
-                f[4 * j + 0] = fmaxf(__uint_as_float(q[0]) + bb.x, 0.0f);
-                f[4 * j + 1] = fmaxf(__uint_as_float(q[1]) + bb.y, 0.0f);
-                f[4 * j + 2] = fmaxf(__uint_as_float(q[2]) + bb.z, 0.0f);
-                f[4 * j + 3] = fmaxf(__uint_as_float(q[3]) + bb.w, 0.0f);
+                f[half][4 * j + 0] = fmaxf(__uint_as_float(q[0]) + bb.x, 0.0f);
+                f[half][4 * j + 1] = fmaxf(__uint_as_float(q[1]) + bb.y, 0.0f);
+                f[half][4 * j + 2] = fmaxf(__uint_as_float(q[2]) + bb.z, 0.0f);
+                f[half][4 * j + 3] = fmaxf(__uint_as_float(q[3]) + bb.w, 0.0f);
             }
-            head_pixel_f(args, s_head, f, tcd.b, yw + 2 * gl + half, tcd.x0 + px);
-        }
+        head_pixel_pair(args, s_head, f[0], f[1], tcd.b, yw + 2 * gl, tcd.x0 + px);
         return;
     }
     uint32_t pk[2][32];                                              // pk[half][i] = channels 2 i, 2 i + 1
