@@ -395,6 +395,7 @@ void UNet::load(const std::string& blob_path, int net_h, int net_w, int n_classe
     const char* cv = std::getenv("MEDSEG_CTA2");
     cta2_enabled_ = !(cv && cv[0] == '0');
     cta2_force_ = cv && cv[0] == '2';
+    cta2_single_pref_ = cv && cv[0] == '1';
     const char* d2 = std::getenv("MEDSEG_DEEP2");
     deep2_enabled_ = !(d2 && d2[0] == '0');
     const char* rb = std::getenv("MEDSEG_RES_BIG");
@@ -498,7 +499,10 @@ void UNet::load(const std::string& blob_path, int net_h, int net_w, int n_classe
             const bool pair_ok = ((h / tc::HALO_TH) * (w / tc::HALO_TW)) % 2 == 0;
             // a resident half-weight set that leaves room for only two halo stages loses to streaming (measured)
             const bool fits2 = 9 * kc * (L.block_n / 2) * 128 <= (res_big_ ? 144 : 96) * 1024 && pair_ok;
-            if (fits1 && !(cta2_force_ && fits2)) {
+            // N = 128 with one chunk (enc2a): since the pair's remote arrive lost its cluster-scope release the pair kernel wins
+            // here too (0.216 -> 0.203 ms); MEDSEG_CTA2=1 keeps the single-CTA kernel
+            const bool prefer_pair = cta2_enabled_ && !cta2_single_pref_ && fits2 && L.block_n == 128;
+            if (fits1 && !prefer_pair && !(cta2_force_ && fits2)) {
                 L.halo = 1;
                 L.resident_kc = kc;
             } else if (fits2 && cta2_enabled_) {

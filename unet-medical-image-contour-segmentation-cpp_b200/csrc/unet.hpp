@@ -82,6 +82,7 @@ class UNet {
     bool halo_enabled_ = true;  // MEDSEG_HALO=0: force the per-tap kernel everywhere (A/B measurements)
     bool cta2_enabled_ = true;  // MEDSEG_CTA2=0: single-CTA halo kernel only
     bool cta2_force_ = false;
+    bool cta2_single_pref_ = false;   // MEDSEG_CTA2=1: single-CTA halo kernel where both forms fit (A/B measurements)
     bool deep2_enabled_ = true;    // MEDSEG_DEEP2=0: per-tap kernel for the N = 256 layers
     bool res_big_ = true;          // MEDSEG_RES_BIG=0: 144 KiB half-weight sets stream instead of staying resident
     bool rowpair_enabled_ = true;  // MEDSEG_ROWPAIR=0: kernels 2 / 3 for the Cout = 64 layers
