@@ -410,8 +410,6 @@ void UNet::load(const std::string& blob_path, int net_h, int net_w, int n_classe
     const char* pv = std::getenv("MEDSEG_HALO_PITCH");
     halo_pitch_ = 10;
     (void)pv;
-    const char* dv = std::getenv("MEDSEG_DESC_MODE");
-    desc_mode_ = dv ? std::atoi(dv) : 0;
     {   // publish the watchdog word to this device's copy of the symbol (mapped host memory: same address under UVA)
         unsigned* wd = watchdog_host_word();
         MS_CUDA(cudaMemcpyToSymbol(tc::g_watchdog_dev, &wd, sizeof(wd)));
@@ -663,7 +661,6 @@ void UNet::run_layer(int li, const uint8_t* d_in_u8, int batch, uint8_t* d_mask,
     a.head_w = head_w_; a.head_b = head_b_; a.n_classes = n_classes_; a.fg_value = fg_value_;
     a.mask = d_mask ? d_mask : scratch_mask_.as<uint8_t>();
     a.logits = d_logits;
-    a.desc_mode = desc_mode_;
     if (naive_) {
         const __nv_bfloat16* src = bufs_[L.src].p;
         if (L.kind == 3) {

@@ -90,7 +90,6 @@ class UNet {
     bool rowpair_stream_ = true;   // MEDSEG_ROWPAIR=1: row-pair kernel only where its weights stay resident (not dec1a)
     bool stream2_enabled_ = true;  // MEDSEG_STREAM2=0: per-tap kernel instead of the streaming pair kernel (dec2a)
     int halo_pitch_ = 16;       // MEDSEG_HALO_PITCH
-    int desc_mode_ = 0;         // MEDSEG_DESC_MODE: UMMA descriptor base-offset convention of the halo kernel
     int64_t n_params_ = 0;
     double flops_ = 0;
     std::vector<UNetLayer> layers_;

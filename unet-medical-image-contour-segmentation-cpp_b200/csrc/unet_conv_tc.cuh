@@ -64,7 +64,6 @@ struct ConvArgs {
     int fg_value;           // value written by the binary head
     uint8_t* mask;          // [batch][H][W]
     float* logits;          // optional [batch][n_classes][H][W]
-    int desc_mode;          // halo kernel: 0 = base_offset 0, 1 = base_offset (addr >> 7) & 7 (bring-up switch)
 };
 
 template <int BLOCK_N, int EPI = 0>
