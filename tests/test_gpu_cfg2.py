@@ -107,3 +107,26 @@ def test_cfg2_every_slice_integer_stages_bit_exact(cfg2):
         eng.submit_batch(it % 2, vol)
         got = eng.wait_batch(it % 2)
         assert (got.slice_start == polys.slice_start).all() and (got.contour_start == polys.contour_start).all() and (got.xy == polys.xy).all()
+
+
+def test_cfg2_forward_is_deterministic_under_repetition(cfg2):
+    """The pipelines hand accumulators, shared-memory stages and staging slabs between warps with relaxed arrives and
+    asynchronous-proxy fences; a missing ordering shows up as run-to-run differences long before it shows up as a wrong
+    answer.  40 repetitions of the bench batch (kernels back to back, persistent CTAs, PDL between layers): logits, deep
+    activations, masks and polygons must be bit-identical every time."""
+    import hashlib
+    eng, vol, _ = cfg2
+    norm = eng.preprocess(vol)
+    seen = set()
+    for it in range(40):
+        mask, logits = eng.process(norm, want_logits=True)
+        acts = b"".join(eng.read_activation(n, B).tobytes() for n in ("p1", "bb")) if it in (0, 39) else b""
+        seen.add((hashlib.sha256(mask.tobytes()).hexdigest(), hashlib.sha256(logits.tobytes()).hexdigest(),
+                  hashlib.sha256(acts).hexdigest() if acts else ""))
+    assert len({s[:2] for s in seen}) == 1, "forward pass is not deterministic"
+    assert len({s[2] for s in seen if s[2]}) == 1, "intermediate activations are not deterministic"
+    polys0, _, _ = eng.process_batch(vol)
+    for it in range(6):
+        eng.submit_batch(it % 2, vol)
+        got = eng.wait_batch(it % 2)
+        assert (got.xy == polys0.xy).all() and (got.contour_start == polys0.contour_start).all()
