@@ -57,6 +57,29 @@ def dist_env():
     return rank, world, local
 
 
+def unet_layer_bytes(names, B, S, n_classes):
+    """Algorithmic HBM bytes per UNet layer of the canonical architecture at batch B, S x S input:
+    every input map read once, every output map written once (bf16 NHWC; the u8 slice in, the u8 mask out), weights once.
+    The skip halves of the concat buffers are counted where they are read (the decoder's first conv)."""
+    px = lambda lvl: B * (S >> lvl) * (S >> lvl)
+    out = {"enc1a": px(0) * (1 + 64 * 2) + 64 * 9 * 4}
+    enc = {1: (64, 64), 2: (64, 128), 3: (128, 256), 4: (256, 512)}
+    out["enc1b"] = px(0) * (64 * 2 + 64 * 2) + px(1) * 64 * 2 + 64 * 64 * 9 * 2
+    for lvl, name in ((1, "enc2"), (2, "enc3"), (3, "enc4")):
+        cin, cout = enc[lvl + 1]
+        out[name + "a"] = px(lvl) * (cin + cout) * 2 + cin * cout * 9 * 2
+        out[name + "b"] = px(lvl) * (cout + cout) * 2 + px(lvl + 1) * cout * 2 + cout * cout * 9 * 2
+    out["bott_a"] = px(4) * (512 + 1024) * 2 + 512 * 1024 * 9 * 2
+    out["bott_b"] = px(4) * (1024 + 1024) * 2 + 1024 * 1024 * 9 * 2
+    for k, lvl, c in ((4, 3, 512), (3, 2, 256), (2, 1, 128), (1, 0, 64)):      # up_k: level lvl + 1 -> lvl; dec_k at level lvl
+        out["up%d" % k] = px(lvl + 1) * 2 * c * 2 + px(lvl) * c * 2 + 2 * c * c * 4 * 2
+        out["dec%da" % k] = px(lvl) * (2 * c + c) * 2 + 2 * c * c * 9 * 2
+        out["dec%db" % k] = px(lvl) * (c + c) * 2 + c * c * 9 * 2
+    out["dec1b_head"] = px(0) * (64 * 2 + 1) + 64 * 64 * 9 * 2
+    out.pop("dec1b", None)
+    return {n: out.get(n, 0) for n in names}
+
+
 def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -373,16 +396,18 @@ def run_ours(args, rank, world, local):
         stages.append({"stage": k, "what": what, "ms": t, "alg_bytes": int(alg[k]), "achieved": alg[k] / t / 1e6 if t > 0 else None,
                        "peak": hbm, "unit": "GB/s", "frac": alg[k] / t / 1e6 / hbm if t > 0 else None, "share_of_step": t / ms_per_step})
     table, by_kernel = [], {}
+    layer_bytes = unet_layer_bytes(names, B, S, eng.info.n_classes)
     for li, name in enumerate(names):
         ms_alone, fl = eng.time_layer(li, B, iters=max(3, min(10, args.steps)))
         ms_l = in_step_ms[li]
         table.append({"layer": name, "kernel": kernels[li], "ms_in_step": ms_l, "ms_alone": ms_alone, "gflop": fl / 1e9,
                       "tflops_in_step": fl / ms_l / 1e9 if ms_l > 0 else None})
-        k = by_kernel.setdefault(kernels[li], {"kernel": kernels[li], "launches": 0, "ms": 0.0, "ms_alone": 0.0, "flop": 0.0})
+        k = by_kernel.setdefault(kernels[li], {"kernel": kernels[li], "launches": 0, "ms": 0.0, "ms_alone": 0.0, "flop": 0.0, "alg_bytes": 0})
         k["launches"] += 1
         k["ms"] += ms_l
         k["ms_alone"] += ms_alone
         k["flop"] += fl
+        k["alg_bytes"] += layer_bytes.get(name, 0)
     kernel_rows = sorted(by_kernel.values(), key=lambda r: -r["ms"])
     for r in kernel_rows:   # per kernel instantiation: algorithmic FLOP of its launches / their event-timed durations
         r["achieved"] = r["flop"] / (r["ms"] / 1e3) / 1e12                 # inside the step -> sustained peak
@@ -390,6 +415,11 @@ def run_ours(args, rank, world, local):
         r["achieved_alone"] = r["flop"] / (r["ms_alone"] / 1e3) / 1e12     # timed alone -> burst peak
         r["frac_alone"] = r["achieved_alone"] / burst
         r["share_of_step"] = r["ms"] / ms_per_step
+        # the other roofline: ALGORITHMIC activation + weight bytes of its launches (every map read once, written once) / the same
+        # in-step time, against the measured HBM peak; `bound` names the roofline this instantiation sits closer to
+        r["hbm_gbs"] = r["alg_bytes"] / (r["ms"] / 1e3) / 1e9 if r["alg_bytes"] else None
+        r["hbm_frac"] = r["hbm_gbs"] / hbm if r["alg_bytes"] else None
+        r["bound"] = "hbm" if (r["hbm_frac"] or 0.0) > r["frac"] else "tensor"
         del r["flop"]
     dominant = kernel_rows[0]
     fwd_ms = float(sum(in_step_ms))
