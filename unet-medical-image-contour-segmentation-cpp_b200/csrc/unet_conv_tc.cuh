@@ -1,8 +1,17 @@
 // unet_conv_tc.cuh -- implicit-GEMM convolution on tcgen05 / TMEM, fed by TMA (sm_100a).
 //
 // This is the dense contraction of the UNet forward that the reference runs inside an opaque
-// TensorRT engine (/root/reference/src/process.cpp:94,147).  One persistent, warp-specialised
-// kernel serves every GEMM-shaped layer of the network:
+// TensorRT engine (/root/reference/src/process.cpp:94,147).  Six persistent, warp-specialised
+// kernels share the PTX wrappers, the epilogues and the pipeline scheme described here (kernel 1);
+// unet.cu picks one per layer from measurements:
+//   1 conv_gemm_kernel      per-tap operand streaming           the transposed convs up1 - up3 (8 epilogue warps)
+//   2 conv_halo_kernel      halo-stationary A, resident weights  A/B fallback of the narrow layers
+//   3 conv_halo2_kernel     kernel 2 as a cta_group::2 pair      enc2*, dec2*, and every N = 256 layer (streamed weights)
+//   4 convt_pair_kernel     transposed conv as a pair GEMM       up4
+//   5 conv_rowpair_kernel   two output rows per GEMM row         A/B fallback of kernel 6
+//   6 conv_rowpair2_kernel  kernel 5 as a cta_group::2 pair      the Cout = 64 layers: enc1b, dec1a, dec1b + head
+//
+// Every GEMM-shaped layer of the network is one of:
 //
 //   conv3x3 (pad 1) + folded BN + ReLU   M = pixels, N = Cout, K = 9 * Cin     (18 layers)
 //   ConvTranspose2d(k=2, s=2) + bias     M = input pixels, N = 4 * Cout, K = Cin  (4 layers)
@@ -1210,9 +1219,10 @@ convt_pair_kernel(const __grid_constant__ CUtensorMap map_a_tile, const __grid_c
 
 
 // ==================================================================================== kernel 5
-// Row-pair halo kernel for the Cout = 64 layers (enc1b, dec1b + head), which kernels 2 / 3 leave on the tcgen05 issue floor:
-// an M = 128 UMMA costs ~72 cycles whether N is 64 or 128 (profiles/r1_mma_rate_microbench.log), so at N = 64 half of every
-// instruction slot is empty and those layers cannot exceed ~45 % of the tensor peak.  Here ONE GEMM row carries TWO output
+// Row-pair halo kernel for the Cout = 64 layers (enc1b, dec1a, dec1b + head), which kernels 2 / 3 leave on the per-instruction
+// floor: an M = 128 UMMA costs ~64 - 72 cycles whether N is 64 or 128 (profiles/r1_mma_rate_microbench.log; what it waits for is
+// its operand read from shared memory, see kernel 6), so at N = 64 half of every instruction slot is empty and those layers
+// cannot exceed ~45 % of the tensor peak with one output pixel per GEMM row.  Here ONE GEMM row carries TWO output
 // pixels, (y, x) and (y + 1, x): accumulator columns [0, 64) are the 64 channels of the even output row, [64, 128) those of
 // the odd row below it.  An A operand read at input-row shift a (relative to the even row) feeds tap dy = a of the even row
 // and tap dy = a - 1 of the odd row, so with the weight tiles of one filter column laid out as [W(dy=+1) | W(0) | W(-1)]
