@@ -25,6 +25,7 @@ namespace dp {
 constexpr int kT = 256;
 constexpr int kW = kT / 32;
 constexpr int kSmemPts = 6144;
+constexpr int kLaneSlice = 48;          // slices with at most this many interior vertices are scanned by a single lane
 // vertices u32[kSmemPts] | work lists uint2[kSmemPts] (two lists of n / 2 slices; later the kept vertices int2[n]) | bitmap
 constexpr size_t kSmemBytes = (size_t)kSmemPts * 4 + (size_t)kSmemPts * 8 + (size_t)(kSmemPts / 32) * 4;
 
@@ -160,22 +161,38 @@ __global__ void __launch_bounds__(kT) simplify_kernel(const Args a) {
             const unsigned long long Ls = (unsigned long long)(L > 0 ? L : 1);
             const int n_in = interior(s0, s1);
             Best b{0ull, 0x7FFFFFFF};
-            for (int k = 1 + first; k <= n_in; k += stride) {
-                int idx = s0 + k;
-                if (idx >= cnt) idx -= cnt;
-                const int2 p = P(idx);
+            auto dist = [&](const int2 p) -> unsigned long long {
                 const long long px = p.x - A.x, py = p.y - A.y;
                 const long long dot = px * dx + py * dy;
-                unsigned long long v;
-                if (L == 0 || dot < 0) {
-                    v = (unsigned long long)(px * px + py * py) * Ls;
-                } else if (dot > L) {
+                if (L == 0 || dot < 0) return (unsigned long long)(px * px + py * py) * Ls;
+                if (dot > L) {
                     const long long qx = p.x - B.x, qy = p.y - B.y;
-                    v = (unsigned long long)(qx * qx + qy * qy) * Ls;
-                } else {
-                    const long long cr = py * dx - px * dy;
-                    v = (unsigned long long)(cr * cr);
+                    return (unsigned long long)(qx * qx + qy * qy) * Ls;
                 }
+                const long long cr = py * dx - px * dy;
+                return (unsigned long long)(cr * cr);
+            };
+            // four vertices per step, all four loads in flight together: a contour too long for shared memory is read from
+            // L2, and one dependent load per iteration made the 51 k-vertex cfg5 contour take milliseconds
+            int k = 1 + first;
+            for (; k + 3 * stride <= n_in; k += 4 * stride) {
+                int2 p[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    int idx = s0 + k + u * stride;
+                    if (idx >= cnt) idx -= cnt;
+                    p[u] = P(idx);
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const unsigned long long v = dist(p[u]);
+                    if (v > b.v) { b.v = v; b.k = k + u * stride; }
+                }
+            }
+            for (; k <= n_in; k += stride) {
+                int idx = s0 + k;
+                if (idx >= cnt) idx -= cnt;
+                const unsigned long long v = dist(P(idx));
                 if (v > b.v) { b.v = v; b.k = k; }
             }
             return b;
@@ -202,11 +219,24 @@ __global__ void __launch_bounds__(kT) simplify_kernel(const Args a) {
             const int nc = s_n[0];
             if (nc == 0) break;
             if (nc >= kW) {
+                // long slices: one warp each.  On the global-scratch path (a contour too long for shared memory) the short ones
+                // -- the bulk of the deep levels -- take one LANE each, 256 slices at a time: a warp per 5-vertex slice spent its
+                // time on the slice's fixed L2 latencies (list entry, end points, atomics).  From shared memory the warp form is
+                // the faster one.
+                const int lane_max = fits ? 0 : kLaneSlice;
                 for (int it = warp; it < nc; it += kW) {
                     const uint2 s = cur[it];
+                    if (interior((int)s.x, (int)s.y) <= lane_max) continue;
                     long long L;
                     Best b = warp_best(scan_slice((int)s.x, (int)s.y, lane, 32, L));
                     if (lane == 0) decide(nxt, (int)s.x, (int)s.y, b, L);
+                }
+                for (int it = tid; it < nc; it += kT) {
+                    const uint2 s = cur[it];
+                    if (interior((int)s.x, (int)s.y) > lane_max) continue;
+                    long long L;
+                    const Best b = scan_slice((int)s.x, (int)s.y, 0, 1, L);
+                    decide(nxt, (int)s.x, (int)s.y, b, L);
                 }
             } else {
                 for (int it = 0; it < nc; ++it) {
