@@ -153,6 +153,14 @@ MS_API int ms_mask2polygon_dev(ms_handle* h, const uint8_t* d_mask, int hgt, int
 MS_API int ms_process_batch_host(ms_handle* h, const uint16_t* h_src, int w, int hgt, int batch,
                                  ms_polygons* out, uint8_t* h_norm_u8, uint8_t* h_mask_u8);
 
+/* BASELINE.json configs[3] ("multi-class UNet with argmax head and per-class contours"): K1 and the UNet once, then for every
+ * requested label k = classes[i] (1 .. 255) postprocess with FOREGROUND_VALUE = k (src/postprocess.cpp:5 made a parameter) and
+ * mask2polygon of (mask == k), all on the device.  outs[i] receives label classes[i]'s polygons in original coordinates;
+ * h_raw_mask_u8 (optional, [batch][net_h][net_w]) the argmax mask, h_clean_masks_u8 (optional, [n_classes][batch][net_h][net_w])
+ * the cleaned masks.  MS_ERR_CAPACITY: every outs[i].n_contours / n_points says what that label needs. */
+MS_API int ms_process_batch_multiclass_host(ms_handle* h, const uint16_t* h_src, int w, int hgt, int batch, const int32_t* classes,
+                                            int n_classes, ms_polygons* outs, uint8_t* h_raw_mask_u8, uint8_t* h_clean_masks_u8);
+
 /* Device-resident variant used for kernel-only timing: input already in HBM, polygons stay in the
  * handle's device workspace.  With n_points / n_contours given the call waits for the two totals (and grows the
  * device polygon capacities when the batch needed more); with both NULL it is fully asynchronous on `stream` -- no

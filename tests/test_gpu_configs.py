@@ -57,7 +57,38 @@ def test_cfg4_1024_four_labels_per_class_contours(ms, tmp_path):
         assert contours_equal(polys.slice(0), ref), k
         n_found += len(ref)
     assert n_found >= 1
+    # the same through ONE C-ABI call (ms_process_batch_multiclass_host: K1 + UNet once, K5 / K6 per label on the device)
+    raw2, per_class2 = eng.process_batch_multiclass(src, classes=(1, 2, 3), want_masks=True)
+    assert (raw2 == raw).all()
+    for k in (1, 2, 3):
+        assert (per_class2[k][0] == per_class[k][0]).all(), k
+        assert contours_equal(per_class2[k][1].slice(0), per_class[k][1].slice(0)), k
     eng.cleanup()
+
+
+def test_multiclass_call_512_fused_path_vs_oracle(unet_engine, torch_unet3, ms):
+    """The multi-class call at 512 x 512 (3-class argmax head, batch 3, non-identity mapping): every label runs the fused
+    K5 + K6 kernel with FOREGROUND_VALUE = k; per label the clean mask equals the oracle's postprocess of the kernel's own
+    argmax mask and the polygons equal cv2's on that clean mask, mapped with (int)(x * scale)."""
+    from medseg_b200 import synth
+    vol = synth.ct_volume(3, 640, 480, first_seed=60)
+    raw, per_class = unet_engine.process_batch_multiclass(vol, classes=(2, 1), want_masks=True)
+    polys_only = unet_engine.process_batch_multiclass(vol, classes=(2, 1))
+    sx, sy = 640 / 512, 480 / 512
+    n = 0
+    for k in (1, 2):
+        clean, polys = per_class[k]
+        for i in range(3):
+            want_clean = op.postprocess_mask(raw[i], fg=k)
+            assert (clean[i] == want_clean).all(), (k, i)
+            want = op.map_contour_points(op.extract_contours(np.where(want_clean == k, 255, 0).astype(np.uint8)), sx, sy)
+            assert contours_equal(polys.slice(i), want), (k, i)
+            assert contours_equal(polys_only[k].slice(i), want), (k, i)
+            n += len(want)
+    assert n >= 3
+    # label 2 alone is the reference's own configuration: identical to the single-label whole-path call
+    ref_polys, _, ref_mask = unet_engine.process_batch(vol, want_mask=True)
+    assert (per_class[2][0] == ref_mask).all() and (per_class[2][1].xy == ref_polys.xy).all()
 
 
 @pytest.mark.parametrize("net_h,net_w", [(128, 256), (256, 512), (384, 256), (128, 1536)])

@@ -81,6 +81,7 @@ ABI = {
     "ms_process_directory": (_I, [_P, C.c_char_p, _I, _I, C.c_char_p, _I, _I, _I, C.POINTER(_L), C.POINTER(_L), C.POINTER(_L)]),
     "ms_polygons_to_json": (_L, [_P, _P, _I, C.c_char_p, _I, _I, _P, _L]),
     "ms_polygons_to_json_batch": (_L, [_P, _P, _P, _I, C.POINTER(C.c_char_p), _I, _I, _I, _P, _L, _P]),
+    "ms_process_batch_multiclass_host": (_I, [_P, _P, _I, _I, _I, _P, _I, _P, _P, _P]),
     "ms_launch_count": (_L, [_P]),
     "ms_set_dp_epsilon": (_I, [_P, C.c_double]),
     "ms_dp_epsilon": (C.c_double, [_P]),
@@ -320,6 +321,37 @@ class Engine:
             clean = self.postprocess(raw, fg_value=int(k))
             out[int(k)] = (clean, self.mask2polygon(clean, threshold=int(k) - 1, orig_w=w, orig_h=h))
         return raw, out
+
+    def process_batch_multiclass(self, src_u16: np.ndarray, classes: Sequence[int], want_masks: bool = False):
+        """cfg4 through ONE C-ABI call (ms_process_batch_multiclass_host): K1 + UNet once, then K5 (FOREGROUND_VALUE = k) + K6 per
+        label on the device.  Returns {k: Polygons} or, with want_masks, (raw_mask, {k: (clean_mask, Polygons)})."""
+        src = np.ascontiguousarray(src_u16)
+        if src.ndim == 2:
+            src = src[None]
+        if src.dtype != np.uint16:
+            raise TypeError("src must be uint16")
+        b, h, w = src.shape
+        cls = np.asarray(list(classes), np.int32)
+        n = len(cls)
+        nh, nw = self.info.net_h, self.info.net_w
+        raw = np.empty((b, nh, nw), np.uint8) if want_masks else None
+        clean = np.empty((n, b, nh, nw), np.uint8) if want_masks else None
+        while True:
+            xy = [np.empty((self._cap_pts, 2), np.int32) for _ in range(n)]
+            cs = [np.empty(self._cap_cnt + 1, np.int32) for _ in range(n)]
+            ss = [np.empty(b + 1, np.int32) for _ in range(n)]
+            pgs = (ms_polygons * n)(*[ms_polygons(_ptr(xy[i]), self._cap_pts, _ptr(cs[i]), self._cap_cnt, _ptr(ss[i]), 0, 0) for i in range(n)])
+            rc = self._l.ms_process_batch_multiclass_host(self._h, _ptr(src), w, h, b, _ptr(cls), n, C.cast(pgs, C.c_void_p), _ptr(raw), _ptr(clean))
+            need_p, need_c = max(int(p.n_points) for p in pgs), max(int(p.n_contours) for p in pgs)
+            if rc == MS_ERR_CAPACITY and (need_p > self._cap_pts or need_c > self._cap_cnt):
+                self._cap_pts, self._cap_cnt = max(self._cap_pts, need_p + 16), max(self._cap_cnt, need_c + 16)
+                continue
+            self._check(rc)
+            break
+        polys = {int(k): Polygons(xy[i][:pgs[i].n_points], cs[i][:pgs[i].n_contours + 1], ss[i]) for i, k in enumerate(cls)}
+        if want_masks:
+            return raw, {int(k): (clean[i], polys[int(k)]) for i, k in enumerate(cls)}
+        return polys
 
     def process_raw_file(self, raw_path: str, w: int, h: int, out_dir: str) -> None:
         self._check(self._l.ms_process_raw_file(self._h, raw_path.encode(), w, h, out_dir.encode()))

@@ -346,10 +346,11 @@ void finish_init(ms_handle* h, const char* log_dir) {
 // the pinned header holds {n_contours, n_points, overflow, trace_errors} and the stream is idle.
 // `d_raw` != null: the class mask straight from the head; K5 (clean mask into `d_mask`) then runs as part of phase A.
 void run_m2p(ms_handle* h, const uint8_t* d_mask, int hgt, int w, int batch, int threshold, int orig_w, int orig_h, cudaStream_t st,
-             const uint8_t* d_raw = nullptr) {
+             const uint8_t* d_raw = nullptr, int fg_value = 0) {
     long long* hh = h->h_header.as<long long>();
+    if (fg_value <= 0) fg_value = h->fg_value;
     for (int attempt = 0; attempt < 3; ++attempt) {
-        if (d_raw) post_poly_phase_a(h->post, h->m2p, h->m2p.poly, d_raw, const_cast<uint8_t*>(d_mask), hgt, w, batch, h->fg_value, h->min_area_ratio, st);
+        if (d_raw) post_poly_phase_a(h->post, h->m2p, h->m2p.poly, d_raw, const_cast<uint8_t*>(d_mask), hgt, w, batch, fg_value, h->min_area_ratio, st);
         else m2p_phase_a(h->m2p, h->m2p.poly, d_mask, hgt, w, batch, threshold, st);
         m2p_phase_b(h->m2p, h->m2p.poly, hgt, w, batch, orig_w, orig_h, st);
         download_sync(h, hh, h->m2p.poly.header.p, 4 * sizeof(long long), st);
@@ -699,6 +700,55 @@ int ms_process_batch_host(ms_handle* h, const uint16_t* h_src, int w, int hgt, i
         if (h_norm_u8) MS_CUDA(cudaMemcpyAsync(h_norm_u8, h->d_norm.p, npx, cudaMemcpyDeviceToHost, h->stream));
         if (h_mask_u8) MS_CUDA(cudaMemcpyAsync(h_mask_u8, h->d_mask.p, npx, cudaMemcpyDeviceToHost, h->stream));
         copy_polygons_out(h, batch, out, h->stream);
+    });
+}
+
+// cfg4 (BASELINE.json configs[3]): per-class contours of a multi-class head in ONE call.  The reference runs the path for one
+// label (FOREGROUND_VALUE = 2, src/postprocess.cpp:5); here K1 and the UNet run once and, for every requested label k, K5 with
+// FOREGROUND_VALUE = k and K6 on (mask == k) -- all on the device, only polygons (and the masks, if asked for) come back.
+int ms_process_batch_multiclass_host(ms_handle* h, const uint16_t* h_src, int w, int hgt, int batch, const int32_t* classes, int n_classes,
+                                     ms_polygons* outs, uint8_t* h_raw_mask_u8, uint8_t* h_clean_masks_u8) {
+    if (!h) return MS_ERR_ARG;
+    return guarded(h, [&] {
+        MS_REQUIRE(h_src && w > 0 && hgt > 0 && classes && outs && n_classes >= 1 && n_classes <= 255, MS_ERR_ARG, "process_batch_multiclass: bad argument");
+        MS_REQUIRE(h->unet.loaded(), MS_ERR_STATE, "no weights loaded (handle was created without a weight blob)");
+        MS_REQUIRE(batch >= 1 && batch <= h->max_batch, MS_ERR_ARG, "batch exceeds max_batch of this handle");
+        for (int i = 0; i < n_classes; ++i) {
+            check_polys(&outs[i], batch);
+            MS_REQUIRE(classes[i] >= 1 && classes[i] <= 255, MS_ERR_ARG, "process_batch_multiclass: labels must be 1 .. 255");
+        }
+        cudaStream_t st = h->stream;
+        const size_t in_bytes = (size_t)w * hgt * 2 * batch;
+        const size_t npx = (size_t)h->net_w * h->net_h * batch;
+        h->d_src.reserve(in_bytes);
+        upload(h, h->d_src.p, h_src, in_bytes, st);
+        uint8_t* norm = h->d_norm.as<uint8_t>();
+        uint8_t* raw = h->d_mask_raw.as<uint8_t>();
+        uint8_t* mask = h->d_mask.as<uint8_t>();
+        preprocess_launch(h->pre, h->d_src.as<uint16_t>(), w, hgt, batch, h->net_w, h->net_h, norm, nullptr, st);
+        h->unet.forward(norm, batch, raw, nullptr, st);
+        if (h_raw_mask_u8) MS_CUDA(cudaMemcpyAsync(h_raw_mask_u8, raw, npx, cudaMemcpyDeviceToHost, st));
+        int rc_capacity = MS_OK;
+        std::string cap_msg;
+        for (int i = 0; i < n_classes; ++i) {
+            // mask_to_image + threshold(127) on a {0, k} mask <=> value > k - 1 (the fused form takes it from fg_value)
+            run_m2p(h, mask, h->net_h, h->net_w, batch, classes[i] - 1, w, hgt, st, raw, classes[i]);
+            h->header_pending = false;
+            if (h_clean_masks_u8) MS_CUDA(cudaMemcpyAsync(h_clean_masks_u8 + (size_t)i * npx, mask, npx, cudaMemcpyDeviceToHost, st));
+            const long long* hh = h->h_header.as<long long>();
+            outs[i].n_contours = hh[0];
+            outs[i].n_points = hh[1];
+            if (outs[i].cap_contours < hh[0] || outs[i].cap_points < hh[1]) {        // report every class's sizes before failing
+                rc_capacity = MS_ERR_CAPACITY;
+                cap_msg = "polygon buffers too small for label " + std::to_string(classes[i]) + ": need " + std::to_string(hh[0]) + " contours, " +
+                          std::to_string(hh[1]) + " points";
+                MS_CUDA(cudaStreamSynchronize(st));
+                continue;
+            }
+            copy_polygons_out(h, batch, &outs[i], st);      // synchronises: the clean mask buffer is reused by the next label
+        }
+        MS_CUDA(cudaStreamSynchronize(st));
+        MS_REQUIRE(rc_capacity == MS_OK, MS_ERR_CAPACITY, cap_msg);
     });
 }
 
