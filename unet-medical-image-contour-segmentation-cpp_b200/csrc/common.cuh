@@ -188,6 +188,22 @@ struct FusedWs {
     DevBuf tab;           // int32 [batch][3][16 * words per slice]: labels, areas, run head positions
 };
 
+// Foreground label per slice of a (possibly virtual) batch.  The reference cleans ONE label (FOREGROUND_VALUE, src/postprocess.cpp:5);
+// the multi-label call (cfg4) runs K5 / K6 once over n_labels x batch VIRTUAL slices: virtual slice s reads class mask s % in_mod
+// and keeps label v[s / in_mod].  single(): the plain batch.
+struct FgSpec {
+    int in_mod;
+    unsigned char v[16];
+    __host__ __device__ int fg(int slice) const { return v[slice / in_mod]; }
+    __host__ __device__ int src(int slice) const { return slice % in_mod; }
+    static FgSpec single(int fg_value, int batch) {
+        FgSpec f{};
+        f.in_mod = batch > 0 ? batch : 1;
+        f.v[0] = (unsigned char)fg_value;
+        return f;
+    }
+};
+
 // K5 postprocess.cu
 struct PostprocessWs {
     CclWs ccl;
@@ -195,7 +211,7 @@ struct PostprocessWs {
     FusedWs fused;
 };
 void postprocess_launch(PostprocessWs& ws, const uint8_t* d_in, uint8_t* d_out, int h, int w, int batch, int fg_value,
-                        float min_area_ratio, cudaStream_t st);
+                        float min_area_ratio, cudaStream_t st, const FgSpec* multi = nullptr);
 
 // K6 mask2polygon.cu
 struct PolyDev {              // device-resident polygon set + counters
@@ -254,9 +270,9 @@ long long* fused_debug_buffer(bool create);   // [32] clock64 stamps of slice 0'
 // do_post: d_in = class mask, d_out = clean mask {0, fg} (postprocess_mask);  do_poly: contours of the result (do_post) or
 // of d_in > thr (otherwise) staged in `poly` for m2p_phase_b.  `poly` may be null when !do_poly.
 void slice_fused_launch(FusedWs& fws, M2pWs* ws, PolyDev* poly, const uint8_t* d_in, uint8_t* d_out, int h, int w, int batch, bool do_post,
-                        bool do_poly, int fg_value, float min_area_ratio, int thr, cudaStream_t st);
+                        bool do_poly, int fg_value, float min_area_ratio, int thr, cudaStream_t st, const FgSpec* multi = nullptr);
 // K5 + phase A of K6 on the class mask: the fused kernel when the slice fits, else postprocess_launch + m2p_phase_a
 void post_poly_phase_a(PostprocessWs& pws, M2pWs& ws, PolyDev& poly, const uint8_t* d_raw, uint8_t* d_clean, int h, int w, int batch,
-                       int fg_value, float min_area_ratio, cudaStream_t st);
+                       int fg_value, float min_area_ratio, cudaStream_t st, const FgSpec* multi = nullptr);
 
 }  // namespace ms

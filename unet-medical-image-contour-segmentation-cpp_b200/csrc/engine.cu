@@ -118,6 +118,7 @@ struct ms_handle {
     // volume / file-list entry points give every GPU a contiguous block and one host thread (src/main.cpp:148-164).
     std::vector<int> devices;
     std::vector<ms_handle*> peers;
+    std::vector<int32_t> mc_slice, mc_cstart, mc_xy;   // ms_process_batch_multiclass_host: the label-major polygon set before the split
     std::string cfg_text;            // the JSON config this handle was created from (peers are created from it)
     bool quiet_console = false;      // peers: console lines are collected per job and printed in job order by the owner
     // bytes this handle moved over PCIe with its own copies (bench.py: e2e.h2d/d2h_bytes_per_step are read from here)
@@ -346,11 +347,10 @@ void finish_init(ms_handle* h, const char* log_dir) {
 // the pinned header holds {n_contours, n_points, overflow, trace_errors} and the stream is idle.
 // `d_raw` != null: the class mask straight from the head; K5 (clean mask into `d_mask`) then runs as part of phase A.
 void run_m2p(ms_handle* h, const uint8_t* d_mask, int hgt, int w, int batch, int threshold, int orig_w, int orig_h, cudaStream_t st,
-             const uint8_t* d_raw = nullptr, int fg_value = 0) {
+             const uint8_t* d_raw = nullptr, const FgSpec* multi = nullptr) {
     long long* hh = h->h_header.as<long long>();
-    if (fg_value <= 0) fg_value = h->fg_value;
     for (int attempt = 0; attempt < 3; ++attempt) {
-        if (d_raw) post_poly_phase_a(h->post, h->m2p, h->m2p.poly, d_raw, const_cast<uint8_t*>(d_mask), hgt, w, batch, fg_value, h->min_area_ratio, st);
+        if (d_raw) post_poly_phase_a(h->post, h->m2p, h->m2p.poly, d_raw, const_cast<uint8_t*>(d_mask), hgt, w, batch, h->fg_value, h->min_area_ratio, st, multi);
         else m2p_phase_a(h->m2p, h->m2p.poly, d_mask, hgt, w, batch, threshold, st);
         m2p_phase_b(h->m2p, h->m2p.poly, hgt, w, batch, orig_w, orig_h, st);
         download_sync(h, hh, h->m2p.poly.header.p, 4 * sizeof(long long), st);
@@ -704,23 +704,30 @@ int ms_process_batch_host(ms_handle* h, const uint16_t* h_src, int w, int hgt, i
 }
 
 // cfg4 (BASELINE.json configs[3]): per-class contours of a multi-class head in ONE call.  The reference runs the path for one
-// label (FOREGROUND_VALUE = 2, src/postprocess.cpp:5); here K1 and the UNet run once and, for every requested label k, K5 with
-// FOREGROUND_VALUE = k and K6 on (mask == k) -- all on the device, only polygons (and the masks, if asked for) come back.
+// label (FOREGROUND_VALUE = 2, src/postprocess.cpp:5); here K1 and the UNet run once and K5 + K6 run ONCE over
+// n_labels x batch virtual slices (FgSpec: virtual slice s cleans label classes[s / batch] of class mask s % batch), so the
+// labels share every launch; the polygon set comes back in one piece and is split per label on the host.
 int ms_process_batch_multiclass_host(ms_handle* h, const uint16_t* h_src, int w, int hgt, int batch, const int32_t* classes, int n_classes,
                                      ms_polygons* outs, uint8_t* h_raw_mask_u8, uint8_t* h_clean_masks_u8) {
     if (!h) return MS_ERR_ARG;
     return guarded(h, [&] {
-        MS_REQUIRE(h_src && w > 0 && hgt > 0 && classes && outs && n_classes >= 1 && n_classes <= 255, MS_ERR_ARG, "process_batch_multiclass: bad argument");
+        MS_REQUIRE(h_src && w > 0 && hgt > 0 && classes && outs && n_classes >= 1 && n_classes <= 16, MS_ERR_ARG,
+                   "process_batch_multiclass: bad argument (1 .. 16 labels)");
         MS_REQUIRE(h->unet.loaded(), MS_ERR_STATE, "no weights loaded (handle was created without a weight blob)");
         MS_REQUIRE(batch >= 1 && batch <= h->max_batch, MS_ERR_ARG, "batch exceeds max_batch of this handle");
+        FgSpec fgs{};
+        fgs.in_mod = batch;
         for (int i = 0; i < n_classes; ++i) {
             check_polys(&outs[i], batch);
             MS_REQUIRE(classes[i] >= 1 && classes[i] <= 255, MS_ERR_ARG, "process_batch_multiclass: labels must be 1 .. 255");
+            fgs.v[i] = (unsigned char)classes[i];
         }
         cudaStream_t st = h->stream;
+        const int vbatch = batch * n_classes;
         const size_t in_bytes = (size_t)w * hgt * 2 * batch;
         const size_t npx = (size_t)h->net_w * h->net_h * batch;
         h->d_src.reserve(in_bytes);
+        h->d_mask.reserve(npx * n_classes);
         upload(h, h->d_src.p, h_src, in_bytes, st);
         uint8_t* norm = h->d_norm.as<uint8_t>();
         uint8_t* raw = h->d_mask_raw.as<uint8_t>();
@@ -728,26 +735,34 @@ int ms_process_batch_multiclass_host(ms_handle* h, const uint16_t* h_src, int w,
         preprocess_launch(h->pre, h->d_src.as<uint16_t>(), w, hgt, batch, h->net_w, h->net_h, norm, nullptr, st);
         h->unet.forward(norm, batch, raw, nullptr, st);
         if (h_raw_mask_u8) MS_CUDA(cudaMemcpyAsync(h_raw_mask_u8, raw, npx, cudaMemcpyDeviceToHost, st));
+        run_m2p(h, mask, h->net_h, h->net_w, vbatch, 0, w, hgt, st, raw, &fgs);
+        h->header_pending = false;
+        if (h_clean_masks_u8) MS_CUDA(cudaMemcpyAsync(h_clean_masks_u8, mask, npx * n_classes, cudaMemcpyDeviceToHost, st));
+        // the whole set (virtual slices in label-major order), then one slice-range per label
+        const long long* hh = h->h_header.as<long long>();
+        const int64_t nc = hh[0], np = hh[1];
+        h->mc_slice.resize((size_t)vbatch + 1);
+        h->mc_cstart.resize((size_t)nc + 1);
+        h->mc_xy.resize((size_t)np * 2);
+        ms_polygons all{h->mc_xy.data(), np, h->mc_cstart.data(), nc, h->mc_slice.data(), 0, 0};
+        copy_polygons_out(h, vbatch, &all, st);
         int rc_capacity = MS_OK;
         std::string cap_msg;
         for (int i = 0; i < n_classes; ++i) {
-            // mask_to_image + threshold(127) on a {0, k} mask <=> value > k - 1 (the fused form takes it from fg_value)
-            run_m2p(h, mask, h->net_h, h->net_w, batch, classes[i] - 1, w, hgt, st, raw, classes[i]);
-            h->header_pending = false;
-            if (h_clean_masks_u8) MS_CUDA(cudaMemcpyAsync(h_clean_masks_u8 + (size_t)i * npx, mask, npx, cudaMemcpyDeviceToHost, st));
-            const long long* hh = h->h_header.as<long long>();
-            outs[i].n_contours = hh[0];
-            outs[i].n_points = hh[1];
-            if (outs[i].cap_contours < hh[0] || outs[i].cap_points < hh[1]) {        // report every class's sizes before failing
+            const int32_t c0 = h->mc_slice[(size_t)i * batch], c1 = h->mc_slice[(size_t)(i + 1) * batch];
+            const int32_t p0 = h->mc_cstart[c0], p1 = h->mc_cstart[c1];
+            outs[i].n_contours = c1 - c0;
+            outs[i].n_points = p1 - p0;
+            if (outs[i].cap_contours < c1 - c0 || outs[i].cap_points < p1 - p0) {     // report every label's sizes before failing
                 rc_capacity = MS_ERR_CAPACITY;
-                cap_msg = "polygon buffers too small for label " + std::to_string(classes[i]) + ": need " + std::to_string(hh[0]) + " contours, " +
-                          std::to_string(hh[1]) + " points";
-                MS_CUDA(cudaStreamSynchronize(st));
+                cap_msg = "polygon buffers too small for label " + std::to_string(classes[i]) + ": need " + std::to_string(c1 - c0) +
+                          " contours, " + std::to_string(p1 - p0) + " points";
                 continue;
             }
-            copy_polygons_out(h, batch, &outs[i], st);      // synchronises: the clean mask buffer is reused by the next label
+            for (int b2 = 0; b2 <= batch; ++b2) outs[i].slice_start[b2] = h->mc_slice[(size_t)i * batch + b2] - c0;
+            for (int32_t c = c0; c <= c1; ++c) outs[i].contour_start[c - c0] = h->mc_cstart[c] - p0;
+            if (p1 > p0) std::memcpy(outs[i].xy, h->mc_xy.data() + 2 * (size_t)p0, (size_t)(p1 - p0) * 8);
         }
-        MS_CUDA(cudaStreamSynchronize(st));
         MS_REQUIRE(rc_capacity == MS_OK, MS_ERR_CAPACITY, cap_msg);
     });
 }

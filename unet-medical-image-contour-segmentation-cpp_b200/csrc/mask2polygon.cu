@@ -1059,7 +1059,7 @@ bool slice_fused_supported(int h, int w) {
 }
 
 void slice_fused_launch(FusedWs& fws, M2pWs* ws, PolyDev* P, const uint8_t* d_in, uint8_t* d_out, int h, int w, int batch, bool do_post,
-                        bool do_poly, int fg_value, float min_area_ratio, int thr, cudaStream_t st) {
+                        bool do_poly, int fg_value, float min_area_ratio, int thr, cudaStream_t st, const FgSpec* multi) {
     MS_REQUIRE(h > 0 && w > 0 && batch > 0 && batch <= 65535, MS_ERR_ARG, "slice kernel: bad shape");
     const fused::Plan pl = fused::plan(h, w);
     MS_REQUIRE(pl.ok, MS_ERR_INTERNAL, "slice kernel: slice does not fit in shared memory");
@@ -1068,7 +1068,8 @@ void slice_fused_launch(FusedWs& fws, M2pWs* ws, PolyDev* P, const uint8_t* d_in
     a.in = d_in; a.out = d_out;
     a.H = h; a.W = w; a.wpitch = cdiv(w, 32); a.batch = batch;
     a.do_post = do_post; a.do_poly = do_poly;
-    a.fg_value = fg_value; a.thr = thr;
+    a.fg = multi ? *multi : FgSpec::single(fg_value, batch);
+    a.thr = thr;
     // src/postprocess.cpp:30,66: static_cast<int>(w * h * MIN_AREA_RATIO) -- int product, float multiply, truncate
     a.min_area = static_cast<int>(static_cast<float>(w * h) * min_area_ratio);
     a.off_z = pl.off_z; a.off_y = pl.off_y; a.off_roff = pl.off_roff; a.off_tab = pl.off_tab;
@@ -1102,15 +1103,16 @@ void slice_fused_launch(FusedWs& fws, M2pWs* ws, PolyDev* P, const uint8_t* d_in
 }
 
 void post_poly_phase_a(PostprocessWs& pws, M2pWs& ws, PolyDev& P, const uint8_t* d_raw, uint8_t* d_clean, int h, int w, int batch,
-                       int fg_value, float min_area_ratio, cudaStream_t st) {
+                       int fg_value, float min_area_ratio, cudaStream_t st, const FgSpec* multi) {
     if (slice_fused_supported(h, w)) {
-        slice_fused_launch(ws.fused, &ws, &P, d_raw, d_clean, h, w, batch, true, true, fg_value, min_area_ratio, 0, st);
+        slice_fused_launch(ws.fused, &ws, &P, d_raw, d_clean, h, w, batch, true, true, fg_value, min_area_ratio, 0, st, multi);
         return;
     }
-    postprocess_launch(pws, d_raw, d_clean, h, w, batch, fg_value, min_area_ratio, st);
+    postprocess_launch(pws, d_raw, d_clean, h, w, batch, fg_value, min_area_ratio, st, multi);
     // mask_to_image + threshold(127) (src/process.cpp:234, src/mask2polygon.cpp:31): after postprocess the mask is {0, fg};
     // LUT(fg) > 127 <=> value == fg <=> value > fg - 1
-    m2p_phase_a(ws, P, d_clean, h, w, batch, fg_value - 1, st);
+    // (several labels: every clean mask is {0, its label}, so "value > 0" is the same test for all of them)
+    m2p_phase_a(ws, P, d_clean, h, w, batch, multi ? 0 : fg_value - 1, st);
 }
 
 void m2p_phase_a(M2pWs& ws, PolyDev& P, const uint8_t* d_mask, int h, int w, int batch, int threshold, cudaStream_t st) {

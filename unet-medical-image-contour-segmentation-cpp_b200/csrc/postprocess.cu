@@ -21,12 +21,12 @@ namespace {
 
 // mask -> bits of (mask == fg), one word per warp; also initialises the heads of the INVERSE image's runs
 // grid = (ceil(W / 256), H, batch), block = 256 (8 words)
-__global__ void __launch_bounds__(256) fg_bits_kernel(const uint8_t* __restrict__ mask, int H, int W, int wpitch, int fg_value,
+__global__ void __launch_bounds__(256) fg_bits_kernel(const uint8_t* __restrict__ mask, int H, int W, int wpitch, const FgSpec fgs,
                                                        uint32_t* __restrict__ bits, int* __restrict__ L_all, int* __restrict__ area_all,
                                                        uint8_t* __restrict__ flag_all) {
     const int x = blockIdx.x * 256 + threadIdx.x, y = blockIdx.y;
     const bool in = x < W;
-    const bool fg = in && mask[((size_t)blockIdx.z * H + y) * W + x] == fg_value;
+    const bool fg = in && mask[((size_t)fgs.src(blockIdx.z) * H + y) * W + x] == fgs.fg(blockIdx.z);
     const unsigned b = __ballot_sync(0xFFFFFFFFu, fg);
     if ((threadIdx.x & 31) == 0 && (x >> 5) < wpitch) {
         bits[((size_t)blockIdx.z * H + y) * wpitch + (x >> 5)] = b;
@@ -104,9 +104,10 @@ __global__ void __launch_bounds__(ccl::kThreads) open_kernel(const uint32_t* __r
 
 // kept = runs of opened components with area >= min_area, expanded to the u8 output.  One thread per word (32 bytes out).
 __global__ void __launch_bounds__(ccl::kThreads) keep_kernel(const uint32_t* __restrict__ opened, int H, int W, int wpitch, int min_area,
-                                                              int fg_value, const int* __restrict__ L_all, const int* __restrict__ area_all,
+                                                              const FgSpec fgs, const int* __restrict__ L_all, const int* __restrict__ area_all,
                                                               uint8_t* __restrict__ out) {
     MS_CCL_WORD_COORDS();
+    const int fg_value = fgs.fg(sl);
     const size_t slice = (size_t)sl * H * W;
     const uint32_t o = opened[((size_t)sl * H + y) * wpitch + wx];
     uint32_t keep = 0;
@@ -136,11 +137,12 @@ __global__ void __launch_bounds__(ccl::kThreads) keep_kernel(const uint32_t* __r
 }  // namespace
 
 void postprocess_launch(PostprocessWs& ws, const uint8_t* d_in, uint8_t* d_out, int h, int w, int batch, int fg_value,
-                        float min_area_ratio, cudaStream_t st) {
+                        float min_area_ratio, cudaStream_t st, const FgSpec* multi) {
+    const FgSpec fgs = multi ? *multi : FgSpec::single(fg_value, batch);
     MS_REQUIRE(h > 0 && w > 0 && batch > 0 && h <= 65535 && batch <= 65535, MS_ERR_ARG, "postprocess: bad shape");
     MS_REQUIRE((int64_t)h * w < ((int64_t)1 << 31), MS_ERR_ARG, "postprocess: slice too large");
     if (slice_fused_supported(h, w)) {     // one CTA per slice, everything on chip (slice_fused.cuh)
-        slice_fused_launch(ws.fused, nullptr, nullptr, d_in, d_out, h, w, batch, true, false, fg_value, min_area_ratio, 0, st);
+        slice_fused_launch(ws.fused, nullptr, nullptr, d_in, d_out, h, w, batch, true, false, fg_value, min_area_ratio, 0, st, multi);
         return;
     }
     const size_t n = (size_t)h * w, nb = n * batch;
@@ -160,7 +162,7 @@ void postprocess_launch(PostprocessWs& ws, const uint8_t* d_in, uint8_t* d_out, 
     uint32_t* Bfill = ws.bin_b.as<uint32_t>();
     const dim3 gw = ccl::grid_for(h, wpitch, batch);
 
-    fg_bits_kernel<<<dim3(cdiv(w, 256), h, batch), 256, 0, st>>>(d_in, h, w, wpitch, fg_value, Bfg, L, A, F);
+    fg_bits_kernel<<<dim3(cdiv(w, 256), h, batch), 256, 0, st>>>(d_in, h, w, wpitch, fgs, Bfg, L, A, F);
     MS_LAUNCH_CHECK();
     ccl::merge_kernel<8, true><<<gw, ccl::kThreads, 0, st>>>(Bfg, h, w, wpitch, L);
     MS_LAUNCH_CHECK();
@@ -175,7 +177,7 @@ void postprocess_launch(PostprocessWs& ws, const uint8_t* d_in, uint8_t* d_out, 
     MS_LAUNCH_CHECK();
     ccl::resolve_kernel<false><<<gw, ccl::kThreads, 0, st>>>(Bopen, h, w, wpitch, L, A, nullptr);
     MS_LAUNCH_CHECK();
-    keep_kernel<<<gw, ccl::kThreads, 0, st>>>(Bopen, h, w, wpitch, min_area, fg_value, L, A, d_out);
+    keep_kernel<<<gw, ccl::kThreads, 0, st>>>(Bopen, h, w, wpitch, min_area, fgs, L, A, d_out);
     MS_LAUNCH_CHECK();
 }
 

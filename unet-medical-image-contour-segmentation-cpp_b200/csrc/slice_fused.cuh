@@ -33,7 +33,8 @@ struct Params {
     uint8_t* out;            // [batch][H][W] clean mask {0, fg} (do_post; may be null)
     int H, W, wpitch, batch;
     int do_post, do_poly;
-    int fg_value, min_area, thr;
+    FgSpec fg;               // do_post: label kept per (virtual) slice and the class mask it reads
+    int min_area, thr;
     // shared-memory layout (word offsets into the dynamic array), computed on the host by plan()
     int off_z, off_y, off_roff, off_tab, rcap, cap_border;
     // global fallback run tables: [batch][3][g_runs]  (labels, areas, run head positions)
@@ -470,12 +471,13 @@ __global__ void __launch_bounds__(kT, 1) slice_kernel(const Params P) {
     uint32_t* roff = smem + P.off_roff;
     int* s_tab = reinterpret_cast<int*>(smem + P.off_tab);
     int* g_tab = P.g_tab + (size_t)b * 3 * P.g_runs;
-    const uint8_t* in = P.in + (size_t)b * H * W;
+    const uint8_t* in = P.in + (size_t)(P.do_post ? P.fg.src(b) : b) * H * W;
+    const int fg_value = P.fg.fg(b);
     MS_FUSED_MARK(0);
 
     // ---------------------------------------------------------------- mask -> bits (X)
     {
-        const uint32_t key = (uint32_t)(P.do_post ? P.fg_value : P.thr) & 0xFFu, key4 = key * 0x01010101u;
+        const uint32_t key = (uint32_t)(P.do_post ? fg_value : P.thr) & 0xFFu, key4 = key * 0x01010101u;
         const bool eq = P.do_post != 0;       // postprocess: mask == FG (postprocess.cpp:18);  mask2polygon: mask > thr (mask2polygon.cpp:31)
         if ((W & 31) == 0 && (reinterpret_cast<uintptr_t>(in) & 15) == 0) {
             const int n16 = H * W / 16;     // 16 pixels per thread and step; lane pairs build one word
@@ -550,7 +552,7 @@ __global__ void __launch_bounds__(kT, 1) slice_kernel(const Params P) {
         MS_FUSED_MARK(5);
         const int min_area = P.do_post ? P.min_area : 0;
         uint8_t* out = (P.do_post && P.out) ? P.out + (size_t)b * H * W : nullptr;
-        const uint32_t v = (uint32_t)P.fg_value;
+        const uint32_t v = (uint32_t)fg_value;
         for (int w = tid; w < nw; w += kT) {
             const uint32_t o = X[w];
             uint32_t keep = 0, roots = 0;
@@ -582,7 +584,7 @@ __global__ void __launch_bounds__(kT, 1) slice_kernel(const Params P) {
                     reinterpret_cast<uint4*>(dst)[0] = make_uint4(wds[0], wds[1], wds[2], wds[3]);
                     reinterpret_cast<uint4*>(dst)[1] = make_uint4(wds[4], wds[5], wds[6], wds[7]);
                 } else {
-                    for (int j = 0; j < 32 && wx * 32 + j < W; ++j) dst[j] = (keep >> j) & 1u ? (uint8_t)P.fg_value : (uint8_t)0;
+                    for (int j = 0; j < 32 && wx * 32 + j < W; ++j) dst[j] = (keep >> j) & 1u ? (uint8_t)fg_value : (uint8_t)0;
                 }
             }
         }
